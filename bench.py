@@ -1,0 +1,518 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the sparse-A x dense-B hot path on B200 (one JSON line on stdout).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5] [--impl b200|reference]
+
+Headline workload (BASELINE.json configs[1], "C2"): libxsmm_spmdm, bf16 inputs / fp32 accumulate,
+M = K = N = 4096, A 99 % zeros, beta = 0.  One STEP = one whole multiply the way samples/spmdm/spmdm.c:88-111
+performs it: all createSparseSlice blocks (dense A -> CSR slices), then all compute blocks (C = A.B).
+metric = effective GFLOP/s = 2.nnz.N / t  (SURVEY.md section 8d).
+
+  value     inputs resident in HBM, stream entries (libxsmm_spmdm_exec_stream), CUDA events on the launch
+            stream, K steps back to back.  Every step uses a different copy of A/B/C out of a ring larger
+            than L2, so nothing is served from cache ("inputs larger than L2").
+  e2e       the same multiply through the host-pointer C-ABI call (libxsmm_spmdm_exec_host): page-locked host
+            A, B in, C out, copies inside the timed region.
+  roofline  the dominant kernel (spmdm compute): algorithmic bytes / its mean duration from CUDA events
+            recorded around every launch inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, OpenMP over block ids like the sample) on this host.
+
+Multi-GPU (N > 1, launched by torchrun, one rank per GPU): the path shards by N-column panels with A
+replicated and NO collective on the data path.  Scaling is WEAK: every rank owns a
+4096-column panel, i.e. the global problem is M = K = 4096, N = 4096.N_gpus.  torch.distributed (NCCL) is
+used for the barriers and the max-over-ranks of the device time only.
+
+--impl reference times the reference CPU implementation on the same workload (rank 0 only).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: kind, parameters
+    "c1": dict(kind="spmdm", M=2048, N=2048, K=2048, density=0.10, dtype="f32", trans="NNN", beta=0.0,
+               desc="spmdm fp32 M=N=K=2048, A 90% zeros, N/N/N, beta=0"),
+    "c2": dict(kind="spmdm", M=4096, N=4096, K=4096, density=0.01, dtype="bf16", trans="NNN", beta=0,
+               desc="spmdm bf16-in/fp32-acc M=K=N=4096, A 99% zeros, N/N/N, beta=0"),
+    "c3": dict(kind="fsspmdm", M=150, K=64, density=0.30, n_unique=8, dtype="f64", N=1 << 20, beta=0.0,
+               desc="dfsspmdm fp64 150x64 30% dense (8 distinct values), N=2^20 columns, beta=0"),
+    "c4": dict(kind="spmdm", M=2048, N=2048, K=2048, density=0.50, dtype="f32", trans="NNN", beta=0.0,
+               desc="spmdm fp32 M=N=K=2048, A 50% zeros, N/N/N, beta=0"),
+    "c4-tnt": dict(kind="spmdm", M=2048, N=2048, K=2048, density=0.50, dtype="f32", trans="TNT", beta=0.0,
+                   desc="spmdm fp32 2048^3 50%, transA/transC (weight update)"),
+    "c4-ntn": dict(kind="spmdm", M=2048, N=2048, K=2048, density=0.50, dtype="f32", trans="NTN", beta=0.0,
+                   desc="spmdm fp32 2048^3 50%, transB (backprop)"),
+    "c5": dict(kind="fsspmdm", M=150, K=64, density=0.30, n_unique=8, dtype="f32", N=1 << 24, beta=0.0,
+               desc="sfsspmdm fp32 150x64 30% dense, N=2^24 columns, beta=0"),
+}
+L2_BYTES = 126 << 20
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons of one GPU, sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 2:]          # upper half = samples taken under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload construction
+# ------------------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def spmdm_host_inputs(xs, wl, seed=1):
+    t = wl["trans"]
+    return xs.workloads.spmdm_inputs(wl["M"], wl["N"], wl["K"], wl["density"], dtype=wl["dtype"], seed=seed,
+                                     transa=t[0], transb=t[1], transc=t[2])
+
+
+def spmdm_bytes(wl, geo, nnz):
+    sA = sB = 2 if wl["dtype"] == "bf16" else 4
+    M, N, K = wl["M"], wl["N"], wl["K"]
+    ptr = 2 * geo["mb"] * geo["kb"] * (geo["bm"] + 1)
+    beta_nz = 1 if float(wl["beta"]) != 0.0 else 0
+    compute = sB * K * N + 4 * M * N * (1 + beta_nz) + 6 * nnz + ptr
+    slicing = sA * M * K + 6 * nnz + ptr
+    return slicing, compute
+
+
+def fs_bytes(wl, N):
+    s = 8 if wl["dtype"] == "f64" else 4
+    return s * N * (wl["K"] + wl["M"] * (2 if float(wl["beta"]) == 1.0 else 1))
+
+
+def fs_operator(xs, wl):
+    return xs.workloads.fsspmdm_operator(wl["M"], wl["K"], wl["density"], wl["n_unique"],
+                                         np.float64 if wl["dtype"] == "f64" else np.float32, seed=1)
+
+
+def fill_device_random(xs, dbuf, nbytes, dtype, seed):
+    """fills a device buffer with uniform [0,1) values by uploading one 64 MiB host chunk repeatedly."""
+    chunk_elems = min(nbytes, 64 << 20) // np.dtype(dtype).itemsize
+    host = np.random.default_rng(seed).random(chunk_elems, np.float32).astype(dtype)
+    off = 0
+    while off < nbytes:
+        n = min(host.nbytes, nbytes - off)
+        xs.load().libxsmm_b200_memcpy_h2d(dbuf.ptr + off, host.ctypes.data, n)
+        off += n
+    xs.check()
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_spmdm_gpu(xs, wl, steps, warmup, want_e2e=True):
+    bf16 = wl["dtype"] == "bf16"
+    dt = xs.LIBXSMM_SPMDM_DATATYPE_BFLOAT16 if bf16 else xs.LIBXSMM_SPMDM_DATATYPE_F32
+    ta, tb, tc = wl["trans"]
+    M, N, K = wl["M"], wl["N"], wl["K"]
+    A, B, C0 = spmdm_host_inputs(xs, wl)
+    nnz = int(np.count_nonzero(A))
+    p = xs.Spmdm(M, N, K, 1)
+    geo = p.geometry
+    b_slice, b_compute = spmdm_bytes(wl, geo, nnz)
+    set_bytes = A.nbytes + B.nbytes + C0.nbytes
+    nsets = max(2, int(np.ceil(2.5 * L2_BYTES / set_bytes)))       # ring > 2.5 x L2: a set is evicted before reuse
+    ring = []
+    for _ in range(nsets):
+        ring.append((xs.DeviceBuffer.from_numpy(A), xs.DeviceBuffer.from_numpy(B), xs.DeviceBuffer(C0.nbytes)))
+    st = xs.Stream()
+    ev = [[xs.Event() for _ in range(3)] for _ in range(steps)]
+    t_first, t_last = xs.Event(), xs.Event()
+
+    def step(i, events=None):
+        dA, dB, dC = ring[i % nsets]
+        if events:
+            events[0].record(st)
+        p.create_slices(dA, ta, bf16, st)
+        if events:
+            events[1].record(st)
+        p.compute(dB, dC, tb, tc, wl["beta"], bf16, st)
+        if events:
+            events[2].record(st)
+
+    for i in range(warmup):
+        step(i)
+    st.synchronize()
+    xs.check()
+    yield "ready"                                  # caller barriers here
+    l0 = xs.launch_count()
+    t_first.record(st)
+    for i in range(steps):
+        step(warmup + i, ev[i])
+    t_last.record(st)
+    st.synchronize()
+    launches = xs.launch_count() - l0
+    total_ms = t_first.elapsed_ms(t_last)
+    slice_ms = float(np.mean([e[0].elapsed_ms(e[1]) for e in ev]))
+    comp_ms = float(np.mean([e[1].elapsed_ms(e[2]) for e in ev]))
+    xs.check()
+    res = dict(total_ms=total_ms, launches=launches, nnz=nnz, flops=2.0 * nnz * N, geo=geo,
+               kernel_ms=comp_ms, kernel_bytes=b_compute, kernel_name="spmdm_compute_kernel",
+               parts={"slice_ms": slice_ms, "compute_ms": comp_ms, "slice_bytes": b_slice, "compute_bytes": b_compute},
+               step_bytes=b_slice + b_compute, ring_sets=nsets, ring_bytes=nsets * set_bytes)
+    yield res
+    # ---- e2e: host pointers through the C ABI -------------------------------------------------------
+    if want_e2e:
+        hA = xs.HostBuffer(A.shape, A.dtype); hA.array[...] = A
+        hB = xs.HostBuffer(B.shape, B.dtype); hB.array[...] = B
+        hC = xs.HostBuffer(C0.shape, np.float32); hC.array[...] = C0
+        for _ in range(max(1, min(warmup, 3))):
+            xs.libxsmm_spmdm_exec_host(p.handle, p.slices, dt, ta, tb, tc, hA, hB, wl["beta"], hC)
+        xs.check()
+        yield "ready-e2e"
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            xs.libxsmm_spmdm_exec_host(p.handle, p.slices, dt, ta, tb, tc, hA, hB, wl["beta"], hC)
+        t1 = time.perf_counter()
+        xs.check()
+        h2d = A.nbytes + B.nbytes + (C0.nbytes if float(wl["beta"]) != 0.0 else 0)
+        yield dict(e2e_ms=(t1 - t0) * 1e3, h2d=h2d, d2h=C0.nbytes, checksum=float(hC.array[::97, ::89].sum()))
+        for h in (hA, hB, hC):
+            h.free()
+    for bufs in ring:
+        for b in bufs:
+            b.free()
+    p.destroy()
+
+
+def run_fs_gpu(xs, wl, steps, warmup, world, want_e2e=True):
+    """C3 / C5: total N columns split into contiguous panels of N / world per rank (A replicated)."""
+    dbl = wl["dtype"] == "f64"
+    dtype = np.float64 if dbl else np.float32
+    a = fs_operator(xs, wl)
+    nnz = int(np.count_nonzero(a))
+    N = wl["N"] // world
+    op = xs.Fsspmdm(a, N, beta=wl["beta"])
+    esz = 8 if dbl else 4
+    bB, bC = wl["K"] * N * esz, wl["M"] * N * esz
+    nsets = max(1, int(np.ceil(2.5 * L2_BYTES / (bB + bC)))) if (bB + bC) < 3 * L2_BYTES else 1
+    ring = []
+    for s in range(nsets):
+        dB, dC = xs.DeviceBuffer(bB), xs.DeviceBuffer(bC)
+        fill_device_random(xs, dB, bB, dtype, 11 + s)
+        dC.fill(0)
+        ring.append((dB, dC))
+    st = xs.Stream()
+    t_first, t_last = xs.Event(), xs.Event()
+    for i in range(warmup):
+        op.execute_stream(*ring[i % nsets], st)
+    st.synchronize(); xs.check()
+    yield "ready"
+    l0 = xs.launch_count()
+    t_first.record(st)
+    for i in range(steps):
+        op.execute_stream(*ring[(warmup + i) % nsets], st)
+    t_last.record(st)
+    st.synchronize()
+    launches = xs.launch_count() - l0
+    total_ms = t_first.elapsed_ms(t_last)
+    xs.check()
+    yield dict(total_ms=total_ms, launches=launches, nnz=nnz, flops=2.0 * nnz * N, geo=dict(sparse=op.is_sparse, baked=op.is_baked),
+               kernel_ms=total_ms / steps, kernel_bytes=fs_bytes(wl, N), kernel_name="fs_baked" if op.is_baked else "fs_generic_kernel",
+               parts={}, step_bytes=fs_bytes(wl, N), ring_sets=nsets, ring_bytes=nsets * (bB + bC))
+    if want_e2e:
+        Ne = min(N, 1 << 20)                      # host panel of at most 2^20 columns per step (537 MB + 1.26 GB for fp64)
+        ope = xs.Fsspmdm(a, Ne, beta=wl["beta"]) if Ne != N else op
+        hB = xs.HostBuffer((wl["K"], Ne), dtype); hB.array[...] = np.random.default_rng(5).random((wl["K"], Ne), np.float32)
+        hC = xs.HostBuffer((wl["M"], Ne), dtype); hC.array[...] = 0
+        ope.execute(hB, hC)
+        xs.check()
+        yield "ready-e2e"
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ope.execute(hB, hC)
+        t1 = time.perf_counter()
+        xs.check()
+        yield dict(e2e_ms=(t1 - t0) * 1e3, h2d=hB.nbytes + (hC.nbytes if float(wl["beta"]) == 1.0 else 0), d2h=hC.nbytes,
+                   e2e_flops=2.0 * nnz * Ne, checksum=float(hC.array[::7, ::4099].sum()))
+        hB.free(); hC.free()
+        if ope is not op:
+            ope.destroy()
+    for bufs in ring:
+        for b in bufs:
+            b.free()
+    op.destroy()
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the UNMODIFIED reference (oracle/_ref) if present, else the oracle port
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference(wl, budget_s, reps_min=1, reps_max=50):
+    """returns dict(value GFLOP/s, ms, cores, kind, sample).  TEST INFRASTRUCTURE use of oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    w = importlib.import_module("libxsmm-1_b200.workloads")
+    cores = host_cores()
+    have_ref = pyoracle.Ref.available()
+    if not have_ref and os.path.isdir("/root/reference/src"):
+        try:
+            pyoracle.build_ref("avx2")
+            have_ref = pyoracle.Ref.available()
+        except Exception:
+            have_ref = False
+    if wl["kind"] == "spmdm":
+        t = wl["trans"]
+        A, B, C0 = w.spmdm_inputs(wl["M"], wl["N"], wl["K"], wl["density"], dtype=wl["dtype"], seed=1, transa=t[0], transb=t[1], transc=t[2])
+        nnz = int(np.count_nonzero(A))
+        flops = 2.0 * nnz * wl["N"]
+        if have_ref:
+            ref = pyoracle.Ref()
+            C = C0.copy()
+            _, _, tm = ref.spmdm(A, B, C, wl["M"], wl["N"], wl["K"], t[0], t[1], t[2], wl["beta"], threads=cores, reps=1, dump=False)   # warm-up
+            reps = int(min(reps_max, max(reps_min, budget_s / max(tm[0, 2], 1e-4))))
+            _, _, tm = ref.spmdm(A, B, C, wl["M"], wl["N"], wl["K"], t[0], t[1], t[2], wl["beta"], threads=cores, reps=reps, dump=False)
+            ms = float(np.median(tm[:, 2])) * 1e3
+            return dict(value=flops / ms / 1e6, ms=ms, best_ms=float(tm[:, 2].min()) * 1e3, cores=cores, kind="reference",
+                        sample="full workload (%s), %d reps after 1 warm-up, median; OpenMP over block ids, AVX2 instantiation bn=48" % (wl["desc"], reps))
+        orc = pyoracle.Oracle()
+        g = orc.geometry(wl["M"], wl["N"], wl["K"], 1, bn=48)
+        t0 = time.perf_counter()
+        sl = orc.slices(g, A, t[0]); C = C0.copy(); orc.compute(g, sl, B, C, t[1], t[2], float(wl["beta"]))
+        ms = (time.perf_counter() - t0) * 1e3
+        return dict(value=flops / ms / 1e6, ms=ms, best_ms=ms, cores=1, kind="port", sample="full workload once, scalar oracle port")
+    # fsspmdm: a bounded slab of columns, ld <= 2^20 (the reference's JIT addresses with 32-bit displacements)
+    a = w.fsspmdm_operator(wl["M"], wl["K"], wl["density"], wl["n_unique"], np.float64 if wl["dtype"] == "f64" else np.float32, seed=1)
+    nnz = int(np.count_nonzero(a))
+    Ns = 1 << 20 if wl["dtype"] == "f64" else 1 << 20
+    rng = np.random.default_rng(3)
+    B = rng.random((wl["K"], Ns), np.float32).astype(a.dtype); C = np.zeros((wl["M"], Ns), a.dtype)
+    flops = 2.0 * nnz * Ns
+    if have_ref:
+        ref = pyoracle.Ref()
+        _, _, tm = ref.fsspmdm(a, B, C, wl["beta"], panel=64, threads=cores, reps=1)
+        reps = int(min(reps_max, max(reps_min, budget_s / max(tm[0], 1e-4))))
+        sparse, chunk, tm = ref.fsspmdm(a, B, C, wl["beta"], panel=64, threads=cores, reps=reps)
+        ms = float(np.median(tm)) * 1e3
+        return dict(value=flops / ms / 1e6, ms=ms, best_ms=float(tm.min()) * 1e3, cores=cores, kind="reference",
+                    sample="2^20-column slab of the workload (ld=2^20), %d reps, median; OpenMP over 64-column panels; branch=%s" % (reps, "sparse_reg" if sparse else "dense"))
+    orc = pyoracle.Oracle()
+    Ns = 1 << 14
+    t0 = time.perf_counter()
+    if a.dtype == np.float64:
+        orc.dfsspmdm_execute(a, np.ascontiguousarray(B[:, :Ns]), np.ascontiguousarray(C[:, :Ns]), wl["beta"], 1)
+    else:
+        orc.sfsspmdm_execute(a, np.ascontiguousarray(B[:, :Ns]), np.ascontiguousarray(C[:, :Ns]), wl["beta"])
+    ms = (time.perf_counter() - t0) * 1e3
+    return dict(value=2.0 * nnz * Ns / ms / 1e6, ms=ms, best_ms=ms, cores=1, kind="port", sample="2^14-column slab, scalar oracle port")
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--others", default="c1,c3,c4,c5", help="extra workloads reported inside the line (N=1 only); '' = none")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric = "effective GFLOP/s (2*nnz*N)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference(wl, budget_s=0.0, reps_min=args.steps + args.warmup, reps_max=args.steps + args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": wl["dtype"], "data": "synthetic",
+                "config": {"workload": wl["desc"], "note": "reference CPU path on this host; one rank only"},
+                "cpu_baseline": {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    if args.gpus > 1 and world == 1:      # convenience: re-launch under torchrun like the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+
+    xs = importlib.import_module("libxsmm-1_b200")
+    xs.load()
+    xs.require_gpu()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    xs.load().libxsmm_b200_set_device(local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        xs.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def run(wl_, want_e2e, sample_clocks):
+        gen = run_spmdm_gpu(xs, wl_, args.steps, args.warmup, want_e2e) if wl_["kind"] == "spmdm" else \
+            run_fs_gpu(xs, wl_, args.steps, args.warmup, 1, want_e2e)
+        assert next(gen) == "ready"
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.25)
+        res = next(gen)
+        barrier()
+        clocks = sampler.finish() if sampler else None
+        res["total_ms"] = max_over_ranks(res["total_ms"])
+        res["flops_all"] = sum_over_ranks(res["flops"])
+        res["launches_all"] = int(sum_over_ranks(res["launches"]))
+        e2e = None
+        if want_e2e:
+            assert next(gen) == "ready-e2e"
+            barrier()
+            e = next(gen)
+            barrier()
+            e["e2e_ms"] = max_over_ranks(e["e2e_ms"])
+            e["flops_all"] = sum_over_ranks(e.get("e2e_flops", res["flops"]))
+            e2e = e
+        for _ in gen:
+            pass
+        return res, e2e, clocks
+
+    res, e2e, clocks = run(wl, not args.no_e2e, rank == 0)
+    ms_per_step = res["total_ms"] / args.steps
+    value = res["flops_all"] / (ms_per_step * 1e6)
+    peak, peak_src = peaks()
+    achieved = res["kernel_bytes"] / (res["kernel_ms"] * 1e6)
+    line = {
+        "metric": metric, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if wl["dtype"] in ("f32", "bf16") else "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "per_gpu": "one N-column panel per rank, A replicated, no collective on the data path",
+                   "global_N": (wl["N"] * world), "inputs": "bf16" if wl["dtype"] == "bf16" else wl["dtype"],
+                   "l2_policy": "inputs larger than L2: ring of %d A/B/C sets = %.0f MB, a different set every step" % (res["ring_sets"], res["ring_bytes"] / 1e6),
+                   "geometry": res["geo"], "nnz": res["nnz"], "step": "createSparseSlice (all blocks) + compute (all blocks)" if wl["kind"] == "spmdm" else "execute"},
+        "hbm_gbs": res["step_bytes"] * world / (ms_per_step * 1e6),
+        "gpu_launches": res["launches_all"],
+        "roofline": {"bound": "hbm", "kernel": res["kernel_name"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": res["kernel_bytes"],
+                     "kernel_ms": res["kernel_ms"], "parts": res["parts"]},
+        "clocks": clocks,
+    }
+    if e2e is not None:
+        e_ms = e2e["e2e_ms"] / args.steps
+        line["e2e"] = {"value": e2e["flops_all"] / (e_ms * 1e6), "unit": "GFLOP/s", "ms_per_step": e_ms,
+                       "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                       "api": "libxsmm_spmdm_exec_host" if wl["kind"] == "spmdm" else "libxsmm_[sd]fsspmdm_execute (host pointers)"}
+    if world == 1 and rank == 0 and args.others:
+        others = {}
+        for name in [n for n in args.others.split(",") if n and n != args.workload]:
+            try:
+                r2, _, _ = run(WORKLOADS[name], False, False)
+                ms2 = r2["total_ms"] / args.steps
+                ach2 = r2["kernel_bytes"] / (r2["kernel_ms"] * 1e6)
+                others[name] = {"workload": WORKLOADS[name]["desc"], "value": r2["flops"] / (ms2 * 1e6), "unit": "GFLOP/s", "ms_per_step": ms2,
+                                "hbm_gbs": r2["step_bytes"] / (ms2 * 1e6), "kernel": r2["kernel_name"], "kernel_ms": r2["kernel_ms"],
+                                "kernel_hbm_gbs": ach2, "kernel_hbm_frac": ach2 / peak, "parts": r2["parts"], "gpu_launches": r2["launches"]}
+            except Exception as ex:      # a secondary workload must never take the headline down
+                others[name] = {"error": repr(ex)[:200]}
+                xs.clear_error()
+        line["other_workloads"] = others
+    if world == 1 and rank == 0 and not args.no_cpu:
+        try:
+            c = cpu_reference(wl, budget_s=12.0)
+            line["cpu_baseline"] = {"value": c["value"], "unit": "GFLOP/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"], "ms_per_step": c["ms"]}
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": host_cores(), "kind": "reference", "sample": "failed: %r" % (ex,)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,112 @@
+/*
+ * libxsmm_b200.h -- stream-ordered, device-pointer entry points of the B200-native SPMDM/FSSPMDM
+ * library (libxsmm_b200.so) plus a few service calls.  These are ADDITIONS to the reference
+ * interface declared in libxsmm_spmdm.h / libxsmm_fsspmdm.h: one call covers the whole problem
+ * (all createSparseSlice blocks / all compute blocks) and is asynchronous on `stream`.
+ * `stream` is a cudaStream_t passed as void* so that this header needs no CUDA headers.
+ */
+#ifndef LIBXSMM_B200_H
+#define LIBXSMM_B200_H
+
+#include <stddef.h>
+#include "libxsmm_spmdm.h"
+#include "libxsmm_fsspmdm.h"
+
+/* All block ids of reference samples/spmdm/spmdm.c:100-104 in one launch.  d_a is a DEVICE pointer. */
+LIBXSMM_API void libxsmm_spmdm_createSparseSlice_fp32_stream(const libxsmm_spmdm_handle* handle, char transa,
+  const float* d_a, libxsmm_CSR_sparseslice* libxsmm_output_csr_a, void* stream);
+LIBXSMM_API void libxsmm_spmdm_createSparseSlice_bfloat16_stream(const libxsmm_spmdm_handle* handle, char transa,
+  const libxsmm_bfloat16* d_a, libxsmm_CSR_sparseslice* libxsmm_output_csr_a, void* stream);
+
+/* All block ids of reference samples/spmdm/spmdm.c:106-110 in one launch.  d_b, d_c are DEVICE pointers;
+ * alpha and beta are HOST pointers read at call time (alpha is ignored like in the reference). */
+LIBXSMM_API void libxsmm_spmdm_compute_fp32_stream(const libxsmm_spmdm_handle* handle, char transa, char transb,
+  const float* alpha, libxsmm_CSR_sparseslice* a_sparse, const float* d_b, char transc, const float* beta,
+  float* d_c, void* stream);
+LIBXSMM_API void libxsmm_spmdm_compute_bfloat16_stream(const libxsmm_spmdm_handle* handle, char transa, char transb,
+  const libxsmm_bfloat16* alpha, libxsmm_CSR_sparseslice* a_sparse, const libxsmm_bfloat16* d_b, char transc,
+  const libxsmm_bfloat16* beta, float* d_c, void* stream);
+
+/* Whole multiply with HOST buffers: copies A and B (and C if *beta != 0) to the device, slices,
+ * multiplies and copies C back; returns when C is complete.  This is what one repetition of the
+ * reference sample does (samples/spmdm/spmdm.c:88-111).  datatype selects the element type of a, b
+ * (the reference never fills handle->datatype, so it is an argument here); beta points at a float
+ * (F32) or at a libxsmm_bfloat16 bit pattern (BFLOAT16).  Host buffers should be page-locked
+ * (libxsmm_b200_host_alloc) for full PCIe speed; pageable memory works but is slower. */
+LIBXSMM_API void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_sparseslice* slices,
+  libxsmm_spmdm_datatype datatype, char transa, char transb, char transc, const void* a, const void* b,
+  const void* beta, float* c);
+/* Same two phases on DEVICE matrices, asynchronous on stream (slice creation, then compute). */
+LIBXSMM_API void libxsmm_spmdm_exec_stream(const libxsmm_spmdm_handle* handle, libxsmm_CSR_sparseslice* slices,
+  libxsmm_spmdm_datatype datatype, char transa, char transb, char transc, const void* d_a, const void* d_b,
+  const void* beta, float* d_c, void* stream);
+
+/* execute() on DEVICE pointers, asynchronous on stream (reference src/libxsmm_fsspmdm.c:260-291). */
+LIBXSMM_API void libxsmm_dfsspmdm_execute_stream(const libxsmm_dfsspmdm* handle, const double* d_B, double* d_C, void* stream);
+LIBXSMM_API void libxsmm_sfsspmdm_execute_stream(const libxsmm_sfsspmdm* handle, const float* d_B, float* d_C, void* stream);
+
+/* 1 if the reference would have taken its sparse_reg branch for this operator (rows without
+ * nonzeros are then left untouched, reference src/generator_spgemm_csr_asparse_reg.c:229,287). */
+LIBXSMM_API int libxsmm_dfsspmdm_is_sparse(const libxsmm_dfsspmdm* handle);
+LIBXSMM_API int libxsmm_sfsspmdm_is_sparse(const libxsmm_sfsspmdm* handle);
+/* 1 if the operator was baked into a specialised kernel at create time, 0 = generic kernel. */
+LIBXSMM_API int libxsmm_dfsspmdm_is_baked(const libxsmm_dfsspmdm* handle);
+LIBXSMM_API int libxsmm_sfsspmdm_is_baked(const libxsmm_sfsspmdm* handle);
+
+/* Sticky error state (the reference entry points return void and are mute unless LIBXSMM_VERBOSE). */
+LIBXSMM_API int libxsmm_b200_last_error(void);
+LIBXSMM_API const char* libxsmm_b200_last_error_string(void);
+LIBXSMM_API void libxsmm_b200_clear_error(void);
+
+/* Number of kernels this library has launched so far in this process. */
+LIBXSMM_API unsigned long long libxsmm_b200_launch_count(void);
+
+/* Page-locked host memory for callers that want full PCIe speed on the host-pointer paths. */
+LIBXSMM_API void* libxsmm_b200_host_alloc(size_t bytes);
+LIBXSMM_API void libxsmm_b200_host_free(void* p);
+
+/* Thin device-memory helpers so that C callers and the test harness need no CUDA headers. */
+LIBXSMM_API void* libxsmm_b200_device_alloc(size_t bytes);
+LIBXSMM_API void libxsmm_b200_device_free(void* p);
+LIBXSMM_API int libxsmm_b200_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
+LIBXSMM_API int libxsmm_b200_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+LIBXSMM_API int libxsmm_b200_memset(void* dst_device, int value, size_t bytes);
+LIBXSMM_API int libxsmm_b200_synchronize(void);
+LIBXSMM_API int libxsmm_b200_device_count(void);
+LIBXSMM_API int libxsmm_b200_set_device(int device);
+
+/* Streams, events, asynchronous copies and graph capture, again so that plain C callers (and the
+ * ctypes harness) can drive the stream entries without CUDA headers.  A stream/event/graph is an
+ * opaque pointer (cudaStream_t / cudaEvent_t / cudaGraphExec_t underneath). */
+LIBXSMM_API void* libxsmm_b200_stream_create(void);
+LIBXSMM_API void libxsmm_b200_stream_destroy(void* stream);
+LIBXSMM_API int libxsmm_b200_stream_synchronize(void* stream);
+LIBXSMM_API void* libxsmm_b200_event_create(void);
+LIBXSMM_API void libxsmm_b200_event_destroy(void* event);
+LIBXSMM_API int libxsmm_b200_event_record(void* event, void* stream);
+LIBXSMM_API int libxsmm_b200_event_synchronize(void* event);
+LIBXSMM_API float libxsmm_b200_event_elapsed_ms(void* start, void* stop);
+LIBXSMM_API int libxsmm_b200_memcpy_h2d_async(void* dst_device, const void* src_host, size_t bytes, void* stream);
+LIBXSMM_API int libxsmm_b200_memcpy_d2h_async(void* dst_host, const void* src_device, size_t bytes, void* stream);
+LIBXSMM_API int libxsmm_b200_memset_async(void* dst_device, int value, size_t bytes, void* stream);
+/* Capture everything enqueued on stream between begin and end into an executable graph. */
+LIBXSMM_API int libxsmm_b200_graph_begin(void* stream);
+LIBXSMM_API void* libxsmm_b200_graph_end(void* stream);
+LIBXSMM_API int libxsmm_b200_graph_launch(void* graph_exec, void* stream);
+LIBXSMM_API void libxsmm_b200_graph_destroy(void* graph_exec);
+
+/* Host-only planning entries (no CUDA call is made; they work on a machine without a GPU).
+ * geometry: the block geometry libxsmm_spmdm_init would choose (reference src/libxsmm_spmdm.c:552-608)
+ *   for bn = 48 | 96 | 6; geom[9] = m n k bm bn bk mb nb kb.  Returns 0 on success.
+ * plan: what create() decides for an operator (reference src/libxsmm_fsspmdm.c:88-143 and
+ *   src/generator_spgemm_csr_asparse_reg.c:111-150): info[5] = nnz, unique values, 1 if the reference
+ *   takes its sparse_reg branch, bytes of x86 code it would emit (0 if not evaluated), N_chunksize.
+ * kernel_source: the CUDA source create() would bake for the operator (free with free_string). */
+LIBXSMM_API int libxsmm_b200_spmdm_geometry(int M, int N, int K, int max_threads, int bn, int* geom);
+LIBXSMM_API int libxsmm_b200_fsspmdm_plan(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta,
+  const void* a_dense, long long* info);
+LIBXSMM_API char* libxsmm_b200_fsspmdm_kernel_source(int is_double, int M, int N, int K, int lda, int ldb, int ldc,
+  double beta, const void* a_dense);
+LIBXSMM_API void libxsmm_b200_free_string(char* s);
+
+#endif /*LIBXSMM_B200_H*/

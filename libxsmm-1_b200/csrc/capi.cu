@@ -1,0 +1,668 @@
+// C ABI of libxsmm_b200.so: the 14 reference entry points (include/libxsmm_spmdm.h,
+// include/libxsmm_fsspmdm.h) plus the stream-ordered additions (include/libxsmm_b200.h).
+// Host logic only; the kernels are in spmdm_kernels.cu / fsspmdm.cu.  No CPU compute path exists:
+// every entry point either launches CUDA kernels or records an error.
+#include "common.cuh"
+#include "../../include/libxsmm_b200.h"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <climits>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+namespace xb {
+
+// ---- error state / counters ------------------------------------------------------------------------
+static std::mutex g_err_mtx;
+static int g_err_code = 0;
+static char g_err_msg[1024] = "";
+static std::atomic<unsigned long long> g_launches(0);
+
+int verbosity()
+{
+  static int v = INT_MIN;
+  if (INT_MIN == v) {
+    const char* e = getenv("LIBXSMM_VERBOSE");   // same switch as the reference (src/libxsmm_main.c:562)
+    v = (e && *e) ? atoi(e) : 0;
+  }
+  return v;
+}
+
+void set_error(int code, const char* fmt, ...)
+{
+  std::lock_guard<std::mutex> lock(g_err_mtx);
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err_msg, sizeof(g_err_msg), fmt, ap);
+  va_end(ap);
+  g_err_code = (0 != code) ? code : -1;
+  if (0 != verbosity()) fprintf(stderr, "LIBXSMM_B200 ERROR: %s\n", g_err_msg);
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ---- SPMDM context -----------------------------------------------------------------------------------
+constexpr int kExecPanels = 8;   // column panels of the pipelined host path (libxsmm_spmdm_exec_host)
+struct SpmdmCtx {
+  Geom g;
+  int simd_w;
+  int max_threads;
+  void* arena_base;
+  SliceArena arena;
+  libxsmm_CSR_sparseslice* table;   // host table of device pointers handed to the caller
+  char* staging;                    // device, max_threads slabs
+  size_t staging_per_tid;
+  std::vector<cudaStream_t> streams;
+  std::mutex mtx;
+  // whole-problem host path (libxsmm_spmdm_exec_host)
+  void* d_a; void* d_b; float* d_c;
+  size_t d_a_bytes, d_b_bytes, d_c_bytes;
+  cudaStream_t xs[3];
+  cudaEvent_t xev[kExecPanels + 1];
+};
+
+static std::mutex g_reg_mtx;
+static std::unordered_map<const void*, SpmdmCtx*> g_registry;   // keyed by the slice arena address
+
+static SpmdmCtx* find_ctx(const libxsmm_spmdm_handle* h)
+{
+  if (0 == h || 0 == h->base_ptr_scratch_A) { set_error(-10, "spmdm: handle not initialised"); return 0; }
+  std::lock_guard<std::mutex> lock(g_reg_mtx);
+  std::unordered_map<const void*, SpmdmCtx*>::const_iterator it = g_registry.find(h->base_ptr_scratch_A);
+  if (it == g_registry.end()) { set_error(-11, "spmdm: unknown handle (not created by libxsmm_spmdm_init or already destroyed)"); return 0; }
+  return it->second;
+}
+
+static bool is_device_ptr(const void* p)
+{
+  cudaPointerAttributes at;
+  if (cudaSuccess != cudaPointerGetAttributes(&at, p)) { (void)cudaGetLastError(); return false; }
+  return cudaMemoryTypeDevice == at.type || cudaMemoryTypeManaged == at.type;
+}
+
+static bool is_t(char c) { return 'T' == c || 't' == c; }
+
+// Geometry of the reference (src/libxsmm_spmdm.c:552-608): bm = 512 or 256, bk = 128, bn bound to the
+// instantiation (:557-583; here selected by LIBXSMM_B200_SPMDM_BN, default 48 = the AVX2 build every
+// GCC build of the reference gets), then bm is lowered one row at a time while the imbalance estimate
+// (biggest/mean block work x busiest/mean thread load) exceeds 1.1.
+static void spmdm_geometry(int M, int N, int K, int max_threads, int bn, Geom* g)
+{
+  g->m = M; g->n = N; g->k = K;
+  g->bm = (M >= 4096 || M <= 1024) ? 512 : 256;
+  g->bn = bn; g->bk = 128;
+  g->mb = (M + g->bm - 1) / g->bm;
+  g->nb = (N + g->bn - 1) / g->bn;
+  g->kb = (K + g->bk - 1) / g->bk;
+  const double total = (double)((size_t)M * (size_t)N);
+  for (;;) {
+    const double per_block = (g->bm * g->bn) / (total / (double)((size_t)g->mb * (size_t)g->nb));
+    const int busiest = (g->mb * g->nb + max_threads - 1) / max_threads;
+    const double per_thread = busiest / ((double)g->mb * g->nb / max_threads);
+    if (!(g->bm > 32 && per_block * per_thread > 1.1)) break;
+    --g->bm;
+    g->mb = (M + g->bm - 1) / g->bm;
+  }
+}
+
+static ColModes spmdm_modes(const Geom& g, int simd_w)
+{
+  ColModes m;
+  m.n_full_end = g.n; m.tail_from = g.n;
+  if (simd_w > 1 && 0 != (g.n % g.bn)) {   // narrow last block (compute template :72-76)
+    m.n_full_end = (g.n / g.bn) * g.bn;
+    const int num_n = g.n - m.n_full_end;
+    int full_regs = num_n / simd_w;
+    if (full_regs > 0 && (full_regs % 2)) --full_regs;
+    m.tail_from = m.n_full_end + full_regs * simd_w;
+  }
+  return m;
+}
+
+static cudaStream_t tid_stream(SpmdmCtx* c, int tid)
+{
+  std::lock_guard<std::mutex> lock(c->mtx);
+  if (0 == c->streams[tid]) XB_CUDA(cudaStreamCreateWithFlags(&c->streams[tid], cudaStreamNonBlocking));
+  return c->streams[tid];
+}
+
+static void slices_whole(const libxsmm_spmdm_handle* handle, char transa, const void* d_a, int is_bf16, cudaStream_t stream)
+{
+  SpmdmCtx* c = find_ctx(handle);
+  if (0 == c) return;
+  SliceArgs a;
+  a.a = d_a; a.transa = is_t(transa); a.lda = a.transa ? c->g.m : c->g.k; a.is_bf16 = is_bf16;
+  a.origin_is_block = 0; a.slice0 = 0; a.simd_w = c->simd_w; a.g = c->g; a.out = c->arena;
+  launch_slices(a, c->g.mb * c->g.kb, stream);
+}
+
+static void compute_whole(const libxsmm_spmdm_handle* handle, char transb, char transc, float beta,
+                          const void* d_b, float* d_c, int is_bf16, cudaStream_t stream)
+{
+  SpmdmCtx* c = find_ctx(handle);
+  if (0 == c) return;
+  ComputeArgs a;
+  a.sl = c->arena; a.b = d_b; a.c = d_c;
+  a.transb = is_t(transb); a.transc = is_t(transc); a.is_bf16 = is_bf16;
+  a.ldb = a.transb ? c->g.k : c->g.n;
+  a.ldc = a.transc ? c->g.m : c->g.n;
+  a.beta = beta; a.g = c->g; a.mb_first = 0; a.mb_count = c->g.mb;
+  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w);
+  launch_compute(a, stream);
+}
+
+// legacy per-block slice creation (reference src/libxsmm_spmdm.c:253-272 / :328-347)
+static void slice_block(const libxsmm_spmdm_handle* handle, char transa, const void* a_in, int is_bf16, int block_id, int tid)
+{
+  SpmdmCtx* c = find_ctx(handle);
+  if (0 == c) return;
+  const Geom& g = c->g;
+  if (block_id < 0 || block_id >= g.mb * g.kb || tid < 0 || tid >= c->max_threads) { set_error(-12, "createSparseSlice: block_id/tid out of range"); return; }
+  const cudaStream_t st = tid_stream(c, tid);
+  const size_t esz = is_bf16 ? 2 : 4;
+  const int kb = block_id / g.mb, mbi = block_id % g.mb;
+  const int nrows = (g.bm < g.m - mbi * g.bm) ? g.bm : (g.m - mbi * g.bm);
+  const int ncols = (g.bk < g.k - kb * g.bk) ? g.bk : (g.k - kb * g.bk);
+  SliceArgs a;
+  a.transa = is_t(transa); a.is_bf16 = is_bf16; a.slice0 = block_id; a.simd_w = c->simd_w; a.g = g; a.out = c->arena;
+  if (is_device_ptr(a_in)) {
+    a.a = a_in; a.lda = a.transa ? g.m : g.k; a.origin_is_block = 0;
+  }
+  else {   // host matrix: stage this block in the tid's slab
+    char* slab = c->staging + (size_t)tid * c->staging_per_tid;
+    if (!a.transa) {
+      const char* src = (const char*)a_in + ((size_t)mbi * g.bm * g.k + (size_t)kb * g.bk) * esz;
+      XB_CUDA(cudaMemcpy2DAsync(slab, ncols * esz, src, (size_t)g.k * esz, ncols * esz, nrows, cudaMemcpyHostToDevice, st));
+      a.lda = ncols;
+    }
+    else {
+      const char* src = (const char*)a_in + ((size_t)kb * g.bk * g.m + (size_t)mbi * g.bm) * esz;
+      XB_CUDA(cudaMemcpy2DAsync(slab, nrows * esz, src, (size_t)g.m * esz, nrows * esz, ncols, cudaMemcpyHostToDevice, st));
+      a.lda = nrows;
+    }
+    a.a = slab; a.origin_is_block = 1;
+  }
+  launch_slices(a, 1, st);
+  XB_CUDA(cudaStreamSynchronize(st));
+}
+
+// legacy per-block compute (reference src/libxsmm_spmdm.c:418-442 / :513-537)
+static void compute_block(const libxsmm_spmdm_handle* handle, char transb, char transc, float beta,
+                          const void* b_in, float* c_in, int is_bf16, int block_id, int tid)
+{
+  SpmdmCtx* c = find_ctx(handle);
+  if (0 == c) return;
+  const Geom& g = c->g;
+  if (block_id < 0 || block_id >= g.mb * g.nb || tid < 0 || tid >= c->max_threads) { set_error(-13, "compute: block_id/tid out of range"); return; }
+  const cudaStream_t st = tid_stream(c, tid);
+  const size_t esz = is_bf16 ? 2 : 4;
+  const int mbi = block_id / g.nb, nbi = block_id % g.nb;
+  const int m0 = mbi * g.bm, n0 = nbi * g.bn;
+  const int num_m = (g.bm < g.m - m0) ? g.bm : (g.m - m0);
+  const int num_n = (g.bn < g.n - n0) ? g.bn : (g.n - n0);
+  const bool tb = is_t(transb), tc = is_t(transc);
+  const bool dev_b = is_device_ptr(b_in), dev_c = is_device_ptr(c_in);
+  ComputeArgs a;
+  a.sl = c->arena; a.transb = tb; a.transc = tc; a.is_bf16 = is_bf16; a.beta = beta; a.g = g;
+  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w);
+  char* slab = c->staging + (size_t)tid * c->staging_per_tid;
+  const size_t slab_b_bytes = (((size_t)g.k * g.bn * 4) + 255) & ~(size_t)255;
+  float* c_stage = (float*)(slab + slab_b_bytes);
+  if (dev_b) {
+    a.b = (const char*)b_in + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
+    a.ldb = tb ? g.k : g.n;
+  }
+  else if (!tb) {
+    XB_CUDA(cudaMemcpy2DAsync(slab, num_n * esz, (const char*)b_in + (size_t)n0 * esz, (size_t)g.n * esz, num_n * esz, g.k, cudaMemcpyHostToDevice, st));
+    a.b = slab; a.ldb = num_n;
+  }
+  else {
+    XB_CUDA(cudaMemcpyAsync(slab, (const char*)b_in + (size_t)n0 * g.k * esz, (size_t)num_n * g.k * esz, cudaMemcpyHostToDevice, st));
+    a.b = slab; a.ldb = g.k;
+  }
+  if (dev_c) {
+    a.c = c_in + (tc ? (size_t)n0 * g.m : (size_t)n0);
+    a.ldc = tc ? g.m : g.n; a.row_origin = 0;
+  }
+  else {
+    a.c = c_stage; a.row_origin = m0; a.ldc = tc ? num_m : num_n;
+    if (0.f != beta) {
+      if (!tc) XB_CUDA(cudaMemcpy2DAsync(c_stage, num_n * 4, c_in + (size_t)m0 * g.n + n0, (size_t)g.n * 4, num_n * 4, num_m, cudaMemcpyHostToDevice, st));
+      else XB_CUDA(cudaMemcpy2DAsync(c_stage, num_m * 4, c_in + (size_t)n0 * g.m + m0, (size_t)g.m * 4, num_m * 4, num_n, cudaMemcpyHostToDevice, st));
+    }
+  }
+  launch_compute(a, st);
+  if (!dev_c) {
+    if (!tc) XB_CUDA(cudaMemcpy2DAsync(c_in + (size_t)m0 * g.n + n0, (size_t)g.n * 4, c_stage, num_n * 4, num_n * 4, num_m, cudaMemcpyDeviceToHost, st));
+    else XB_CUDA(cudaMemcpy2DAsync(c_in + (size_t)n0 * g.m + m0, (size_t)g.m * 4, c_stage, num_m * 4, num_m * 4, num_n, cudaMemcpyDeviceToHost, st));
+  }
+  XB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+// =====================================================================================================
+// SPMDM
+// =====================================================================================================
+extern "C" {
+
+void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_handle* handle,
+                        libxsmm_CSR_sparseslice** libxsmm_output_csr)
+{
+  if (0 == handle) { set_error(-20, "spmdm_init: NULL handle"); return; }
+  memset(handle, 0, sizeof(*handle));
+  if (libxsmm_output_csr) *libxsmm_output_csr = 0;
+  if (M <= 0 || N <= 0 || K <= 0) { set_error(-21, "spmdm_init: empty problem %dx%dx%d", M, N, K); handle->m = M; handle->n = N; handle->k = K; return; }
+  if (max_threads < 1) max_threads = 1;
+  int bn = 48;
+  const char* env = getenv("LIBXSMM_B200_SPMDM_BN");
+  if (env && *env) { const int v = atoi(env); if (96 == v || 48 == v || 6 == v) bn = v; }
+  SpmdmCtx* c = new SpmdmCtx();
+  spmdm_geometry(M, N, K, max_threads, bn, &c->g);
+  c->simd_w = (96 == bn) ? 16 : ((48 == bn) ? 8 : 1);
+  c->max_threads = max_threads;
+  c->streams.assign((size_t)max_threads, (cudaStream_t)0);
+  c->d_a = 0; c->d_b = 0; c->d_c = 0; c->d_a_bytes = c->d_b_bytes = c->d_c_bytes = 0;
+  c->xs[0] = c->xs[1] = c->xs[2] = 0;
+  for (int i = 0; i <= kExecPanels; ++i) c->xev[i] = 0;
+  const Geom& g = c->g;
+  const size_t ns = (size_t)g.mb * g.kb, cap = (size_t)g.bm * g.bk;
+  const size_t row_bytes = ((ns * (g.bm + 1) * 2) + 255) & ~(size_t)255;
+  const size_t col_bytes = ns * cap * 2, val_bytes = ns * cap * 4;
+  c->arena_base = 0; c->staging = 0; c->table = 0;
+  XB_CUDA(cudaMalloc(&c->arena_base, row_bytes + col_bytes + val_bytes));
+  // per-tid staging slab for the legacy per-block entries on HOST matrices: an A block, or a B panel
+  // (k x bn) followed by a C tile (bm x bn); the reference's slab holds the latter two (:148-155)
+  {
+    const size_t a_blk = cap * 4;
+    const size_t bc = ((((size_t)g.k * g.bn * 4) + 255) & ~(size_t)255) + (size_t)g.bm * g.bn * 4;
+    size_t per = a_blk > bc ? a_blk : bc;
+    per = (per + 4095) & ~(size_t)4095;
+    c->staging_per_tid = per;
+    XB_CUDA(cudaMalloc((void**)&c->staging, per * (size_t)max_threads));
+  }
+  if (0 == c->arena_base || 0 == c->staging) {   // the reference leaves NULL pointers on failure (:140-144,165-168)
+    if (c->arena_base) cudaFree(c->arena_base);
+    if (c->staging) cudaFree(c->staging);
+    delete c;
+    handle->m = M; handle->n = N; handle->k = K;
+    return;
+  }
+  c->arena.rowidx = (uint16_t*)c->arena_base;
+  c->arena.colidx = (uint16_t*)((char*)c->arena_base + row_bytes);
+  c->arena.values = (float*)((char*)c->arena_base + row_bytes + col_bytes);
+  c->table = (libxsmm_CSR_sparseslice*)malloc(sizeof(libxsmm_CSR_sparseslice) * ns);
+  for (size_t s = 0; s < ns; ++s) {
+    c->table[s].rowidx = c->arena.rowidx + s * (g.bm + 1);
+    c->table[s].colidx = c->arena.colidx + s * cap;
+    c->table[s].values = c->arena.values + s * cap;
+  }
+  handle->m = g.m; handle->n = g.n; handle->k = g.k;
+  handle->bm = g.bm; handle->bn = g.bn; handle->bk = g.bk;
+  handle->mb = g.mb; handle->nb = g.nb; handle->kb = g.kb;
+  handle->datatype = LIBXSMM_SPMDM_DATATYPE_F32;
+  handle->base_ptr_scratch_A = (char*)c->arena_base;
+  handle->base_ptr_scratch_B_scratch_C = c->staging;
+  handle->memory_for_scratch_per_thread = (int)(c->staging_per_tid > (size_t)INT_MAX ? INT_MAX : c->staging_per_tid);
+  if (libxsmm_output_csr) *libxsmm_output_csr = c->table;
+  {
+    std::lock_guard<std::mutex> lock(g_reg_mtx);
+    g_registry[c->arena_base] = c;
+  }
+  if (verbosity() > 0) fprintf(stderr, "LIBXSMM_B200 spmdm_init: %dx%dx%d bm=%d bn=%d bk=%d mb=%d nb=%d kb=%d\n", M, N, K, g.bm, g.bn, g.bk, g.mb, g.nb, g.kb);
+}
+
+void libxsmm_spmdm_destroy(libxsmm_spmdm_handle* handle)
+{
+  if (0 == handle || 0 == handle->base_ptr_scratch_A) return;
+  SpmdmCtx* c = 0;
+  {
+    std::lock_guard<std::mutex> lock(g_reg_mtx);
+    std::unordered_map<const void*, SpmdmCtx*>::iterator it = g_registry.find(handle->base_ptr_scratch_A);
+    if (it != g_registry.end()) { c = it->second; g_registry.erase(it); }
+  }
+  if (c) {
+    for (size_t i = 0; i < c->streams.size(); ++i) if (c->streams[i]) { cudaStreamSynchronize(c->streams[i]); cudaStreamDestroy(c->streams[i]); }
+    for (int i = 0; i < 3; ++i) if (c->xs[i]) { cudaStreamSynchronize(c->xs[i]); cudaStreamDestroy(c->xs[i]); }
+    for (int i = 0; i <= kExecPanels; ++i) if (c->xev[i]) cudaEventDestroy(c->xev[i]);
+    if (c->d_a) cudaFree(c->d_a);
+    if (c->d_b) cudaFree(c->d_b);
+    if (c->d_c) cudaFree(c->d_c);
+    cudaFree(c->arena_base);
+    cudaFree(c->staging);
+    free(c->table);
+    delete c;
+  }
+  handle->base_ptr_scratch_A = 0;              // like the reference (:173-179): arenas go, the handle stays
+  handle->base_ptr_scratch_B_scratch_C = 0;
+}
+
+int libxsmm_spmdm_get_num_createSparseSlice_blocks(const libxsmm_spmdm_handle* handle) { return handle->mb * handle->kb; }
+int libxsmm_spmdm_get_num_compute_blocks(const libxsmm_spmdm_handle* handle) { return handle->mb * handle->nb; }
+
+void libxsmm_spmdm_createSparseSlice_fp32_thread(const libxsmm_spmdm_handle* handle, char transa, const float* a,
+  libxsmm_CSR_sparseslice* libxsmm_output_csr_a, int block_id, int tid, int nthreads)
+{
+  (void)libxsmm_output_csr_a; (void)nthreads;
+  slice_block(handle, transa, a, 0, block_id, tid);
+}
+
+void libxsmm_spmdm_createSparseSlice_bfloat16_thread(const libxsmm_spmdm_handle* handle, char transa, const libxsmm_bfloat16* a,
+  libxsmm_CSR_sparseslice* libxsmm_output_csr_a, int block_id, int tid, int nthreads)
+{
+  (void)libxsmm_output_csr_a; (void)nthreads;
+  slice_block(handle, transa, a, 1, block_id, tid);
+}
+
+void libxsmm_spmdm_compute_fp32_thread(const libxsmm_spmdm_handle* handle, char transa, char transb, const float* alpha,
+  libxsmm_CSR_sparseslice* a_sparse, const float* b, char transc, const float* beta, float* c, int block_id, int tid, int nthreads)
+{
+  (void)transa; (void)alpha; (void)a_sparse; (void)nthreads;   // transa/alpha unused like the reference (tpl.c:60-61)
+  compute_block(handle, transb, transc, *beta, b, c, 0, block_id, tid);
+}
+
+void libxsmm_spmdm_compute_bfloat16_thread(const libxsmm_spmdm_handle* handle, char transa, char transb, const libxsmm_bfloat16* alpha,
+  libxsmm_CSR_sparseslice* a_sparse, const libxsmm_bfloat16* b, char transc, const libxsmm_bfloat16* beta, float* c,
+  int block_id, int tid, int nthreads)
+{
+  (void)transa; (void)alpha; (void)a_sparse; (void)nthreads;
+  // the reference converts the raw 16-bit pattern as an INTEGER (bf16 tpl.c:91,113,164): mirrored
+  compute_block(handle, transb, transc, (float)(*beta), b, c, 1, block_id, tid);
+}
+
+// ---- stream-ordered whole-problem entries -----------------------------------------------------------
+void libxsmm_spmdm_createSparseSlice_fp32_stream(const libxsmm_spmdm_handle* handle, char transa, const float* d_a,
+  libxsmm_CSR_sparseslice* libxsmm_output_csr_a, void* stream)
+{
+  (void)libxsmm_output_csr_a;
+  slices_whole(handle, transa, d_a, 0, (cudaStream_t)stream);
+}
+
+void libxsmm_spmdm_createSparseSlice_bfloat16_stream(const libxsmm_spmdm_handle* handle, char transa, const libxsmm_bfloat16* d_a,
+  libxsmm_CSR_sparseslice* libxsmm_output_csr_a, void* stream)
+{
+  (void)libxsmm_output_csr_a;
+  slices_whole(handle, transa, d_a, 1, (cudaStream_t)stream);
+}
+
+void libxsmm_spmdm_compute_fp32_stream(const libxsmm_spmdm_handle* handle, char transa, char transb, const float* alpha,
+  libxsmm_CSR_sparseslice* a_sparse, const float* d_b, char transc, const float* beta, float* d_c, void* stream)
+{
+  (void)transa; (void)alpha; (void)a_sparse;
+  compute_whole(handle, transb, transc, *beta, d_b, d_c, 0, (cudaStream_t)stream);
+}
+
+void libxsmm_spmdm_compute_bfloat16_stream(const libxsmm_spmdm_handle* handle, char transa, char transb, const libxsmm_bfloat16* alpha,
+  libxsmm_CSR_sparseslice* a_sparse, const libxsmm_bfloat16* d_b, char transc, const libxsmm_bfloat16* beta, float* d_c, void* stream)
+{
+  (void)transa; (void)alpha; (void)a_sparse;
+  compute_whole(handle, transb, transc, (float)(*beta), d_b, d_c, 1, (cudaStream_t)stream);
+}
+
+void libxsmm_spmdm_exec_stream(const libxsmm_spmdm_handle* handle, libxsmm_CSR_sparseslice* slices,
+  libxsmm_spmdm_datatype datatype, char transa, char transb, char transc, const void* d_a, const void* d_b,
+  const void* beta, float* d_c, void* stream)
+{
+  (void)slices;
+  const int is_bf16 = (LIBXSMM_SPMDM_DATATYPE_BFLOAT16 == datatype);
+  const float beta_f = is_bf16 ? (float)(*(const libxsmm_bfloat16*)beta) : *(const float*)beta;
+  slices_whole(handle, transa, d_a, is_bf16, (cudaStream_t)stream);
+  compute_whole(handle, transb, transc, beta_f, d_b, d_c, is_bf16, (cudaStream_t)stream);
+}
+
+void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_sparseslice* slices,
+  libxsmm_spmdm_datatype datatype, char transa, char transb, char transc, const void* a, const void* b,
+  const void* beta, float* c_host)
+{
+  (void)slices;
+  SpmdmCtx* c = find_ctx(handle);
+  if (0 == c) return;
+  std::lock_guard<std::mutex> lock(c->mtx);
+  const Geom& g = c->g;
+  const int is_bf16 = (LIBXSMM_SPMDM_DATATYPE_BFLOAT16 == datatype);
+  const size_t esz = is_bf16 ? 2 : 4;
+  const size_t a_bytes = (size_t)g.m * g.k * esz, b_bytes = (size_t)g.k * g.n * esz, c_bytes = (size_t)g.m * g.n * 4;
+  const float beta_f = is_bf16 ? (float)(*(const libxsmm_bfloat16*)beta) : *(const float*)beta;
+  const bool tb = is_t(transb), tc = is_t(transc);
+  if (c->d_a_bytes < a_bytes) { if (c->d_a) cudaFree(c->d_a); c->d_a = 0; XB_CUDA(cudaMalloc(&c->d_a, a_bytes)); c->d_a_bytes = a_bytes; }
+  if (c->d_b_bytes < b_bytes) { if (c->d_b) cudaFree(c->d_b); c->d_b = 0; XB_CUDA(cudaMalloc(&c->d_b, b_bytes)); c->d_b_bytes = b_bytes; }
+  if (c->d_c_bytes < c_bytes) { if (c->d_c) cudaFree(c->d_c); c->d_c = 0; XB_CUDA(cudaMalloc((void**)&c->d_c, c_bytes)); c->d_c_bytes = c_bytes; }
+  if (0 == c->xs[0]) {
+    for (int i = 0; i < 3; ++i) XB_CUDA(cudaStreamCreateWithFlags(&c->xs[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kExecPanels + 1; ++i) XB_CUDA(cudaEventCreateWithFlags(&c->xev[i], cudaEventDisableTiming));
+  }
+  if (0 == c->d_a || 0 == c->d_b || 0 == c->d_c) return;
+  // Three streams: xs[0] uploads (A first, then the B -- and C -- panels in column order), xs[1] runs the
+  // kernels (slicing, then one compute launch per column panel as soon as that panel has landed),
+  // xs[2] downloads finished C panels.  PCIe is full duplex, so uploads of later panels, the kernels
+  // and the downloads of earlier panels all overlap.  Column panels are contiguous row ranges of B / C
+  // when those are stored transposed, and strided 2-D copies otherwise.
+  const ColModes modes = spmdm_modes(g, c->simd_w);
+  int npanels = kExecPanels;
+  // panel boundaries are multiples of 256 columns so that every launch keeps whole CTA tiles and
+  // the reference's column modes (defined on global column numbers) are unaffected by the split
+  int pw = (((g.n + npanels - 1) / npanels) + 255) / 256 * 256;
+  if (pw <= 0) pw = 256;
+  npanels = (g.n + pw - 1) / pw;
+  XB_CUDA(cudaMemcpyAsync(c->d_a, a, a_bytes, cudaMemcpyHostToDevice, c->xs[0]));
+  XB_CUDA(cudaEventRecord(c->xev[kExecPanels], c->xs[0]));
+  XB_CUDA(cudaStreamWaitEvent(c->xs[1], c->xev[kExecPanels], 0));
+  {
+    SliceArgs sa;
+    sa.a = c->d_a; sa.transa = is_t(transa); sa.lda = sa.transa ? g.m : g.k; sa.is_bf16 = is_bf16;
+    sa.origin_is_block = 0; sa.slice0 = 0; sa.simd_w = c->simd_w; sa.g = g; sa.out = c->arena;
+    launch_slices(sa, g.mb * g.kb, c->xs[1]);
+  }
+  for (int p = 0; p < npanels; ++p) {
+    const int n0 = p * pw, w = (g.n - n0 < pw) ? (g.n - n0) : pw;
+    char* db = (char*)c->d_b; const char* hb = (const char*)b;
+    if (tb) XB_CUDA(cudaMemcpyAsync(db + (size_t)n0 * g.k * esz, hb + (size_t)n0 * g.k * esz, (size_t)w * g.k * esz, cudaMemcpyHostToDevice, c->xs[0]));
+    else XB_CUDA(cudaMemcpy2DAsync(db + (size_t)n0 * esz, (size_t)g.n * esz, hb + (size_t)n0 * esz, (size_t)g.n * esz, (size_t)w * esz, g.k, cudaMemcpyHostToDevice, c->xs[0]));
+    if (0.f != beta_f) {
+      if (tc) XB_CUDA(cudaMemcpyAsync(c->d_c + (size_t)n0 * g.m, c_host + (size_t)n0 * g.m, (size_t)w * g.m * 4, cudaMemcpyHostToDevice, c->xs[0]));
+      else XB_CUDA(cudaMemcpy2DAsync(c->d_c + n0, (size_t)g.n * 4, c_host + n0, (size_t)g.n * 4, (size_t)w * 4, g.m, cudaMemcpyHostToDevice, c->xs[0]));
+    }
+    XB_CUDA(cudaEventRecord(c->xev[p], c->xs[0]));
+    XB_CUDA(cudaStreamWaitEvent(c->xs[1], c->xev[p], 0));
+    {
+      ComputeArgs ca;
+      ca.sl = c->arena; ca.transb = tb; ca.transc = tc; ca.is_bf16 = is_bf16;
+      ca.ldb = tb ? g.k : g.n; ca.ldc = tc ? g.m : g.n;
+      ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
+      ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
+      ca.beta = beta_f; ca.g = g; ca.mb_first = 0; ca.mb_count = g.mb;
+      ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes;
+      launch_compute(ca, c->xs[1]);
+    }
+    XB_CUDA(cudaEventRecord(c->xev[p], c->xs[1]));
+    XB_CUDA(cudaStreamWaitEvent(c->xs[2], c->xev[p], 0));
+    if (tc) XB_CUDA(cudaMemcpyAsync(c_host + (size_t)n0 * g.m, c->d_c + (size_t)n0 * g.m, (size_t)w * g.m * 4, cudaMemcpyDeviceToHost, c->xs[2]));
+    else XB_CUDA(cudaMemcpy2DAsync(c_host + n0, (size_t)g.n * 4, c->d_c + n0, (size_t)g.n * 4, (size_t)w * 4, g.m, cudaMemcpyDeviceToHost, c->xs[2]));
+  }
+  XB_CUDA(cudaStreamSynchronize(c->xs[2]));
+  XB_CUDA(cudaStreamSynchronize(c->xs[0]));
+}
+
+// =====================================================================================================
+// FSSPMDM
+// =====================================================================================================
+struct libxsmm_dfsspmdm;
+struct libxsmm_sfsspmdm;
+
+static void fs_execute_any(const FsOperator* op, const void* B, void* C)
+{
+  if (0 == op) { set_error(-30, "fsspmdm_execute: NULL handle"); return; }
+  int M, N, K, ldb, ldc, beta_one;
+  fs_shape(op, &M, &N, &K, &ldb, &ldc, &beta_one);
+  const size_t esz = fs_is_double(op) ? 8 : 4;
+  if (is_device_ptr(B) && is_device_ptr(C)) {
+    fs_execute(op, B, C, N, ldb, ldc, cudaStreamPerThread);
+    XB_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    return;
+  }
+  // HOST panels: pipeline column chunks through compact device staging on three streams so that
+  // upload, kernel and download of neighbouring chunks overlap
+  static std::mutex mtx;
+  std::lock_guard<std::mutex> lock(mtx);
+  const int kSlots = 3;
+  static cudaStream_t st[kSlots] = { 0, 0, 0 };
+  static char* dB[kSlots] = { 0, 0, 0 };
+  static char* dC[kSlots] = { 0, 0, 0 };
+  static size_t capB = 0, capC = 0;
+  long long chunk = 1 << 16;
+  if (chunk > N) chunk = N;
+  const size_t needB = (size_t)K * chunk * esz, needC = (size_t)M * chunk * esz;
+  for (int s = 0; s < kSlots; ++s) if (0 == st[s]) XB_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+  if (capB < needB) { for (int s = 0; s < kSlots; ++s) { if (dB[s]) cudaFree(dB[s]); dB[s] = 0; XB_CUDA(cudaMalloc((void**)&dB[s], needB)); } capB = needB; }
+  if (capC < needC) { for (int s = 0; s < kSlots; ++s) { if (dC[s]) cudaFree(dC[s]); dC[s] = 0; XB_CUDA(cudaMalloc((void**)&dC[s], needC)); } capC = needC; }
+  for (int s = 0; s < kSlots; ++s) if (0 == dB[s] || 0 == dC[s]) { capB = capC = 0; return; }
+  int slot = 0;
+  for (long long n0 = 0; n0 < N; n0 += chunk, slot = (slot + 1) % kSlots) {
+    const long long w = (N - n0 < chunk) ? (N - n0) : chunk;
+    XB_CUDA(cudaMemcpy2DAsync(dB[slot], w * esz, (const char*)B + n0 * esz, (size_t)ldb * esz, w * esz, K, cudaMemcpyHostToDevice, st[slot]));
+    if (fs_needs_c_input(op))   // beta == 1, or rows the sparse branch leaves untouched
+      XB_CUDA(cudaMemcpy2DAsync(dC[slot], w * esz, (char*)C + n0 * esz, (size_t)ldc * esz, w * esz, M, cudaMemcpyHostToDevice, st[slot]));
+    fs_execute(op, dB[slot], dC[slot], w, w, w, st[slot]);
+    XB_CUDA(cudaMemcpy2DAsync((char*)C + n0 * esz, (size_t)ldc * esz, dC[slot], w * esz, w * esz, M, cudaMemcpyDeviceToHost, st[slot]));
+  }
+  for (int s = 0; s < kSlots; ++s) XB_CUDA(cudaStreamSynchronize(st[s]));
+}
+
+libxsmm_dfsspmdm* libxsmm_dfsspmdm_create(libxsmm_blasint M, libxsmm_blasint N, libxsmm_blasint K,
+  libxsmm_blasint lda, libxsmm_blasint ldb, libxsmm_blasint ldc, const double alpha, const double beta, const double* a_dense)
+{
+  if (!(1.0 == alpha)) { set_error(-31, "dfsspmdm_create: alpha must be 1 (reference src/libxsmm_fsspmdm.c:67)"); return 0; }
+  return (libxsmm_dfsspmdm*)fs_create(1, M, N, K, lda, ldb, ldc, beta, a_dense);
+}
+
+void libxsmm_dfsspmdm_execute(const libxsmm_dfsspmdm* handle, const double* B, double* C) { fs_execute_any((const FsOperator*)handle, B, C); }
+void libxsmm_dfsspmdm_destroy(libxsmm_dfsspmdm* handle) { fs_destroy((FsOperator*)handle); }
+
+libxsmm_sfsspmdm* libxsmm_sfsspmdm_create(libxsmm_blasint M, libxsmm_blasint N, libxsmm_blasint K,
+  libxsmm_blasint lda, libxsmm_blasint ldb, libxsmm_blasint ldc, const float alpha, const float beta, const float* a_dense)
+{
+  if (!(1.f == alpha)) { set_error(-31, "sfsspmdm_create: alpha must be 1 (reference src/libxsmm_fsspmdm.c:173)"); return 0; }
+  return (libxsmm_sfsspmdm*)fs_create(0, M, N, K, lda, ldb, ldc, (double)beta, a_dense);
+}
+
+void libxsmm_sfsspmdm_execute(const libxsmm_sfsspmdm* handle, const float* B, float* C) { fs_execute_any((const FsOperator*)handle, B, C); }
+void libxsmm_sfsspmdm_destroy(libxsmm_sfsspmdm* handle) { fs_destroy((FsOperator*)handle); }
+
+void libxsmm_dfsspmdm_execute_stream(const libxsmm_dfsspmdm* handle, const double* d_B, double* d_C, void* stream)
+{
+  const FsOperator* op = (const FsOperator*)handle;
+  if (0 == op) { set_error(-30, "fsspmdm_execute_stream: NULL handle"); return; }
+  int M, N, K, ldb, ldc, b1;
+  fs_shape(op, &M, &N, &K, &ldb, &ldc, &b1);
+  fs_execute(op, d_B, d_C, N, ldb, ldc, (cudaStream_t)stream);
+}
+
+void libxsmm_sfsspmdm_execute_stream(const libxsmm_sfsspmdm* handle, const float* d_B, float* d_C, void* stream)
+{
+  const FsOperator* op = (const FsOperator*)handle;
+  if (0 == op) { set_error(-30, "fsspmdm_execute_stream: NULL handle"); return; }
+  int M, N, K, ldb, ldc, b1;
+  fs_shape(op, &M, &N, &K, &ldb, &ldc, &b1);
+  fs_execute(op, d_B, d_C, N, ldb, ldc, (cudaStream_t)stream);
+}
+
+int libxsmm_dfsspmdm_is_sparse(const libxsmm_dfsspmdm* handle) { return fs_is_sparse_branch((const FsOperator*)handle); }
+int libxsmm_sfsspmdm_is_sparse(const libxsmm_sfsspmdm* handle) { return fs_is_sparse_branch((const FsOperator*)handle); }
+int libxsmm_dfsspmdm_is_baked(const libxsmm_dfsspmdm* handle) { return fs_is_baked((const FsOperator*)handle); }
+int libxsmm_sfsspmdm_is_baked(const libxsmm_sfsspmdm* handle) { return fs_is_baked((const FsOperator*)handle); }
+
+// =====================================================================================================
+// service
+// =====================================================================================================
+int libxsmm_b200_last_error(void) { std::lock_guard<std::mutex> lock(g_err_mtx); return g_err_code; }
+const char* libxsmm_b200_last_error_string(void) { return g_err_msg; }
+void libxsmm_b200_clear_error(void) { std::lock_guard<std::mutex> lock(g_err_mtx); g_err_code = 0; g_err_msg[0] = 0; }
+unsigned long long libxsmm_b200_launch_count(void) { return g_launches.load(); }
+
+void* libxsmm_b200_host_alloc(size_t bytes)
+{
+  void* p = 0;
+  if (cudaSuccess != cudaMallocHost(&p, bytes)) { (void)cudaGetLastError(); set_error(-40, "host_alloc(%zu) failed", bytes); return 0; }
+  return p;
+}
+void libxsmm_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void* libxsmm_b200_device_alloc(size_t bytes)
+{
+  void* p = 0;
+  if (cudaSuccess != cudaMalloc(&p, bytes ? bytes : 1)) { (void)cudaGetLastError(); set_error(-41, "device_alloc(%zu) failed", bytes); return 0; }
+  return p;
+}
+void libxsmm_b200_device_free(void* p) { if (p) cudaFree(p); }
+int libxsmm_b200_memcpy_h2d(void* d, const void* s, size_t n) { const cudaError_t e = cudaMemcpy(d, s, n, cudaMemcpyHostToDevice); if (e) set_error((int)e, "memcpy_h2d: %s", cudaGetErrorString(e)); return (int)e; }
+int libxsmm_b200_memcpy_d2h(void* d, const void* s, size_t n) { const cudaError_t e = cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost); if (e) set_error((int)e, "memcpy_d2h: %s", cudaGetErrorString(e)); return (int)e; }
+int libxsmm_b200_memset(void* d, int v, size_t n) { const cudaError_t e = cudaMemset(d, v, n); if (e) set_error((int)e, "memset: %s", cudaGetErrorString(e)); return (int)e; }
+int libxsmm_b200_synchronize(void) { const cudaError_t e = cudaDeviceSynchronize(); if (e) set_error((int)e, "synchronize: %s", cudaGetErrorString(e)); return (int)e; }
+int libxsmm_b200_device_count(void) { int n = 0; if (cudaSuccess != cudaGetDeviceCount(&n)) { (void)cudaGetLastError(); return 0; } return n; }
+int libxsmm_b200_set_device(int device) { const cudaError_t e = cudaSetDevice(device); if (e) set_error((int)e, "set_device: %s", cudaGetErrorString(e)); return (int)e; }
+
+void* libxsmm_b200_stream_create(void) { cudaStream_t s = 0; XB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return (void*)s; }
+void libxsmm_b200_stream_destroy(void* s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+int libxsmm_b200_stream_synchronize(void* s) { const cudaError_t e = cudaStreamSynchronize((cudaStream_t)s); if (e) set_error((int)e, "stream_synchronize: %s", cudaGetErrorString(e)); return (int)e; }
+void* libxsmm_b200_event_create(void) { cudaEvent_t ev = 0; XB_CUDA(cudaEventCreate(&ev)); return (void*)ev; }
+void libxsmm_b200_event_destroy(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+int libxsmm_b200_event_record(void* ev, void* s) { const cudaError_t e = cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)s); if (e) set_error((int)e, "event_record: %s", cudaGetErrorString(e)); return (int)e; }
+int libxsmm_b200_event_synchronize(void* ev) { const cudaError_t e = cudaEventSynchronize((cudaEvent_t)ev); if (e) set_error((int)e, "event_synchronize: %s", cudaGetErrorString(e)); return (int)e; }
+float libxsmm_b200_event_elapsed_ms(void* a, void* b) { float ms = -1.f; const cudaError_t e = cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b); if (e) { set_error((int)e, "event_elapsed: %s", cudaGetErrorString(e)); return -1.f; } return ms; }
+int libxsmm_b200_memcpy_h2d_async(void* d, const void* s, size_t n, void* st) { const cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, (cudaStream_t)st); if (e) set_error((int)e, "memcpy_h2d_async: %s", cudaGetErrorString(e)); return (int)e; }
+int libxsmm_b200_memcpy_d2h_async(void* d, const void* s, size_t n, void* st) { const cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st); if (e) set_error((int)e, "memcpy_d2h_async: %s", cudaGetErrorString(e)); return (int)e; }
+int libxsmm_b200_memset_async(void* d, int v, size_t n, void* st) { const cudaError_t e = cudaMemsetAsync(d, v, n, (cudaStream_t)st); if (e) set_error((int)e, "memset_async: %s", cudaGetErrorString(e)); return (int)e; }
+int libxsmm_b200_graph_begin(void* st) { const cudaError_t e = cudaStreamBeginCapture((cudaStream_t)st, cudaStreamCaptureModeThreadLocal); if (e) set_error((int)e, "graph_begin: %s", cudaGetErrorString(e)); return (int)e; }
+void* libxsmm_b200_graph_end(void* st)
+{
+  cudaGraph_t g = 0; cudaGraphExec_t x = 0;
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t)st, &g);
+  if (cudaSuccess == e) e = cudaGraphInstantiate(&x, g, 0);
+  if (g) cudaGraphDestroy(g);
+  if (e) { set_error((int)e, "graph_end: %s", cudaGetErrorString(e)); return 0; }
+  return (void*)x;
+}
+int libxsmm_b200_graph_launch(void* x, void* st) { const cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)x, (cudaStream_t)st); if (e) set_error((int)e, "graph_launch: %s", cudaGetErrorString(e)); return (int)e; }
+void libxsmm_b200_graph_destroy(void* x) { if (x) cudaGraphExecDestroy((cudaGraphExec_t)x); }
+
+// ---- host-only planning entries (no CUDA calls; usable without a GPU) --------------------------------
+int libxsmm_b200_spmdm_geometry(int M, int N, int K, int max_threads, int bn, int* geom)
+{
+  if (M <= 0 || N <= 0 || K <= 0 || 0 == geom) return -1;
+  if (max_threads < 1) max_threads = 1;
+  Geom g;
+  spmdm_geometry(M, N, K, max_threads, bn, &g);
+  geom[0] = g.m; geom[1] = g.n; geom[2] = g.k; geom[3] = g.bm; geom[4] = g.bn; geom[5] = g.bk;
+  geom[6] = g.mb; geom[7] = g.nb; geom[8] = g.kb;
+  return 0;
+}
+
+int libxsmm_b200_fsspmdm_plan(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta,
+                              const void* a_dense, long long* info)
+{
+  FsOperator* o = fs_plan(is_double, M, N, K, lda, ldb, ldc, beta, a_dense);
+  if (0 == o) return -1;
+  if (info) fs_plan_info(o, info);
+  fs_destroy(o);
+  return 0;
+}
+
+char* libxsmm_b200_fsspmdm_kernel_source(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta,
+                                         const void* a_dense)
+{
+  FsOperator* o = fs_plan(is_double, M, N, K, lda, ldb, ldc, beta, a_dense);
+  if (0 == o) return 0;
+  char* src = fs_kernel_source(o);
+  fs_destroy(o);
+  return src;
+}
+
+void libxsmm_b200_free_string(char* s) { free(s); }
+
+}  // extern "C"

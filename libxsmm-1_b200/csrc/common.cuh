@@ -1,0 +1,88 @@
+// Shared declarations of the B200-native SPMDM / FSSPMDM implementation (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace xb {
+
+// ---- sticky error state (reference entry points return void: src/libxsmm_spmdm.c:140-142) ----
+void set_error(int code, const char* fmt, ...);
+int verbosity();
+void count_launch(int n);
+
+#define XB_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t xb_e_ = (call);                                                            \
+    if (cudaSuccess != xb_e_) {                                                            \
+      xb::set_error((int)xb_e_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,              \
+                    cudaGetErrorString(xb_e_));                                            \
+    }                                                                                      \
+  } while (0)
+
+// ---- SPMDM ----------------------------------------------------------------------------------
+// Block geometry, same meaning as the fields of libxsmm_spmdm_handle
+// (reference include/libxsmm_spmdm.h:42-60).
+struct Geom { int m, n, k, bm, bn, bk, mb, nb, kb; };
+
+// Flat device layout of the CSR slice arena.  Slice s = kb*mb + mb owns
+//   rowidx[s*(bm+1) ..], colidx[s*bm*bk ..], values[s*bm*bk ..]
+// (same logical arrays as reference src/libxsmm_spmdm.c:126-136; the byte packing differs
+// because the reference leaves `values` only 2-byte aligned).
+struct SliceArena {
+  uint16_t* rowidx;
+  uint16_t* colidx;
+  float* values;
+};
+
+constexpr int kSliceStripRows = 64;   // rows of one slice handled by one CTA of the slicing kernel
+
+struct SliceArgs {
+  const void* a;        // dense A (float or bf16 bits)
+  long long lda;        // elements between consecutive rows ('N') or consecutive k ('T')
+  int transa;           // 0: A is m x k row-major, 1: A is stored k x m
+  int is_bf16;
+  int origin_is_block;  // 1: `a` already points at the block's first element (legacy staged block)
+  int slice0;           // slice handled by blockIdx.y == 0
+  int simd_w;           // vector width of the reference instantiation mirrored (NaN rule)
+  Geom g;
+  SliceArena out;
+};
+
+// mode boundaries of the reference's narrow last block (compute template :72-76,372-434)
+struct ColModes { int n_full_end; int tail_from; };
+
+struct ComputeArgs {
+  SliceArena sl;
+  const void* b;      // local column 0 / k 0
+  long long ldb;      // 'N': elements between k rows; 'T': elements between n rows
+  float* c;           // local row 0 / local column 0
+  long long ldc;      // 'N': elements between m rows; 'T': elements between n rows
+  int transb, transc, is_bf16;
+  float beta;
+  Geom g;
+  int mb_first, mb_count;   // row blocks computed
+  int row_origin;           // global row that local C row 0 corresponds to
+  int col_origin;           // global column that local column 0 corresponds to
+  int ncols;                // local columns computed
+  ColModes modes;           // in GLOBAL column numbering
+};
+
+void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream);
+void launch_compute(const ComputeArgs& args, cudaStream_t stream);
+
+// ---- FSSPMDM --------------------------------------------------------------------------------
+struct FsOperator;   // fsspmdm.cu
+FsOperator* fs_plan(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta, const void* a_dense);   // host only
+void fs_plan_info(const FsOperator* o, long long* info);
+char* fs_kernel_source(const FsOperator* o);
+FsOperator* fs_create(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta, const void* a_dense);
+void fs_execute(const FsOperator* op, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream);
+int fs_is_sparse_branch(const FsOperator* o);
+int fs_is_baked(const FsOperator* o);
+int fs_needs_c_input(const FsOperator* o);
+int fs_is_double(const FsOperator* o);
+void fs_shape(const FsOperator* o, int* M, int* N, int* K, int* ldb, int* ldc, int* beta_one);
+void fs_destroy(FsOperator* op);
+
+}  // namespace xb

@@ -1,0 +1,274 @@
+// FSSPMDM: a fixed sparse operator A (M x K) baked at create time, applied to a dense B with
+// very many columns:  C[:, 0:N] = A * B[:, 0:N] + beta * C   (beta in {0,1}).
+// Replaces reference src/libxsmm_fsspmdm.c (create :48-257, execute :260-291, destroy :294-329)
+// and the kernel emitted by src/generator_spgemm_csr_asparse_reg.c:196-300.
+#include "common.cuh"
+#include "fsspmdm_jit.h"
+#include <vector>
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <cstdio>
+
+namespace xb {
+
+struct FsOperator {
+  // leading fields mirror the reference's private handle (src/libxsmm_main.h:695-715) so that code
+  // peeking at M/N/K/ldb/ldc/N_chunksize/a_dense keeps working; a_dense == NULL <=> sparse branch.
+  int M, N, K, ldb, ldc, N_chunksize;
+  void* a_dense;      // DEVICE copy of the packed M x K operator (dense branch only)
+  void* kernel;       // opaque: the baked kernel (FsJit*) or NULL
+  // ---- private ----
+  int is_double;
+  int beta_one;
+  int sparse_branch;  // the branch the reference would take (decides empty-row behaviour)
+  int nnz, n_unique;
+  long long x86_code_size;   // bytes the reference's generator would emit (0 if not evaluated)
+  int* d_rowptr;      // M+1
+  int* d_col;         // per nonzero: column index
+  void* d_val;        // per nonzero: value as executed (double or float)
+  std::vector<int> rowptr, col;
+  std::vector<double> val;
+  FsJit* jit;
+};
+
+// ---- branch rule of the reference ------------------------------------------------------------------
+// x86 bytes the reference's sparse_reg generator would emit; the sparse branch exists only while this
+// fits its 128 KiB JIT buffer (src/libxsmm_main.c:66-67).  Displacement sizes follow the encoder
+// (src/generator_x86_instructions.c:52-77): none if 0, one byte if a multiple of the operand size
+// within +-127 units, else four.  Byte-exact against the reference (tests pin the threshold).
+static int fs_disp(long long off, int unit)
+{
+  if (0 == off) return 0;
+  if (0 == (off % unit) && off / unit <= 127 && off / unit >= -128) return 1;
+  return 4;
+}
+static long long fs_x86_code_size(const FsOperator& o)
+{
+  long long sz = 40 + (long long)o.n_unique * 76;
+  for (int m = 0; m < o.M; ++m) {
+    const int lo = o.rowptr[m], hi = o.rowptr[m + 1];
+    const long long coff = (long long)m * o.ldc * 8;
+    if (hi == lo) continue;
+    sz += o.beta_one ? (6 + fs_disp(coff, 64)) : 6;
+    sz += 3 + fs_disp(coff + 64, 1);
+    for (int u = lo; u < hi; ++u) {
+      const long long boff = (long long)o.col[u] * o.ldb * 8;
+      sz += 6 + fs_disp(boff, 64) + 3 + fs_disp(boff + 64, 1);
+    }
+    sz += 6 + fs_disp(coff, 64);
+  }
+  return sz;
+}
+
+// ---- generic kernel: operator streamed from global memory (warp-uniform addresses), B through L1 ----
+struct FsDev {
+  int M, beta_one, skip_empty;
+  long long ldb, ldc;
+  const int* rowptr;
+  const int* col;
+  const void* val;
+};
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) fs_generic_kernel(const FsDev p, const T* __restrict__ B, T* __restrict__ C, long long ncols)
+{
+  const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (n >= ncols) return;
+  const T* __restrict__ val = (const T*)p.val;
+  const T* Bn = B + n;
+  for (int m = 0; m < p.M; ++m) {
+    const int lo = __ldg(p.rowptr + m), hi = __ldg(p.rowptr + m + 1);
+    if (hi == lo && p.skip_empty) continue;
+    T* crow = C + (long long)m * p.ldc + n;
+    T acc[VEC];
+    if (p.beta_one) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] = (n + e < ncols) ? crow[e] : (T)0;
+    }
+    else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] = (T)0;
+    }
+    for (int j = lo; j < hi; ++j) {
+      const T v = __ldg(val + j);
+      const T* brow = Bn + (long long)__ldg(p.col + j) * p.ldb;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T b = (n + e < ncols) ? __ldg(brow + e) : (T)0;
+        acc[e] = fma(v, b, acc[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) if (n + e < ncols) crow[e] = acc[e];
+  }
+}
+
+// ---- create -------------------------------------------------------------------------------------------
+template <typename T>
+static void fs_build_csr(FsOperator& o, const T* a, int lda)
+{
+  o.rowptr.assign(o.M + 1, 0);
+  for (int i = 0; i < o.M; ++i) {
+    o.rowptr[i] = (int)o.col.size();
+    for (int j = 0; j < o.K; ++j) {
+      const T v = a[(size_t)i * lda + j];
+      if (v != (T)0) { o.col.push_back(j); o.val.push_back((double)v); }   // NaN kept, -0 dropped (:88-116)
+    }
+  }
+  o.rowptr[o.M] = (int)o.col.size();
+  o.nnz = (int)o.col.size();
+}
+
+// Host-only part of create(): contract check, CSR, unique-value table, branch rule.  No CUDA calls,
+// so that it can be exercised (and is, tests/test_host_logic.py) on a machine without a GPU.
+FsOperator* fs_plan(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta, const void* a_dense)
+{
+  // the reference asserts this contract (src/libxsmm_fsspmdm.c:65-71) and calls a NULL kernel when it
+  // is violated in a release build; here a violation is an error and create returns NULL.
+  if (M <= 0 || K <= 0 || N < 16 || 0 != (N % 16) || K > lda || N > ldb || N > ldc || 0 == a_dense
+      || !(beta == 0.0 || beta == 1.0)) {
+    set_error(-1, "fsspmdm_create: contract violated (M=%d N=%d K=%d lda=%d ldb=%d ldc=%d beta=%g)", M, N, K, lda, ldb, ldc, beta);
+    return 0;
+  }
+  FsOperator* o = new FsOperator();
+  o->M = M; o->N = N; o->K = K; o->ldb = ldb; o->ldc = ldc;
+  o->a_dense = 0; o->kernel = 0; o->jit = 0;
+  o->is_double = is_double; o->beta_one = (1.0 == beta);
+  o->d_rowptr = 0; o->d_col = 0; o->d_val = 0;
+  if (is_double) fs_build_csr(*o, (const double*)a_dense, lda); else fs_build_csr(*o, (const float*)a_dense, lda);
+
+  // unique-value table of the sparse_reg generator (:125-150); for a NaN value the search "hits"
+  // every entry and the LAST one wins, i.e. the emitted kernel multiplies with that entry instead.
+  o->n_unique = 0;
+  o->sparse_branch = 0;
+  o->x86_code_size = 0;
+  if (is_double && o->nnz > 0) {
+    std::vector<double> table;
+    std::vector<double> exec_val(o->val);
+    table.push_back(o->val[0]);
+    for (int u = 1; u < o->nnz && (int)table.size() <= 32; ++u) {
+      int hit = -1;
+      for (int z = 0; z < (int)table.size(); ++z) if (!(table[z] < o->val[u]) && !(table[z] > o->val[u])) hit = z;
+      if (hit < 0) table.push_back(o->val[u]); else exec_val[u] = table[hit];
+    }
+    o->n_unique = (int)table.size();
+    if (o->n_unique <= 31) {
+      o->x86_code_size = fs_x86_code_size(*o);
+      if (o->x86_code_size <= 131072) {
+        o->sparse_branch = 1;
+        o->val.swap(exec_val);
+      }
+    }
+  }
+  o->N_chunksize = o->sparse_branch ? 8 : 16;   // what the reference reports (:119,133,225,239)
+  return o;
+}
+
+FsOperator* fs_create(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta, const void* a_dense)
+{
+  FsOperator* o = fs_plan(is_double, M, N, K, lda, ldb, ldc, beta, a_dense);
+  if (0 == o) return 0;
+
+  // device side of the operator
+  const size_t nalloc = (size_t)(o->nnz > 0 ? o->nnz : 1);
+  XB_CUDA(cudaMalloc(&o->d_rowptr, sizeof(int) * (M + 1)));
+  XB_CUDA(cudaMalloc(&o->d_col, sizeof(int) * nalloc));
+  XB_CUDA(cudaMalloc(&o->d_val, 8 * nalloc));
+  if (0 == o->d_rowptr || 0 == o->d_col || 0 == o->d_val) { fs_destroy(o); return 0; }
+  XB_CUDA(cudaMemcpy(o->d_rowptr, o->rowptr.data(), sizeof(int) * (M + 1), cudaMemcpyHostToDevice));
+  if (o->nnz > 0) XB_CUDA(cudaMemcpy(o->d_col, o->col.data(), sizeof(int) * (size_t)o->nnz, cudaMemcpyHostToDevice));
+  if (o->nnz > 0) {
+    if (is_double) XB_CUDA(cudaMemcpy(o->d_val, o->val.data(), 8 * (size_t)o->nnz, cudaMemcpyHostToDevice));
+    else {
+      std::vector<float> vf(o->val.begin(), o->val.end());
+      XB_CUDA(cudaMemcpy(o->d_val, vf.data(), 4 * (size_t)o->nnz, cudaMemcpyHostToDevice));
+    }
+  }
+  if (!o->sparse_branch) {   // dense branch keeps a packed copy of A like the reference (:136-142)
+    const size_t esz = is_double ? 8 : 4;
+    std::vector<char> packed((size_t)M * K * esz);
+    for (int i = 0; i < M; ++i) memcpy(&packed[(size_t)i * K * esz], (const char*)a_dense + (size_t)i * lda * esz, (size_t)K * esz);
+    XB_CUDA(cudaMalloc(&o->a_dense, packed.size()));
+    if (o->a_dense) XB_CUDA(cudaMemcpy(o->a_dense, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  }
+  // bake the operator into a specialised kernel (the GPU counterpart of the reference's JIT)
+  o->jit = fs_jit_build(is_double, M, K, o->beta_one, o->sparse_branch /*skip empty rows*/,
+                        o->rowptr.data(), o->col.data(), o->val.data());
+  o->kernel = o->jit;
+  if (verbosity() > 0) {
+    fprintf(stderr, "LIBXSMM_B200 fsspmdm: %dx%d nnz=%d unique=%d branch=%s kernel=%s\n", M, K, o->nnz, o->n_unique,
+            o->sparse_branch ? "sparse" : "dense", o->jit ? "baked" : "generic");
+  }
+  return o;
+}
+
+void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream)
+{
+  if (0 == o || ncols <= 0) return;
+  count_launch(1);
+  if (o->jit && fs_jit_launch(o->jit, dB, dC, ncols, ldb, ldc, stream)) return;
+  FsDev d;
+  d.M = o->M; d.beta_one = o->beta_one; d.skip_empty = o->sparse_branch;
+  d.ldb = ldb; d.ldc = ldc; d.rowptr = o->d_rowptr; d.col = o->d_col; d.val = o->d_val;
+  const int threads = 256;
+  if (o->is_double) {
+    const bool v2 = (0 == (ldb & 1)) && (0 == (ldc & 1)) && (0 == (((uintptr_t)dB | (uintptr_t)dC) & 15));
+    if (v2) {
+      const long long blocks = (ncols + 2 * threads - 1) / (2 * threads);
+      fs_generic_kernel<double, 2><<<(unsigned)blocks, threads, 0, stream>>>(d, (const double*)dB, (double*)dC, ncols);
+    }
+    else {
+      const long long blocks = (ncols + threads - 1) / threads;
+      fs_generic_kernel<double, 1><<<(unsigned)blocks, threads, 0, stream>>>(d, (const double*)dB, (double*)dC, ncols);
+    }
+  }
+  else {
+    const bool v4 = (0 == (ldb & 3)) && (0 == (ldc & 3)) && (0 == (((uintptr_t)dB | (uintptr_t)dC) & 15));
+    if (v4) {
+      const long long blocks = (ncols + 4 * threads - 1) / (4 * threads);
+      fs_generic_kernel<float, 4><<<(unsigned)blocks, threads, 0, stream>>>(d, (const float*)dB, (float*)dC, ncols);
+    }
+    else {
+      const long long blocks = (ncols + threads - 1) / threads;
+      fs_generic_kernel<float, 1><<<(unsigned)blocks, threads, 0, stream>>>(d, (const float*)dB, (float*)dC, ncols);
+    }
+  }
+  XB_CUDA(cudaGetLastError());
+}
+
+void fs_destroy(FsOperator* o)
+{
+  if (0 == o) return;
+  if (o->jit) fs_jit_destroy(o->jit);
+  if (o->d_rowptr) cudaFree(o->d_rowptr);
+  if (o->d_col) cudaFree(o->d_col);
+  if (o->d_val) cudaFree(o->d_val);
+  if (o->a_dense) cudaFree(o->a_dense);
+  delete o;
+}
+
+int fs_is_sparse_branch(const FsOperator* o) { return o ? o->sparse_branch : 0; }
+int fs_is_baked(const FsOperator* o) { return (o && o->jit) ? 1 : 0; }
+int fs_needs_c_input(const FsOperator* o)
+{
+  if (0 == o) return 0;
+  if (o->beta_one) return 1;
+  if (o->sparse_branch) for (int m = 0; m < o->M; ++m) if (o->rowptr[m] == o->rowptr[m + 1]) return 1;   // untouched rows
+  return 0;
+}
+int fs_is_double(const FsOperator* o) { return o ? o->is_double : 0; }
+void fs_plan_info(const FsOperator* o, long long* info)
+{
+  info[0] = o->nnz; info[1] = o->n_unique; info[2] = o->sparse_branch; info[3] = o->x86_code_size; info[4] = o->N_chunksize;
+}
+char* fs_kernel_source(const FsOperator* o)
+{
+  return fs_jit_source(o->is_double, o->M, o->K, o->beta_one, o->sparse_branch, o->rowptr.data(), o->col.data(), o->val.data());
+}
+void fs_shape(const FsOperator* o, int* M, int* N, int* K, int* ldb, int* ldc, int* beta_one)
+{
+  *M = o->M; *N = o->N; *K = o->K; *ldb = o->ldb; *ldc = o->ldc; *beta_one = o->beta_one;
+}
+
+}  // namespace xb

@@ -1,0 +1,207 @@
+// Create-time kernel baking for FSSPMDM through NVRTC (loaded lazily with dlopen so that the
+// library itself loads on machines without a CUDA toolkit; create() then falls back to the generic
+// kernel and records the reason).  The compiled cubin is loaded with the CUDA runtime's library API.
+#include "fsspmdm_jit.h"
+#include "common.cuh"
+#include <nvrtc.h>
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <mutex>
+
+namespace xb {
+
+struct FsJit {
+  cudaLibrary_t lib;
+  cudaKernel_t kern;
+  int block;
+  int cols_per_thread;
+};
+
+namespace {
+
+struct Nvrtc {
+  void* h;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+};
+
+Nvrtc* nvrtc()
+{
+  static Nvrtc api;
+  static int state = 0;   // 0 unknown, 1 ok, -1 unavailable
+  static std::mutex mtx;
+  std::lock_guard<std::mutex> lock(mtx);
+  if (0 == state) {
+    const char* names[] = { "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so" };
+    api.h = 0;
+    for (size_t i = 0; i < sizeof(names) / sizeof(*names) && 0 == api.h; ++i) api.h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+    state = -1;
+    if (api.h) {
+      *(void**)&api.CreateProgram = dlsym(api.h, "nvrtcCreateProgram");
+      *(void**)&api.CompileProgram = dlsym(api.h, "nvrtcCompileProgram");
+      *(void**)&api.GetCUBINSize = dlsym(api.h, "nvrtcGetCUBINSize");
+      *(void**)&api.GetCUBIN = dlsym(api.h, "nvrtcGetCUBIN");
+      *(void**)&api.GetProgramLogSize = dlsym(api.h, "nvrtcGetProgramLogSize");
+      *(void**)&api.GetProgramLog = dlsym(api.h, "nvrtcGetProgramLog");
+      *(void**)&api.DestroyProgram = dlsym(api.h, "nvrtcDestroyProgram");
+      if (api.CreateProgram && api.CompileProgram && api.GetCUBINSize && api.GetCUBIN && api.DestroyProgram) state = 1;
+    }
+  }
+  return 1 == state ? &api : 0;
+}
+
+const int kBlock = 128;
+
+void append(std::string& s, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  s += buf;
+}
+
+// The emitted kernel: one thread per column of B/C.  Every B row that the operator touches is loaded
+// once into a named register (coalesced across the warp), every output row is then an in-order chain
+// of fused multiply-adds with literal operator values -- the rounding sequence of the reference's
+// emitted kernel (generator :227-300) -- and is stored as soon as it is complete.
+std::string emit(int is_double, int M, int K, int beta_one, int skip_empty,
+                 const int* rowptr, const int* col, const double* val)
+{
+  const char* T = is_double ? "double" : "float";
+  std::vector<char> used(K, 0);
+  for (int u = 0; u < rowptr[M]; ++u) used[col[u]] = 1;
+  std::string s;
+  s.reserve(64 * (size_t)rowptr[M] + 4096);
+  append(s, "extern \"C\" __global__ void __launch_bounds__(%d) fs_baked(const %s* __restrict__ B, %s* __restrict__ C, long long ncols, long long ldb, long long ldc)\n{\n", kBlock, T, T);
+  append(s, "  const long long n = (long long)blockIdx.x * %d + threadIdx.x;\n  if (n >= ncols) return;\n", kBlock);
+  append(s, "  const %s* __restrict__ b = B + n;\n  %s* __restrict__ c = C + n;\n  %s acc;\n", T, T, T);
+  for (int k = 0; k < K; ++k) if (used[k]) append(s, "  const %s b%d = __ldg(b + %dLL * ldb);\n", T, k, k);
+  for (int m = 0; m < M; ++m) {
+    const int lo = rowptr[m], hi = rowptr[m + 1];
+        if (hi == lo) {
+      if (!skip_empty && !beta_one) append(s, "  c[%dLL * ldc] = 0;\n", m);
+      continue;
+    }
+    if (beta_one) append(s, "  acc = c[%dLL * ldc];\n", m); else append(s, "  acc = 0;\n");
+    for (int u = lo; u < hi; ++u) {
+      if (is_double) {
+        long long bits; const double v = val[u];
+        memcpy(&bits, &v, 8);
+        append(s, "  acc = fma(__longlong_as_double(0x%016llxLL), b%d, acc);\n", (unsigned long long)bits, col[u]);
+      }
+      else {
+        int bits; const float v = (float)val[u];
+        memcpy(&bits, &v, 4);
+        append(s, "  acc = fmaf(__int_as_float(0x%08x), b%d, acc);\n", (unsigned)bits, col[u]);
+      }
+    }
+    append(s, "  c[%dLL * ldc] = acc;\n", m);
+  }
+  s += "}\n";
+  return s;
+}
+
+bool supported(int is_double, int M, int K, const int* rowptr, const int* col)
+{
+  std::vector<char> used(K, 0);
+  int nused = 0;
+  for (int u = 0; u < rowptr[M]; ++u) if (!used[col[u]]) { used[col[u]] = 1; ++nused; }
+  // B rows live in registers: 2 registers per double, 1 per float, out of 255
+  return rowptr[M] > 0 && (is_double ? nused <= 100 : nused <= 200) && rowptr[M] <= 60000;
+}
+
+std::mutex g_cache_mtx;
+std::map<std::string, std::vector<char> > g_cubin_cache;
+
+}  // namespace
+
+char* fs_jit_source(int is_double, int M, int K, int beta_one, int skip_empty,
+                    const int* rowptr, const int* col, const double* val)
+{
+  const std::string s = emit(is_double, M, K, beta_one, skip_empty, rowptr, col, val);
+  char* out = (char*)malloc(s.size() + 1);
+  if (out) memcpy(out, s.c_str(), s.size() + 1);
+  return out;
+}
+
+FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty,
+                    const int* rowptr, const int* col, const double* val)
+{
+  const char* env = getenv("LIBXSMM_B200_FSSPMDM_JIT");
+  if (env && '0' == *env) return 0;
+  if (!supported(is_double, M, K, rowptr, col)) return 0;
+  Nvrtc* rt = nvrtc();
+  if (0 == rt) { set_error(-2, "fsspmdm: NVRTC (libnvrtc.so.12) not found; using the generic kernel"); return 0; }
+  const std::string src = emit(is_double, M, K, beta_one, skip_empty, rowptr, col, val);
+  std::vector<char> cubin;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mtx);
+    std::map<std::string, std::vector<char> >::const_iterator it = g_cubin_cache.find(src);
+    if (it != g_cubin_cache.end()) cubin = it->second;
+  }
+  if (cubin.empty()) {
+    nvrtcProgram prog = 0;
+    if (NVRTC_SUCCESS != rt->CreateProgram(&prog, src.c_str(), "fs_baked.cu", 0, 0, 0)) { set_error(-3, "nvrtcCreateProgram failed"); return 0; }
+    const char* opts[] = { "--gpu-architecture=sm_100a", "-lineinfo", "--fmad=false" };
+    const nvrtcResult rc = rt->CompileProgram(prog, 3, opts);
+    if (NVRTC_SUCCESS != rc) {
+      size_t n = 0;
+      std::string log;
+      if (rt->GetProgramLogSize && NVRTC_SUCCESS == rt->GetProgramLogSize(prog, &n) && n > 1) { log.resize(n); rt->GetProgramLog(prog, &log[0]); }
+      set_error(-4, "fsspmdm: NVRTC compile failed (%d): %.300s", (int)rc, log.c_str());
+      rt->DestroyProgram(&prog);
+      return 0;
+    }
+    size_t sz = 0;
+    if (NVRTC_SUCCESS != rt->GetCUBINSize(prog, &sz) || 0 == sz) { set_error(-5, "nvrtcGetCUBINSize failed"); rt->DestroyProgram(&prog); return 0; }
+    cubin.resize(sz);
+    rt->GetCUBIN(prog, cubin.data());
+    rt->DestroyProgram(&prog);
+    std::lock_guard<std::mutex> lock(g_cache_mtx);
+    g_cubin_cache[src] = cubin;
+  }
+  FsJit* j = new FsJit();
+  j->block = kBlock;
+  j->cols_per_thread = 1;
+  cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), 0, 0, 0, 0, 0, 0);
+  if (cudaSuccess == e) e = cudaLibraryGetKernel(&j->kern, j->lib, "fs_baked");
+  if (cudaSuccess != e) {
+    set_error((int)e, "fsspmdm: loading the baked kernel failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    delete j;
+    return 0;
+  }
+  return j;
+}
+
+bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream)
+{
+  const long long per_block = (long long)j->block * j->cols_per_thread;
+  const long long blocks = (ncols + per_block - 1) / per_block;
+  void* args[] = { (void*)&dB, (void*)&dC, (void*)&ncols, (void*)&ldb, (void*)&ldc };
+  const cudaError_t e = cudaLaunchKernel((const void*)j->kern, dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, 0, stream);
+  if (cudaSuccess != e) { set_error((int)e, "fsspmdm: baked kernel launch failed: %s", cudaGetErrorString(e)); return false; }
+  return true;
+}
+
+void fs_jit_destroy(FsJit* j)
+{
+  if (0 == j) return;
+  cudaLibraryUnload(j->lib);
+  delete j;
+}
+
+}  // namespace xb

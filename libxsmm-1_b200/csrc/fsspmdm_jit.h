@@ -1,0 +1,18 @@
+// Baking a fixed sparse operator into a specialised sm_100a kernel at create time -- the GPU
+// counterpart of the reference's x86 JIT (src/generator_spgemm_csr_asparse_reg.c:196-300): A's
+// values become immediates, A's column indices become register names, B's rows live in registers.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace xb {
+struct FsJit;
+// returns NULL when the operator is outside what the baked kernel supports (the caller then uses the
+// generic kernel) or when NVRTC is not available (reported through set_error).
+FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty_rows,
+                    const int* rowptr, const int* col, const double* val);
+bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream);
+void fs_jit_destroy(FsJit* j);
+// the CUDA source that would be compiled (for tests / inspection); caller frees with free()
+char* fs_jit_source(int is_double, int M, int K, int beta_one, int skip_empty_rows,
+                    const int* rowptr, const int* col, const double* val);
+}  // namespace xb

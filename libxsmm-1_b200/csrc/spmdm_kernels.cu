@@ -1,0 +1,508 @@
+// SPMDM kernels for sm_100a:
+//   K1  spmdm_slice_kernel    dense A -> CSR slices   (reference createSparseSlice templates)
+//   K2  spmdm_compute_kernel  C = beta*C + slices * B (reference compute templates)
+// Hand-written CUDA; no library calls on the data path.
+#include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace xb {
+
+// =================================================================================================
+// K1: slice compaction.
+// One cluster of CTAs per slice (bm x 128 block of A), one CTA per strip of 64 rows.  The strip
+// is staged once in shared memory (coalesced 16-byte loads; transposed on the fly for transa='T'),
+// every warp then owns rows: 4 ballots per row give the per-lane exclusive prefix in ascending
+// column order, a warp scan gives row offsets inside the strip, and strip totals are exchanged
+// between the CTAs of the cluster through distributed shared memory so that every CTA knows its
+// base offset inside the slice without a second kernel.
+// Bit-exact with reference src/template/libxsmm_spmdm_createSparseSlice_{fp32,bfloat16}_thread.tpl.c:
+// row pointers, column indices and values in [0, nnz) of every slice.
+// =================================================================================================
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_R = kSliceStripRows;
+constexpr int K1_TPITCH = K1_R + 1;   // pitch of the transposed tile (conflict-free column reads)
+
+// Non-zero test of the reference: vector loops use an ordered compare (NaN dropped,
+// src/libxsmm_spmdm_begin_avx2.h:54), the scalar remainder keeps NaN (fp32 tpl.c:129-133).
+__device__ __forceinline__ bool k1_keep(float v, int k, int vec_end)
+{
+  return (v < 0.f || v > 0.f) || (k >= vec_end && v != v);
+}
+
+__global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs p)
+{
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ __align__(16) uint32_t tile[128 * K1_TPITCH];
+  __shared__ uint32_t row_cnt[K1_R];
+  __shared__ uint32_t row_off[K1_R];
+  __shared__ uint32_t strip_tot[8];
+
+  const Geom& g = p.g;
+  const int s = p.slice0 + (int)blockIdx.y;
+  const int kb = s / g.mb, mbi = s - kb * g.mb;
+  const int nrows = min(g.bm, g.m - mbi * g.bm);
+  const int ncols = min(g.bk, g.k - kb * g.bk);
+  int vec_end = p.is_bf16 ? (ncols / (4 * p.simd_w)) * (4 * p.simd_w) : (ncols / p.simd_w) * p.simd_w;
+  if (p.simd_w <= 1) vec_end = 0;
+  const int strip = (int)blockIdx.x, nstrips = (int)gridDim.x;
+  const int r0 = strip * K1_R;
+  const int rcount = max(0, min(K1_R, nrows - r0));
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long origin = p.origin_is_block ? 0ll
+    : (p.transa ? ((long long)kb * g.bk * p.lda + (long long)mbi * g.bm)
+                : ((long long)mbi * g.bm * p.lda + (long long)kb * g.bk));
+
+  // ---- stage the strip: tile holds fp32 bit patterns (bf16 widened by <<16) --------------------
+  if (!p.transa) {
+    if (!p.is_bf16) {
+      const float* A = (const float*)p.a + origin + (long long)r0 * p.lda;
+      const bool vec = (0 == (p.lda & 3)) && (0 == ((uintptr_t)A & 15));
+      for (int idx = tid; idx < rcount * 32; idx += K1_THREADS) {
+        const int r = idx >> 5, k = (idx & 31) * 4;
+        const float* src = A + (long long)r * p.lda + k;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (vec && k + 3 < ncols) w = __ldg((const uint4*)src);
+        else {
+          if (k < ncols) w.x = __float_as_uint(__ldg(src));
+          if (k + 1 < ncols) w.y = __float_as_uint(__ldg(src + 1));
+          if (k + 2 < ncols) w.z = __float_as_uint(__ldg(src + 2));
+          if (k + 3 < ncols) w.w = __float_as_uint(__ldg(src + 3));
+        }
+        *(uint4*)&tile[r * 128 + k] = w;
+      }
+    }
+    else {
+      const uint16_t* A = (const uint16_t*)p.a + origin + (long long)r0 * p.lda;
+      const bool vec = (0 == (p.lda & 3)) && (0 == ((uintptr_t)A & 7));
+      for (int idx = tid; idx < rcount * 32; idx += K1_THREADS) {
+        const int r = idx >> 5, k = (idx & 31) * 4;
+        const uint16_t* src = A + (long long)r * p.lda + k;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (vec && k + 3 < ncols) {
+          const uint2 raw = __ldg((const uint2*)src);
+          w.x = raw.x << 16; w.y = raw.x & 0xFFFF0000u; w.z = raw.y << 16; w.w = raw.y & 0xFFFF0000u;
+        }
+        else {
+          if (k < ncols) w.x = (uint32_t)__ldg(src) << 16;
+          if (k + 1 < ncols) w.y = (uint32_t)__ldg(src + 1) << 16;
+          if (k + 2 < ncols) w.z = (uint32_t)__ldg(src + 2) << 16;
+          if (k + 3 < ncols) w.w = (uint32_t)__ldg(src + 3) << 16;
+        }
+        *(uint4*)&tile[r * 128 + k] = w;
+      }
+    }
+  }
+  else {  // A stored k x m: consecutive rows of the slice are contiguous in memory
+    for (int idx = tid; idx < ncols * K1_R; idx += K1_THREADS) {
+      const int k = idx / K1_R, r = idx - k * K1_R;
+      if (r < rcount) {
+        const long long at = origin + (long long)k * p.lda + r0 + r;
+        tile[k * K1_TPITCH + r] = p.is_bf16 ? ((uint32_t)__ldg((const uint16_t*)p.a + at) << 16)
+                                            : __float_as_uint(__ldg((const float*)p.a + at));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 1: per-row counts -------------------------------------------------------------------
+  for (int r = warp; r < rcount; r += K1_WARPS) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 32 * j + lane;
+      const float v = __uint_as_float(p.transa ? tile[k * K1_TPITCH + r] : tile[r * 128 + k]);
+      const bool keep = (k < ncols) && k1_keep(v, k, vec_end);
+      c += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (0 == lane) row_cnt[r] = c;
+  }
+  __syncthreads();
+
+  // ---- strip-local exclusive scan of the 64 row counts (warp 0, two rows per lane) ---------------
+  uint32_t total = 0;
+  if (0 == warp) {
+    const uint32_t a0 = (2 * lane < rcount) ? row_cnt[2 * lane] : 0u;
+    const uint32_t a1 = (2 * lane + 1 < rcount) ? row_cnt[2 * lane + 1] : 0u;
+    uint32_t inc = a0 + a1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    row_off[2 * lane] = inc - (a0 + a1);
+    row_off[2 * lane + 1] = inc - a1;
+    total = inc;   // valid in lane 31
+  }
+
+  // ---- exchange strip totals across the cluster (distributed shared memory) ----------------------
+  cluster.sync();   // every CTA of the cluster is resident before remote shared memory is touched
+  if (31 == tid) {
+    for (int q = 0; q < nstrips; ++q) *cluster.map_shared_rank(&strip_tot[strip], q) = total;
+  }
+  cluster.sync();
+  uint32_t base = 0;
+  for (int q = 0; q < strip; ++q) base += strip_tot[q];
+
+  // ---- pass 2: write row pointers, column indices, values ---------------------------------------
+  uint16_t* ro = p.out.rowidx + (size_t)s * (g.bm + 1);
+  uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
+  float* va = p.out.values + (size_t)s * g.bm * g.bk;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int r = warp; r < rcount; r += K1_WARPS) {
+    uint32_t pos = base + row_off[r];
+    if (0 == lane) ro[r0 + r] = (uint16_t)pos;   // u16 like the reference's counter (tpl.c:72,78)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 32 * j + lane;
+      const float v = __uint_as_float(p.transa ? tile[k * K1_TPITCH + r] : tile[r * 128 + k]);
+      const bool keep = (k < ncols) && k1_keep(v, k, vec_end);
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const uint32_t q = pos + __popc(bal & lt);
+        co[q] = (uint16_t)k;
+        va[q] = v;
+      }
+      pos += __popc(bal);
+    }
+  }
+  if (strip == nstrips - 1 && 0 == tid) ro[nrows] = (uint16_t)(base + strip_tot[strip]);
+}
+
+void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
+{
+  if (nslices <= 0) return;
+  const int nstrips = (args.g.bm + K1_R - 1) / K1_R;   // <= 8 because bm <= 512
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)nstrips, (unsigned)nslices, 1);
+  cfg.blockDim = dim3(K1_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)nstrips;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch(1);
+  XB_CUDA(cudaLaunchKernelEx(&cfg, spmdm_slice_kernel, args));
+}
+
+// =================================================================================================
+// K2: sliced SpMM.
+// CTA = 16 warps x RPW rows of one row block (mb) x BN = 32*VEC columns.  Per k-block the
+// 128 x BN panel of B is staged in shared memory (double buffered, cp.async 16-byte copies;
+// transposed on the fly for transb='T'; bf16 kept as bf16 and widened in registers).  A warp
+// owns RPW consecutive rows -- their nonzeros are contiguous in the slice, so the warp fetches
+// them with coalesced 32-wide loads and broadcasts (column, value) by shuffle -- and a lane owns
+// VEC consecutive columns: one 16-byte shared-memory read and VEC fused multiply-adds per nonzero.
+// Per output element this is the reference's rounding sequence: start from beta*C, one fma per
+// nonzero in ascending (kb, column) order (compute template :309-370).  PARTIAL = true is the
+// variant for the columns of the narrow last block that the reference accumulates per k-block
+// from zero and then adds (:372-434).
+// =================================================================================================
+constexpr int K2_THREADS = 512;
+constexpr int K2_WARPS = K2_THREADS / 32;
+
+template <bool BF16> struct K2Elem { typedef float type; };
+template <> struct K2Elem<true> { typedef uint16_t type; };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <bool BF16, int VEC>
+__device__ __forceinline__ void k2_fma_row(float (&acc)[VEC], const unsigned char* brow, float val)
+{
+  if (!BF16) {
+    const float4 b = *(const float4*)brow;
+    acc[0] = fmaf(val, b.x, acc[0]); acc[1] = fmaf(val, b.y, acc[1]);
+    acc[2] = fmaf(val, b.z, acc[2]); acc[3] = fmaf(val, b.w, acc[3]);
+  }
+  else {
+    const uint4 b = *(const uint4*)brow;
+    const uint32_t w[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[2 * e] = fmaf(val, __uint_as_float(w[e] << 16), acc[2 * e]);
+      acc[2 * e + 1] = fmaf(val, __uint_as_float(w[e] & 0xFFFF0000u), acc[2 * e + 1]);
+    }
+  }
+}
+
+template <bool BF16, bool PARTIAL, int RPW>
+__global__ void __launch_bounds__(K2_THREADS, 1) spmdm_compute_kernel(const ComputeArgs p)
+{
+  typedef typename K2Elem<BF16>::type elem_t;
+  constexpr int VEC = BF16 ? 8 : 4;
+  constexpr int BN = 32 * VEC;
+  constexpr int TM = K2_WARPS * RPW;
+  constexpr int ROWB = BN * (int)sizeof(elem_t);   // 512 bytes per tile row
+  constexpr int TILEB = 128 * ROWB;                // 64 KiB per stage
+  constexpr int CPITCH = BN + 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const Geom& g = p.g;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_per_mb = (g.bm + TM - 1) / TM;
+  const int mbi = p.mb_first + (int)blockIdx.y / tiles_per_mb;
+  const int ml0 = ((int)blockIdx.y % tiles_per_mb) * TM;       // first block-local row of the CTA
+  const int rows_in_block = min(g.bm, g.m - mbi * g.bm);
+  if (ml0 >= rows_in_block) return;
+  const int tile_rows = min(TM, rows_in_block - ml0);
+  const int n0 = (int)blockIdx.x * BN;                        // local column of the CTA
+  const int mycol = n0 + lane * VEC;
+  const int wrow0 = ml0 + warp * RPW;                         // block-local first row of the warp
+  const int nvalid = max(0, min(RPW, rows_in_block - wrow0));
+  const int crow0 = mbi * g.bm + ml0 - p.row_origin;          // local C row of the CTA's first row
+  const size_t cap = (size_t)g.bm * g.bk;
+
+  float acc[RPW][VEC];
+  float run[PARTIAL ? RPW : 1][PARTIAL ? VEC : 1];
+  (void)run;
+
+  // ---- start value: 0, C or beta*C (reference compute template :81-212) --------------------------
+  const bool cvec = (0 == (p.ldc & 3)) && (0 == ((uintptr_t)p.c & 15));
+  if (0.f == p.beta) {
+#pragma unroll
+    for (int i = 0; i < RPW; ++i)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[i][e] = 0.f;
+  }
+  else {
+    if (p.transc) {  // C stored n x m: stage the tile through shared memory for coalesced reads
+      float* Cs = (float*)smem;
+      for (int idx = tid; idx < BN * TM; idx += K2_THREADS) {
+        const int n = idx / TM, r = idx - n * TM;
+        float v = 0.f;
+        if (r < tile_rows && n0 + n < p.ncols) v = p.c[(size_t)(n0 + n) * p.ldc + crow0 + r];
+        Cs[r * CPITCH + n] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < RPW; ++i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[i][e] = Cs[(warp * RPW + i) * CPITCH + lane * VEC + e];
+      __syncthreads();
+    }
+    else {
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const float* src = p.c + (size_t)(crow0 + warp * RPW + i) * p.ldc + mycol;
+        if (i < nvalid && cvec && mycol + VEC <= p.ncols) {
+#pragma unroll
+          for (int q = 0; q < VEC / 4; ++q) {
+            const float4 v = *(const float4*)(src + 4 * q);
+            acc[i][4 * q] = v.x; acc[i][4 * q + 1] = v.y; acc[i][4 * q + 2] = v.z; acc[i][4 * q + 3] = v.w;
+          }
+        }
+        else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[i][e] = (i < nvalid && mycol + e < p.ncols) ? src[e] : 0.f;
+        }
+      }
+    }
+    if (1.f != p.beta) {
+#pragma unroll
+      for (int i = 0; i < RPW; ++i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[i][e] = p.beta * acc[i][e];
+    }
+  }
+  if (PARTIAL) {
+#pragma unroll
+    for (int i = 0; i < RPW; ++i)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { run[i][e] = acc[i][e]; acc[i][e] = 0.f; }
+  }
+
+  // ---- B panel loader -----------------------------------------------------------------------------
+  const elem_t* Bg = (const elem_t*)p.b;
+  constexpr int EPC = 16 / (int)sizeof(elem_t);   // elements per 16-byte chunk
+  const bool bvec = (0 == (p.ldb % EPC)) && (0 == ((uintptr_t)p.b & 15));
+  auto fill = [&](int kb, unsigned char* dst) {
+    const int k0 = kb * g.bk;
+    const int numk = min(g.bk, g.k - k0);
+    if (!p.transb) {   // B stored k x n: a tile row is 32 chunks of 16 bytes
+      for (int idx = tid; idx < numk * 32; idx += K2_THREADS) {
+        const int kk = idx >> 5, ch = idx & 31;
+        const int nl = n0 + ch * EPC;
+        const elem_t* src = Bg + (size_t)(k0 + kk) * p.ldb + nl;
+        elem_t* d = (elem_t*)(dst + kk * ROWB) + ch * EPC;
+        if (bvec && nl + EPC <= p.ncols) cp_async16(d, src);
+        else {
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) d[e] = (nl + e < p.ncols) ? src[e] : (elem_t)0;
+        }
+      }
+    }
+    else {             // B stored n x k: a thread walks k for one column, 16 bytes at a time
+      constexpr int CPT = K2_THREADS / BN;         // k-chunks in flight per pass
+      const int n = tid % BN, c0 = tid / BN;
+      const bool in = (n0 + n < p.ncols);
+      const elem_t* srow = Bg + (size_t)(n0 + n) * p.ldb + k0;
+      for (int ch = c0; ch * EPC < numk; ch += CPT) {
+        const int kk = ch * EPC;
+        __align__(16) elem_t v[EPC];
+        if (in && bvec && kk + EPC <= numk && 0 == (k0 % EPC)) {
+          const uint4 raw = *(const uint4*)(srow + kk);
+          *(uint4*)v = raw;
+        }
+        else {
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) v[e] = (in && kk + e < numk) ? srow[kk + e] : (elem_t)0;
+        }
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) if (kk + e < numk) ((elem_t*)(dst + (kk + e) * ROWB))[n] = v[e];
+      }
+    }
+  };
+
+  // ---- main loop over k blocks ----------------------------------------------------------------------
+  fill(0, smem);
+  cp_async_commit();
+  for (int kb = 0; kb < g.kb; ++kb) {
+    unsigned char* cur = smem + (kb & 1) * TILEB;
+    if (kb + 1 < g.kb) fill(kb + 1, smem + ((kb + 1) & 1) * TILEB);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    if (nvalid > 0) {
+      const int s = kb * g.mb + mbi;
+      const uint16_t* ro = p.sl.rowidx + (size_t)s * (g.bm + 1) + wrow0;
+      const uint16_t* cp = p.sl.colidx + s * cap;
+      const float* vp = p.sl.values + s * cap;
+      int myrp = 0;
+      if (lane <= RPW) myrp = (int)ro[min(lane, nvalid)];
+      int rs[RPW + 1];
+#pragma unroll
+      for (int i = 0; i <= RPW; ++i) rs[i] = __shfl_sync(0xffffffffu, myrp, i);
+#pragma unroll
+      for (int i = 1; i <= RPW; ++i) rs[i] = max(rs[i], rs[i - 1]);   // wrapped u16 pointer: empty row (tpl.c:292-297)
+      const int pend = rs[RPW];
+      const unsigned char* bbase = cur + lane * 16;
+      for (int p0 = rs[0]; p0 < pend; p0 += 32) {
+        const int q = p0 + lane;
+        uint32_t off_l = 0; float val_l = 0.f;
+        if (q < pend) { off_l = (uint32_t)cp[q] * ROWB; val_l = vp[q]; }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const int lo = max(rs[i], p0) - p0, hi = min(rs[i + 1], p0 + 32) - p0;
+          for (int t = lo; t < hi; ++t) {
+            const uint32_t off = __shfl_sync(0xffffffffu, off_l, t);
+            const float val = __shfl_sync(0xffffffffu, val_l, t);
+            k2_fma_row<BF16, VEC>(acc[i], bbase + off, val);
+          }
+        }
+      }
+      if (PARTIAL) {
+#pragma unroll
+        for (int i = 0; i < RPW; ++i)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) { run[i][e] = acc[i][e] + run[i][e]; acc[i][e] = 0.f; }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  if (PARTIAL) {
+#pragma unroll
+    for (int i = 0; i < RPW; ++i)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[i][e] = run[i][e];
+  }
+
+  // ---- write C --------------------------------------------------------------------------------------
+  if (p.transc) {
+    float* Cs = (float*)smem;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) Cs[(warp * RPW + i) * CPITCH + lane * VEC + e] = acc[i][e];
+    __syncthreads();
+    for (int idx = tid; idx < BN * TM; idx += K2_THREADS) {
+      const int n = idx / TM, r = idx - n * TM;
+      if (r < tile_rows && n0 + n < p.ncols) p.c[(size_t)(n0 + n) * p.ldc + crow0 + r] = Cs[r * CPITCH + n];
+    }
+  }
+  else {
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      if (i < nvalid) {
+        float* dst = p.c + (size_t)(crow0 + warp * RPW + i) * p.ldc + mycol;
+        if (cvec && mycol + VEC <= p.ncols) {
+#pragma unroll
+          for (int q = 0; q < VEC / 4; ++q)
+            *(float4*)(dst + 4 * q) = make_float4(acc[i][4 * q], acc[i][4 * q + 1], acc[i][4 * q + 2], acc[i][4 * q + 3]);
+        }
+        else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) if (mycol + e < p.ncols) dst[e] = acc[i][e];
+        }
+      }
+    }
+  }
+}
+
+template <bool BF16, bool PARTIAL, int RPW>
+static void launch_compute_variant(const ComputeArgs& a, cudaStream_t stream)
+{
+  constexpr int VEC = BF16 ? 8 : 4;
+  constexpr int BN = 32 * VEC;
+  constexpr int TM = K2_WARPS * RPW;
+  const size_t tiles = 2 * 128 * (size_t)BN * (BF16 ? 2 : 4);
+  const size_t cstage = (size_t)TM * (BN + 1) * 4;
+  const size_t smem = tiles > cstage ? tiles : cstage;
+  auto kern = spmdm_compute_kernel<BF16, PARTIAL, RPW>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tiles_per_mb = (a.g.bm + TM - 1) / TM;
+  const dim3 grid((unsigned)((a.ncols + BN - 1) / BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
+  count_launch(1);
+  kern<<<grid, K2_THREADS, smem, stream>>>(a);
+  XB_CUDA(cudaGetLastError());
+}
+
+// Splits the column range into the reference's accumulation modes and launches each part:
+//   [0, n_full_end)          full-width blocks: in-order fma chain
+//   [n_full_end, tail_from)  narrow block, vector part: per-kb partial sums
+//   [tail_from, N)           narrow block, scalar part: in-order fma chain (GCC contracts += b*v)
+void launch_compute(const ComputeArgs& args, cudaStream_t stream)
+{
+  if (args.ncols <= 0 || args.mb_count <= 0) return;
+  const int c_lo = args.col_origin, c_hi = args.col_origin + args.ncols;
+  const int cut[4] = { c_lo, min(max(args.modes.n_full_end, c_lo), c_hi), min(max(args.modes.tail_from, c_lo), c_hi), c_hi };
+  for (int part = 0; part < 3; ++part) {
+    const int lo = cut[part], hi = cut[part + 1];
+    if (hi <= lo) continue;
+    ComputeArgs a = args;
+    const size_t esz = args.is_bf16 ? 2 : 4;
+    const long long shift = lo - c_lo;
+    a.b = (const char*)args.b + (args.transb ? (size_t)shift * args.ldb * esz : (size_t)shift * esz);
+    a.c = args.c + (args.transc ? (size_t)shift * args.ldc : (size_t)shift);
+    a.col_origin = lo;
+    a.ncols = hi - lo;
+    const bool partial = (1 == part);
+    if (args.is_bf16) {
+      if (partial) launch_compute_variant<true, true, 4>(a, stream);
+      else launch_compute_variant<true, false, 8>(a, stream);
+    }
+    else {
+      if (partial) launch_compute_variant<false, true, 4>(a, stream);
+      else launch_compute_variant<false, false, 8>(a, stream);
+    }
+  }
+}
+
+}  // namespace xb
