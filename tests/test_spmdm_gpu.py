@@ -123,7 +123,11 @@ def test_special_values_in_a(gpu, oracle):
     g, sl, C = gpu_spmdm(gpu, A, B, C0, M, N, K)
     og, osl, OC = oracle_spmdm(oracle, g, A, B, C0, "N", "N", "N", 0.0)
     valid_slices_equal(og, sl, osl)
-    np.testing.assert_array_equal(C.view(np.uint32), OC.view(np.uint32))
+    # a kept NaN poisons its output row on both sides; NaN payload bits are implementation defined
+    assert np.isnan(OC[5]).all() and np.isnan(C[5]).all()
+    ok = ~np.isnan(OC)
+    np.testing.assert_array_equal(np.isnan(C), np.isnan(OC))
+    np.testing.assert_array_equal(C[ok].view(np.uint32), OC[ok].view(np.uint32))
 
 
 def test_all_zero_and_dense_wrap(gpu, oracle):
