@@ -70,6 +70,7 @@ struct ComputeArgs {
 
 void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream);
 void launch_compute(const ComputeArgs& args, cudaStream_t stream);
+bool launch_compute_tma(const ComputeArgs& args, bool partial, cudaStream_t stream);   // false: panel does not qualify
 
 // ---- FSSPMDM --------------------------------------------------------------------------------
 struct FsOperator;   // fsspmdm.cu

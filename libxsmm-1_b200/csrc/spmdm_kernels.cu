@@ -4,6 +4,7 @@
 // Hand-written CUDA; no library calls on the data path.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <mutex>
 
 namespace cg = cooperative_groups;
 
@@ -478,12 +479,45 @@ static void launch_compute_variant(const ComputeArgs& a, cudaStream_t stream)
 //   [0, n_full_end)          full-width blocks: in-order fma chain
 //   [n_full_end, tail_from)  narrow block, vector part: per-kb partial sums
 //   [tail_from, N)           narrow block, scalar part: in-order fma chain (GCC contracts += b*v)
+static cudaStream_t side_stream()
+{
+  static cudaStream_t s = 0;
+  static std::once_flag once;
+  std::call_once(once, [] { XB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); });
+  return s;
+}
+
+static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
+{
+  if (launch_compute_tma(a, partial, stream)) return;   // TMA fast path (spmdm_compute_tma.cu)
+  if (a.is_bf16) {
+    if (partial) launch_compute_variant<true, true, 4>(a, stream);
+    else launch_compute_variant<true, false, 8>(a, stream);
+  }
+  else {
+    if (partial) launch_compute_variant<false, true, 4>(a, stream);
+    else launch_compute_variant<false, false, 8>(a, stream);
+  }
+}
+
 void launch_compute(const ComputeArgs& args, cudaStream_t stream)
 {
   if (args.ncols <= 0 || args.mb_count <= 0) return;
   const int c_lo = args.col_origin, c_hi = args.col_origin + args.ncols;
   const int cut[4] = { c_lo, min(max(args.modes.n_full_end, c_lo), c_hi), min(max(args.modes.tail_from, c_lo), c_hi), c_hi };
-  for (int part = 0; part < 3; ++part) {
+  // the narrow last block (at most bn - 1 columns, two small launches) runs on a side stream, forked from
+  // and joined back into `stream`, so that it overlaps the main launch instead of serialising behind it
+  const bool narrow = (cut[3] > cut[1]) && (cut[1] > cut[0]);
+  cudaEvent_t fork = 0, join = 0;
+  cudaStream_t side = stream;
+  if (narrow) {
+    side = side_stream();
+    XB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    XB_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    XB_CUDA(cudaEventRecord(fork, stream));
+    XB_CUDA(cudaStreamWaitEvent(side, fork, 0));
+  }
+  for (int part = 2; part >= 0; --part) {
     const int lo = cut[part], hi = cut[part + 1];
     if (hi <= lo) continue;
     ComputeArgs a = args;
@@ -493,15 +527,13 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
     a.c = args.c + (args.transc ? (size_t)shift * args.ldc : (size_t)shift);
     a.col_origin = lo;
     a.ncols = hi - lo;
-    const bool partial = (1 == part);
-    if (args.is_bf16) {
-      if (partial) launch_compute_variant<true, true, 4>(a, stream);
-      else launch_compute_variant<true, false, 8>(a, stream);
-    }
-    else {
-      if (partial) launch_compute_variant<false, true, 4>(a, stream);
-      else launch_compute_variant<false, false, 8>(a, stream);
-    }
+    launch_part(a, 1 == part, (0 == part) ? stream : side);
+  }
+  if (narrow) {
+    XB_CUDA(cudaEventRecord(join, side));
+    XB_CUDA(cudaStreamWaitEvent(stream, join, 0));
+    XB_CUDA(cudaEventDestroy(fork));
+    XB_CUDA(cudaEventDestroy(join));
   }
 }
 

@@ -133,7 +133,7 @@ def test_special_values_in_a(gpu, oracle):
 def test_all_zero_and_dense_wrap(gpu, oracle):
     """empty A; and a fully dense 512 x 128 slice whose u16 counter wraps to 0 like the reference's
     (quirk Q4, template :72): row pointers are compared modulo 2^16."""
-    M, N, K = 512, 64, 128
+    M, N, K = 512, 96, 128            # N a multiple of bn: the balance loop keeps bm = 512
     B = np.random.default_rng(1).random((K, N)).astype(np.float32)
     C0 = np.ones((M, N), np.float32)
     A = np.zeros((M, K), np.float32)
