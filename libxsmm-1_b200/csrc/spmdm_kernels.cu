@@ -172,9 +172,187 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
   if (strip == nstrips - 1 && 0 == tid) ro[nrows] = (uint16_t)(base + strip_tot[strip]);
 }
 
+// -------------------------------------------------------------------------------------------------
+// K1 for transa = 'N' (A stored m x k): one CTA per slice, a warp owns a contiguous range of rows.
+// Pass 1 streams the rows (one 16-byte / 8-byte load per lane per row, four rows in flight per warp) and
+// only counts; the per-warp totals are scanned once per CTA; pass 2 re-reads the rows (now L1/L2
+// resident), rebuilds the ballots and writes row pointers, column indices and values.  A is read from
+// HBM exactly once; no cluster, one __syncthreads.
+// -------------------------------------------------------------------------------------------------
+constexpr int K1N_THREADS = 1024;
+constexpr int K1N_WARPS = K1N_THREADS / 32;
+
+// A lane holds four consecutive elements (columns lane*4 .. lane*4+3) of a row "as loaded": four fp32
+// words, or two words of packed bf16 pairs; widen() gives the fp32 bit patterns (bf16 << 16).
+template <bool BF16> struct K1Raw;
+template <> struct K1Raw<false> {
+  typedef uint4 raw_t;
+  static __device__ __forceinline__ raw_t zero() { return make_uint4(0, 0, 0, 0); }
+  static __device__ __forceinline__ raw_t load(const void* a, long long lda, int row, int lane, int ncols, bool vec)
+  {
+    const int k = lane * 4;
+    const float* src = (const float*)a + (long long)row * lda + k;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (vec && k + 3 < ncols) w = __ldg((const uint4*)src);
+    else {
+      if (k < ncols) w.x = __float_as_uint(__ldg(src));
+      if (k + 1 < ncols) w.y = __float_as_uint(__ldg(src + 1));
+      if (k + 2 < ncols) w.z = __float_as_uint(__ldg(src + 2));
+      if (k + 3 < ncols) w.w = __float_as_uint(__ldg(src + 3));
+    }
+    return w;
+  }
+  static __device__ __forceinline__ uint4 widen(raw_t r) { return r; }
+};
+template <> struct K1Raw<true> {
+  typedef uint2 raw_t;
+  static __device__ __forceinline__ raw_t zero() { return make_uint2(0, 0); }
+  static __device__ __forceinline__ raw_t load(const void* a, long long lda, int row, int lane, int ncols, bool vec)
+  {
+    const int k = lane * 4;
+    const uint16_t* src = (const uint16_t*)a + (long long)row * lda + k;
+    uint2 r = make_uint2(0, 0);
+    if (vec && k + 3 < ncols) r = __ldg((const uint2*)src);
+    else {
+      if (k < ncols) r.x = (uint32_t)__ldg(src);
+      if (k + 1 < ncols) r.x |= (uint32_t)__ldg(src + 1) << 16;
+      if (k + 2 < ncols) r.y = (uint32_t)__ldg(src + 2);
+      if (k + 3 < ncols) r.y |= (uint32_t)__ldg(src + 3) << 16;
+    }
+    return r;
+  }
+  static __device__ __forceinline__ uint4 widen(raw_t r) { return make_uint4(r.x << 16, r.x & 0xFFFF0000u, r.y << 16, r.y & 0xFFFF0000u); }
+};
+
+// keep-mask of the lane's four elements.  FULL = complete 128-column block whose columns are all inside the
+// reference's vector loops: kept iff ordered-nonzero, i.e. |v| > 0 (NaN and -0.0 dropped, denormals kept).
+template <bool FULL>
+__device__ __forceinline__ uint32_t k1n_mask(uint4 w, int lane, int ncols, int vec_end)
+{
+  if (FULL) {
+    return (fabsf(__uint_as_float(w.x)) > 0.f ? 1u : 0u) | (fabsf(__uint_as_float(w.y)) > 0.f ? 2u : 0u)
+         | (fabsf(__uint_as_float(w.z)) > 0.f ? 4u : 0u) | (fabsf(__uint_as_float(w.w)) > 0.f ? 8u : 0u);
+  }
+  const int k = lane * 4;
+  uint32_t m = 0;
+  if (k < ncols && k1_keep(__uint_as_float(w.x), k, vec_end)) m |= 1u;
+  if (k + 1 < ncols && k1_keep(__uint_as_float(w.y), k + 1, vec_end)) m |= 2u;
+  if (k + 2 < ncols && k1_keep(__uint_as_float(w.z), k + 2, vec_end)) m |= 4u;
+  if (k + 3 < ncols && k1_keep(__uint_as_float(w.w), k + 3, vec_end)) m |= 8u;
+  return m;
+}
+
+// ROWS = rows a warp handles (>= rows per warp); KEEP = rows stay in registers between the two phases,
+// otherwise phase 2 re-reads them (fp32 slices of 512 rows do not fit the register file).
+template <bool BF16, bool FULL, int ROWS, bool KEEP>
+__global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const SliceArgs p)
+{
+  typedef K1Raw<BF16> Raw;
+  typedef typename Raw::raw_t raw_t;
+  __shared__ uint32_t wtot[K1N_WARPS];
+  const Geom& g = p.g;
+  const int s = p.slice0 + (int)blockIdx.x;
+  const int kb = s / g.mb, mbi = s - kb * g.mb;
+  const int nrows = min(g.bm, g.m - mbi * g.bm);
+  const int ncols = min(g.bk, g.k - kb * g.bk);
+  int vec_end = BF16 ? (ncols / (4 * p.simd_w)) * (4 * p.simd_w) : (ncols / p.simd_w) * p.simd_w;
+  if (p.simd_w <= 1) vec_end = 0;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rpw = (g.bm + K1N_WARPS - 1) / K1N_WARPS;      // rows per warp (<= 16 because bm <= 512)
+  const int row_lo = warp * rpw, row_hi = min(nrows, row_lo + rpw);
+  const size_t esz = BF16 ? 2 : 4;
+  const long long origin = p.origin_is_block ? 0ll : ((long long)mbi * g.bm * p.lda + (long long)kb * g.bk);
+  const char* A = (const char*)p.a + origin * (long long)esz;
+  const bool vec = (0 == (p.lda & 3)) && (0 == ((uintptr_t)A & (BF16 ? 7 : 15)));
+
+  // ---- phase 1: load, test, count ---------------------------------------------------------------------
+  raw_t w[KEEP ? ROWS : 8];
+  uint32_t masks[(ROWS + 7) / 8];        // 4 bits per row
+#pragma unroll
+  for (int j = 0; j < (ROWS + 7) / 8; ++j) masks[j] = 0;
+#pragma unroll
+  for (int j0 = 0; j0 < ROWS; j0 += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      w[KEEP ? j0 + j : j] = (row_lo + j0 + j < row_hi) ? Raw::load(A, p.lda, row_lo + j0 + j, lane, ncols, vec) : Raw::zero();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      masks[(j0 + j) / 8] |= k1n_mask<FULL>(Raw::widen(w[KEEP ? j0 + j : j]), lane, ncols, vec_end) << (4 * ((j0 + j) % 8));
+  }
+  uint32_t mine = 0;
+#pragma unroll
+  for (int j = 0; j < (ROWS + 7) / 8; ++j) mine += __popc(masks[j]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  if (0 == lane) wtot[warp] = mine;
+  __syncthreads();
+  uint32_t pos;   // first output position of this warp's rows
+  {
+    const uint32_t t = wtot[lane];
+    uint32_t inc = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += u;
+    }
+    pos = __shfl_sync(0xffffffffu, inc - t, warp);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (0 == tid) p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
+  }
+
+  // ---- phase 2: positions and stores -----------------------------------------------------------------------
+  uint16_t* ro = p.out.rowidx + (size_t)s * (g.bm + 1);
+  uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
+  float* va = p.out.values + (size_t)s * g.bm * g.bk;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int k = lane * 4;
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) {
+    if (row_lo + j < row_hi) {     // warp-uniform
+      const uint32_t m = (masks[j / 8] >> (4 * (j % 8))) & 15u;
+      const uint4 v = Raw::widen(KEEP ? w[KEEP ? j : 0] : Raw::load(A, p.lda, row_lo + j, lane, ncols, vec));
+      // lane order = column order: count the kept elements of lower lanes with one ballot per bit of the
+      // per-lane count (0..4)
+      const uint32_t nm = __popc(m);
+      const uint32_t b0 = __ballot_sync(0xffffffffu, nm & 1u), b1 = __ballot_sync(0xffffffffu, nm & 2u), b2 = __ballot_sync(0xffffffffu, nm & 4u);
+      uint32_t q = pos + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+      if (0 == lane) ro[row_lo + j] = (uint16_t)pos;
+      if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); ++q; }
+      if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); ++q; }
+      if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); ++q; }
+      if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); ++q; }
+      pos += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    }
+  }
+}
+
+template <bool BF16, int ROWS, bool KEEP>
+static void launch_slice_n(const SliceArgs& args, int nslices, bool full, cudaStream_t stream)
+{
+  if (full) spmdm_slice_n_kernel<BF16, true, ROWS, KEEP><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+  else spmdm_slice_n_kernel<BF16, false, ROWS, KEEP><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+}
+
 void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
 {
   if (nslices <= 0) return;
+  if (!args.transa) {
+    count_launch(1);
+    // FULL: every slice is a complete 128-column block inside the reference's vector loops (k % 128 == 0
+    // makes the NaN rule of the scalar remainder unreachable)
+    const bool full = (0 == (args.g.k % 128)) && (args.simd_w > 1);
+    const int rpw = (args.g.bm + K1N_WARPS - 1) / K1N_WARPS;
+    if (args.is_bf16) {
+      if (rpw <= 8) launch_slice_n<true, 8, true>(args, nslices, full, stream);
+      else launch_slice_n<true, 16, true>(args, nslices, full, stream);
+    }
+    else {
+      if (rpw <= 8) launch_slice_n<false, 8, true>(args, nslices, full, stream);
+      else launch_slice_n<false, 16, false>(args, nslices, full, stream);
+    }
+    XB_CUDA(cudaGetLastError());
+    return;
+  }
   const int nstrips = (args.g.bm + K1_R - 1) / K1_R;   // <= 8 because bm <= 512
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)nstrips, (unsigned)nslices, 1);
