@@ -10,3 +10,4 @@ Import with ``importlib.import_module("libxsmm-1_b200")`` (the directory name is
 """
 from .api import *          # noqa: F401,F403
 from . import workloads     # noqa: F401
+from . import sharding      # noqa: F401
