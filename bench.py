@@ -386,6 +386,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        wl = dict(wl)
+        if wl["kind"] == "spmdm" and args.gpus > 1:      # the GPU arm's global problem: one 4096-column panel per GPU
+            wl["N"] = wl["N"] * args.gpus
+            wl["desc"] += " x %d column panels (global N = %d)" % (args.gpus, wl["N"])
         r = cpu_reference(wl, budget_s=0.0, reps_min=args.steps + args.warmup, reps_max=args.steps + args.warmup)
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
