@@ -6,6 +6,7 @@
 #include <nvrtc.h>
 #include <dlfcn.h>
 #include <cstdio>
+#include <cstdint>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -19,8 +20,8 @@ namespace xb {
 struct FsJit {
   cudaLibrary_t lib;
   cudaKernel_t kern;
+  cudaKernel_t kern2;   // two columns per thread (float only), or NULL
   int block;
-  int cols_per_thread;
 };
 
 namespace {
@@ -73,44 +74,72 @@ void append(std::string& s, const char* fmt, ...)
   s += buf;
 }
 
-// The emitted kernel: one thread per column of B/C.  Every B row that the operator touches is loaded
-// once into a named register (coalesced across the warp), every output row is then an in-order chain
-// of fused multiply-adds with literal operator values -- the rounding sequence of the reference's
-// emitted kernel (generator :227-300) -- and is stored as soon as it is complete.
-std::string emit(int is_double, int M, int K, int beta_one, int skip_empty,
+// The emitted kernel: one thread per CPT consecutive columns of B/C (CPT = 1, or 2 as a vector of two).
+// Every B row that the operator touches is loaded once into a named register (coalesced across the warp),
+// every output row is then an in-order chain of fused multiply-adds with literal operator values -- the
+// rounding sequence of the reference's emitted kernel (generator :227-300) -- and is stored, with a
+// streaming store, as soon as it is complete.
+void emit_kernel(std::string& s, const char* name, int cpt, int is_double, int M, int K, int beta_one, int skip_empty,
                  const int* rowptr, const int* col, const double* val)
 {
   const char* T = is_double ? "double" : "float";
+  char V[16];
+  snprintf(V, sizeof(V), "%s%s", T, 2 == cpt ? "2" : "");
   std::vector<char> used(K, 0);
   for (int u = 0; u < rowptr[M]; ++u) used[col[u]] = 1;
-  std::string s;
-  s.reserve(64 * (size_t)rowptr[M] + 4096);
-  append(s, "extern \"C\" __global__ void __launch_bounds__(%d) fs_baked(const %s* __restrict__ B, %s* __restrict__ C, long long ncols, long long ldb, long long ldc)\n{\n", kBlock, T, T);
-  append(s, "  const long long n = (long long)blockIdx.x * %d + threadIdx.x;\n  if (n >= ncols) return;\n", kBlock);
-  append(s, "  const %s* __restrict__ b = B + n;\n  %s* __restrict__ c = C + n;\n  %s acc;\n", T, T, T);
-  for (int k = 0; k < K; ++k) if (used[k]) append(s, "  const %s b%d = __ldg(b + %dLL * ldb);\n", T, k, k);
-  for (int m = 0; m < M; ++m) {
-    const int lo = rowptr[m], hi = rowptr[m + 1];
-        if (hi == lo) {
-      if (!skip_empty && !beta_one) append(s, "  c[%dLL * ldc] = 0;\n", m);
-      continue;
+  append(s, "extern \"C\" __global__ void __launch_bounds__(%d) %s(const %s* __restrict__ B, %s* __restrict__ C, long long ncols, long long ldb, long long ldc)\n{\n", kBlock, name, T, T);
+  append(s, "  const long long n = ((long long)blockIdx.x * %d + threadIdx.x) * %d;\n  if (n >= ncols) return;\n", kBlock, cpt);
+  append(s, "  const %s* __restrict__ b = B + n;\n  %s* __restrict__ c = C + n;\n  %s acc;\n", T, T, V);
+  for (int k = 0; k < K; ++k) if (used[k]) append(s, "  const %s b%d = __ldcs((const %s*)(b + %dLL * ldb));\n", V, k, V, k);
+  // beta = 1: the C rows of a group are fetched together ahead of the group's chains, so that their latency
+  // is paid once per group instead of once per row (loads cannot be hoisted over the stores by the compiler)
+  const int group = beta_one ? (is_double ? 8 : 16) : 1;
+  for (int m0 = 0; m0 < M; m0 += group) {
+    if (beta_one) {
+      for (int m = m0; m < M && m < m0 + group; ++m)
+        if (rowptr[m + 1] != rowptr[m]) append(s, "  %s c%d = __ldcs((const %s*)(c + %dLL * ldc));\n", V, m, V, m);
     }
-    if (beta_one) append(s, "  acc = c[%dLL * ldc];\n", m); else append(s, "  acc = 0;\n");
-    for (int u = lo; u < hi; ++u) {
-      if (is_double) {
-        long long bits; const double v = val[u];
-        memcpy(&bits, &v, 8);
-        append(s, "  acc = fma(__longlong_as_double(0x%016llxLL), b%d, acc);\n", (unsigned long long)bits, col[u]);
+    for (int m = m0; m < M && m < m0 + group; ++m) {
+      const int lo = rowptr[m], hi = rowptr[m + 1];
+      if (hi == lo) {
+        if (!skip_empty && !beta_one) {
+          if (2 == cpt) append(s, "  acc.x = 0; acc.y = 0; __stcs((%s*)(c + %dLL * ldc), acc);\n", V, m);
+          else append(s, "  __stcs(c + %dLL * ldc, (%s)0);\n", m, T);
+        }
+        continue;
       }
-      else {
-        int bits; const float v = (float)val[u];
-        memcpy(&bits, &v, 4);
-        append(s, "  acc = fmaf(__int_as_float(0x%08x), b%d, acc);\n", (unsigned)bits, col[u]);
+      if (beta_one) append(s, "  acc = c%d;\n", m);
+      else if (2 == cpt) append(s, "  acc.x = 0; acc.y = 0;\n");
+      else append(s, "  acc = 0;\n");
+      for (int u = lo; u < hi; ++u) {
+        char lit[64];
+        if (is_double) {
+          long long bits; const double v = val[u];
+          memcpy(&bits, &v, 8);
+          snprintf(lit, sizeof(lit), "__longlong_as_double(0x%016llxLL)", (unsigned long long)bits);
+        }
+        else {
+          int bits; const float v = (float)val[u];
+          memcpy(&bits, &v, 4);
+          snprintf(lit, sizeof(lit), "__int_as_float(0x%08x)", (unsigned)bits);
+        }
+        const char* f = is_double ? "fma" : "fmaf";
+        if (2 == cpt) append(s, "  acc.x = %s(%s, b%d.x, acc.x); acc.y = %s(%s, b%d.y, acc.y);\n", f, lit, col[u], f, lit, col[u]);
+        else append(s, "  acc = %s(%s, b%d, acc);\n", f, lit, col[u]);
       }
+      append(s, "  __stcs((%s*)(c + %dLL * ldc), acc);\n", V, m);
     }
-    append(s, "  c[%dLL * ldc] = acc;\n", m);
   }
   s += "}\n";
+}
+
+std::string emit(int is_double, int M, int K, int beta_one, int skip_empty,
+                 const int* rowptr, const int* col, const double* val)
+{
+  std::string s;
+  s.reserve(160 * (size_t)rowptr[M] + 8192);
+  emit_kernel(s, "fs_baked", 1, is_double, M, K, beta_one, skip_empty, rowptr, col, val);
+  if (!is_double) emit_kernel(s, "fs_baked2", 2, is_double, M, K, beta_one, skip_empty, rowptr, col, val);   // 8-byte accesses
   return s;
 }
 
@@ -175,9 +204,10 @@ FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty,
   }
   FsJit* j = new FsJit();
   j->block = kBlock;
-  j->cols_per_thread = 1;
+  j->kern2 = 0;
   cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), 0, 0, 0, 0, 0, 0);
   if (cudaSuccess == e) e = cudaLibraryGetKernel(&j->kern, j->lib, "fs_baked");
+  if (cudaSuccess == e && !is_double) e = cudaLibraryGetKernel(&j->kern2, j->lib, "fs_baked2");
   if (cudaSuccess != e) {
     set_error((int)e, "fsspmdm: loading the baked kernel failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -189,10 +219,12 @@ FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty,
 
 bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream)
 {
-  const long long per_block = (long long)j->block * j->cols_per_thread;
+  // the 2-column form needs 8-byte aligned rows: even pitches, even column count, aligned bases
+  const bool two = (0 != j->kern2) && (0 == ((ldb | ldc | ncols) & 1)) && (0 == (((uintptr_t)dB | (uintptr_t)dC) & 7));
+  const long long per_block = (long long)j->block * (two ? 2 : 1);
   const long long blocks = (ncols + per_block - 1) / per_block;
   void* args[] = { (void*)&dB, (void*)&dC, (void*)&ncols, (void*)&ldb, (void*)&ldc };
-  const cudaError_t e = cudaLaunchKernel((const void*)j->kern, dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, 0, stream);
+  const cudaError_t e = cudaLaunchKernel((const void*)(two ? j->kern2 : j->kern), dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, 0, stream);
   if (cudaSuccess != e) { set_error((int)e, "fsspmdm: baked kernel launch failed: %s", cudaGetErrorString(e)); return false; }
   return true;
 }
