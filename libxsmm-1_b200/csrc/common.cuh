@@ -70,7 +70,8 @@ struct ComputeArgs {
 
 void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream);
 void launch_compute(const ComputeArgs& args, cudaStream_t stream);
-bool launch_compute_tma(const ComputeArgs& args, bool partial, cudaStream_t stream);   // false: panel does not qualify
+bool launch_compute_tma(const ComputeArgs& args, bool partial, cudaStream_t stream);
+bool launch_compute_tc(const ComputeArgs& args, cudaStream_t stream);   // tcgen05 dense branch; false: does not qualify   // false: panel does not qualify
 
 // ---- FSSPMDM --------------------------------------------------------------------------------
 struct FsOperator;   // fsspmdm.cu

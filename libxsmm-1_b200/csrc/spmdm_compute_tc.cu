@@ -1,0 +1,317 @@
+// K4: tensor-core branch of the spmdm compute step for the DENSE regime (fp32 inputs), sm_100a.
+//
+//   C[128 rows, 128 cols] = beta*C + sum_kb densify(slice(kb, mb))[128 x 128] * B[kb*128 .. +128, 128 cols]
+//
+// The CSR slice block is scattered back into a dense, 128B-swizzled K-major shared-memory tile and fed to
+// tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8) with the accumulator in TMEM.  fp32 accuracy comes from
+// the error-compensated 3xTF32 split: a = a_hi + a_lo, b = b_hi + b_lo with the *_hi parts representable in
+// TF32, and D += a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (the dropped a_lo*b_lo term is 2^-22 relative).
+//   * A_hi / A_lo: built by the worker warps from (colidx, values) of the slice, once per k-block.
+//   * B: 32 x 128 chunks by TMA (SWIZZLE_128B_ATOM_32B, MN-major operand: four boxes of 32 columns), two stages;
+//     the raw chunk serves as b_hi (the tensor core ignores the low 13 mantissa bits), the workers write
+//     b_lo = b - trunc(b) into a second buffer with the same swizzled addressing.
+//   * one thread issues the MMAs; tcgen05.commit releases B stages / the A tile / signals the epilogue.
+//   * every k-block's accumulator is drained into registers by tcgen05.ld (thread = row, 32 columns per
+//     instruction) while the next k-block's MMAs run into the other TMEM buffer; epilogue: + beta*C, 16-byte stores.
+// This branch does NOT keep the reference's rounding sequence (tensor-core accumulation order); it is used
+// where the relative-error contract (1e-5) is the bar.  It never touches operands the reference would skip
+// in a way that changes finite results: dropped (zero) entries of A are exact zeros in the dense tile.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cstdlib>
+
+namespace xb {
+
+constexpr int TC_BM = 128;          // rows per CTA (UMMA M)
+constexpr int TC_BN = 128;          // columns per CTA (UMMA N)
+constexpr int TC_KC = 32;           // k per B chunk = one 128-byte swizzle row of fp32
+constexpr int TC_WORKERS = 8;       // worker warps (densify, split, epilogue)
+constexpr int TC_THREADS = (2 + TC_WORKERS) * 32;
+constexpr int TC_A_CHUNK = TC_BM * 128;             // bytes of one 128 x 32 fp32 K-major tile (16 KiB)
+constexpr int TC_B_CHUNK = TC_KC * TC_BN * 4;       // bytes of one 32 x 128 fp32 chunk (16 KiB)
+constexpr int TC_SMEM_A_HI = 0;
+constexpr int TC_SMEM_A_LO = 4 * TC_A_CHUNK;                       // 64 KiB
+constexpr int TC_SMEM_B = 8 * TC_A_CHUNK;                          // 128 KiB: stage s -> raw at +s*32K, lo at +s*32K+16K
+constexpr int TC_SMEM_BAR = TC_SMEM_B + 4 * TC_B_CHUNK;            // 192 KiB
+constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 128;
+
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
+{
+  // reference for the field layout: CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;        // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+  asm volatile(
+    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+    : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// byte offset of element (row, k) inside the 4 x [128 rows x 128 B] K-major SWIZZLE_128B tile of A
+__device__ __forceinline__ uint32_t tc_a_offset(int row, int k)
+{
+  const int chunk = k >> 5, kk = k & 31;
+  return (uint32_t)(chunk * TC_A_CHUNK + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) & 7) << 4) + ((kk & 3) << 2));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeArgs p)
+{
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar = (uint64_t*)(smem + TC_SMEM_BAR);
+  uint64_t* b_full = bar;          // [2] TMA landed (tx bytes)
+  uint64_t* b_split = bar + 2;     // [2] workers wrote b_lo
+  uint64_t* b_free = bar + 4;      // [2] MMAs that read the stage have completed
+  uint64_t* a_ready = bar + 6;     // workers built A for this k-block
+  uint64_t* a_free = bar + 7;      // MMAs of the k-block have completed
+  uint64_t* acc_full = bar + 8;    // [2] the k-block's MMAs into accumulator buffer (kb & 1) have completed
+  uint64_t* acc_free = bar + 10;   // [2] the workers have drained that buffer
+  uint32_t* tmem_slot = (uint32_t*)(bar + 12);
+
+  const Geom& g = p.g;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_per_mb = (g.bm + TC_BM - 1) / TC_BM;
+  const int mbi = p.mb_first + (int)blockIdx.y / tiles_per_mb;
+  const int ml0 = ((int)blockIdx.y % tiles_per_mb) * TC_BM;
+  const int rows_in_block = min(g.bm, g.m - mbi * g.bm);
+  if (ml0 >= rows_in_block) return;
+  const int tile_rows = min(TC_BM, rows_in_block - ml0);
+  const int n0 = (int)blockIdx.x * TC_BN;
+  const int nchunks = g.kb * 4;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (0 == tid) {
+    mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1);
+    mbar_init(&b_split[0], TC_WORKERS); mbar_init(&b_split[1], TC_WORKERS);
+    mbar_init(&b_free[0], 1); mbar_init(&b_free[1], 1);
+    mbar_init(a_ready, TC_WORKERS); mbar_init(a_free, 1);
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1); mbar_init(&acc_free[0], TC_WORKERS); mbar_init(&acc_free[1], TC_WORKERS);
+    mbar_fence_init();
+  }
+  if (1 == warp) {   // TMEM: 2 x 128 columns of fp32 accumulators (one warp allocates and later frees)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (0 == warp) {
+    // ---------------- TMA producer: B chunks, two stages ----------------
+    if (0 == lane) {
+      tma_prefetch_desc(&tmB);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c & 1, f = c >> 1;
+        if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
+        mbar_arrive_expect_tx(&b_full[s], TC_B_CHUNK);
+        unsigned char* dst = smem + TC_SMEM_B + s * 2 * TC_B_CHUNK;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * (TC_KC * 128), &tmB, n0 + 32 * j, c * TC_KC, &b_full[s]);
+      }
+    }
+  }
+  else if (1 == warp) {
+    // ---------------- MMA issuer ----------------
+    if (0 == lane) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = F32, A = B = TF32,
+      // A K-major, B MN-major, N = 128, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < g.kb; ++kb) {
+        // The accumulator of a k-block is drained into registers by the workers (IEEE adds) instead of being
+        // carried in TMEM over the whole K loop: the tensor core truncates on every accumulation, and over
+        // K/8*3 accumulations that bias would exceed the 1e-5 contract.  Two TMEM buffers alternate.
+        const uint32_t tmem_acc = tmem_d + (uint32_t)((kb & 1) * TC_BN);
+        if (kb >= 2) mbar_wait(&acc_free[kb & 1], ((kb >> 1) - 1) & 1);
+        mbar_wait(a_ready, kb & 1);
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = kb * 4 + cc, s = c & 1;
+          mbar_wait(&b_split[s], (c >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = sbase + TC_SMEM_A_HI + cc * TC_A_CHUNK;
+          const uint32_t a_lo = sbase + TC_SMEM_A_LO + cc * TC_A_CHUNK;
+          const uint32_t b_hi = sbase + TC_SMEM_B + s * 2 * TC_B_CHUNK;
+          const uint32_t b_lo = b_hi + TC_B_CHUNK;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            // A (K-major): 8 k = 32 bytes further inside the swizzled 128-byte rows; 8-row groups 1024 B apart
+            const uint64_t dah = tc_smem_desc(a_hi + ks * 32, 16, 1024, 2);
+            const uint64_t dal = tc_smem_desc(a_lo + ks * 32, 16, 1024, 2);
+            // B (MN-major TF32: only the 128-byte swizzle with 32-byte atoms exists; pinned with tools/umma_probe):
+            // atoms of 4 k x 128 B, k groups 512 B apart (SBO), 32-column blocks 4096 B apart (LBO); 8 k = 1024 B
+            const uint64_t dbh = tc_smem_desc(b_hi + ks * 1024, TC_KC * 128, 512, 1);
+            const uint64_t dbl = tc_smem_desc(b_lo + ks * 1024, TC_KC * 128, 512, 1);
+            tc_mma_tf32(tmem_acc, dah, dbh, idesc, (cc > 0 || ks > 0) ? 1u : 0u);
+            tc_mma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+            tc_mma_tf32(tmem_acc, dal, dbh, idesc, 1u);
+          }
+          tc_commit(&b_free[s]);
+        }
+        tc_commit(a_free);
+        tc_commit(&acc_full[kb & 1]);
+      }
+    }
+  }
+  else {
+    // ---------------- workers: densify A, split B, epilogue ----------------
+    const int w = warp - 2;                       // 0..7
+    const int wt = tid - 64;                      // 0..255
+    const size_t cap = (size_t)g.bm * g.bk;
+    // this thread's part of the output: row (quarter*32 + lane), 64 columns; warp w may touch TMEM lanes
+    // 32*(w%4) .. +31, and the two warps that share a lane quarter take 64 columns each
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int chalf = (w >> 2) * 64;              // warps 2..5 -> columns 0..63; warps 6..9 -> 64..127
+    float run[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) run[j] = 0.f;
+    auto drain = [&](int kbd) {                   // run += accumulator of k-block kbd
+      mbar_wait(&acc_full[kbd & 1], (kbd >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < 64; cb += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((kbd & 1) * TC_BN + chalf + cb), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) run[cb + j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (0 == lane) mbar_arrive(&acc_free[kbd & 1]);
+    };
+    for (int kb = 0; kb < g.kb; ++kb) {
+      // (1) A tile of this k-block: wait until the previous k-block's MMAs are done, zero, scatter
+      if (kb > 0) mbar_wait(a_free, (kb - 1) & 1);
+      {
+        uint4* z = (uint4*)(smem + TC_SMEM_A_HI);
+        for (int i = wt; i < (8 * TC_A_CHUNK) / 16; i += TC_WORKERS * 32) z[i] = make_uint4(0, 0, 0, 0);
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(TC_WORKERS * 32) : "memory");   // zero-fill complete before the scatter
+      {
+        const int s = kb * g.mb + mbi;
+        const uint16_t* ro = p.sl.rowidx + (size_t)s * (g.bm + 1) + ml0;
+        const uint16_t* co = p.sl.colidx + s * cap;
+        const float* va = p.sl.values + s * cap;
+        for (int r = w; r < tile_rows; r += TC_WORKERS) {      // a warp per row: coalesced reads of its nonzeros
+          const int lo = (int)__ldg(ro + r), hi = (int)__ldg(ro + r + 1);   // hi < lo (wrapped counter) = empty row
+          for (int q = lo + lane; q < hi; q += 32) {
+            const int k = (int)__ldg(co + q);
+            const float v = __ldg(va + q);
+            const float vh = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            const uint32_t off = tc_a_offset(r, k);
+            *(float*)(smem + TC_SMEM_A_HI + off) = vh;
+            *(float*)(smem + TC_SMEM_A_LO + off) = v - vh;
+          }
+        }
+      }
+      fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (0 == lane) mbar_arrive(a_ready);
+      // (2) B chunks of this k-block: b_lo = b - trunc_tf32(b), same (swizzled) addresses
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = kb * 4 + cc, s = c & 1;
+        mbar_wait(&b_full[s], (c >> 1) & 1);
+        const uint4* src = (const uint4*)(smem + TC_SMEM_B + s * 2 * TC_B_CHUNK);
+        uint4* dst = (uint4*)(smem + TC_SMEM_B + s * 2 * TC_B_CHUNK + TC_B_CHUNK);
+#pragma unroll
+        for (int i = 0; i < TC_B_CHUNK / 16 / (TC_WORKERS * 32); ++i) {
+          const uint4 b = src[wt + i * TC_WORKERS * 32];
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(b.x) - __uint_as_float(b.x & 0xFFFFE000u));
+          l.y = __float_as_uint(__uint_as_float(b.y) - __uint_as_float(b.y & 0xFFFFE000u));
+          l.z = __float_as_uint(__uint_as_float(b.z) - __uint_as_float(b.z & 0xFFFFE000u));
+          l.w = __float_as_uint(__uint_as_float(b.w) - __uint_as_float(b.w & 0xFFFFE000u));
+          dst[wt + i * TC_WORKERS * 32] = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (0 == lane) mbar_arrive(&b_split[s]);
+      }
+      // (3) drain the previous k-block's accumulator while this k-block's MMAs run
+      if (kb > 0) drain(kb - 1);
+    }
+    drain(g.kb - 1);
+    // (4) epilogue: + beta*C, 16-byte streaming stores
+    const size_t crow = (size_t)(mbi * g.bm + ml0 + row - p.row_origin);
+    if (row < tile_rows) {
+      float* dst = p.c + crow * p.ldc + n0 + chalf;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const int col = n0 + chalf + j;
+        float4 o = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
+        if (col + 3 < p.ncols) {
+          if (0.f != p.beta) {
+            const float4 cin = *(const float4*)(dst + j);
+            o.x = fmaf(p.beta, cin.x, o.x); o.y = fmaf(p.beta, cin.y, o.y); o.z = fmaf(p.beta, cin.z, o.z); o.w = fmaf(p.beta, cin.w, o.w);
+          }
+          st_global_cs_f4(dst + j, o);
+        }
+        else {
+          const float e[4] = { o.x, o.y, o.z, o.w };
+#pragma unroll
+          for (int t = 0; t < 4; ++t) if (col + t < p.ncols) dst[j + t] = (0.f != p.beta) ? fmaf(p.beta, dst[j + t], e[t]) : e[t];
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (1 == warp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(256) : "memory");
+  }
+}
+
+bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
+                              unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows);
+
+// returns false when the panel does not qualify (caller falls back to the CUDA-core kernels)
+bool launch_compute_tc(const ComputeArgs& a, cudaStream_t stream)
+{
+  if (a.is_bf16 || a.transb || a.transc) return false;
+  if (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3)) return false;
+  CUtensorMap map;
+  if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 4, 32, TC_KC)) return false;
+  static bool configured = false;
+  if (!configured) {
+    XB_CUDA(cudaFuncSetAttribute(spmdm_compute_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles_per_mb = (a.g.bm + TC_BM - 1) / TC_BM;
+  const dim3 grid((unsigned)((a.ncols + TC_BN - 1) / TC_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
+  count_launch(1);
+  spmdm_compute_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
+  XB_CUDA(cudaGetLastError());
+  return true;
+}
+
+}  // namespace xb

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -317,10 +318,12 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
       const uint32_t b0 = __ballot_sync(0xffffffffu, nm & 1u), b1 = __ballot_sync(0xffffffffu, nm & 2u), b2 = __ballot_sync(0xffffffffu, nm & 4u);
       uint32_t q = pos + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
       if (0 == lane) ro[row_lo + j] = (uint16_t)pos;
-      if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); ++q; }
-      if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); ++q; }
-      if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); ++q; }
-      if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); ++q; }
+      if (m) {   // few lanes hold nonzeros in the sparse regime: one divergent region per row
+        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); ++q; }
+        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); ++q; }
+        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); ++q; }
+        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); }
+      }
       pos += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     }
   }
@@ -343,8 +346,11 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
     const bool full = (0 == (args.g.k % 128)) && (args.simd_w > 1);
     const int rpw = (args.g.bm + K1N_WARPS - 1) / K1N_WARPS;
     if (args.is_bf16) {
+      static int keep16 = -1;
+      if (keep16 < 0) { const char* e = getenv("LIBXSMM_B200_K1_KEEP"); keep16 = (e && '1' == *e) ? 1 : 0; }
       if (rpw <= 8) launch_slice_n<true, 8, true>(args, nslices, full, stream);
-      else launch_slice_n<true, 16, true>(args, nslices, full, stream);
+      else if (keep16) launch_slice_n<true, 16, true>(args, nslices, full, stream);
+      else launch_slice_n<true, 16, false>(args, nslices, full, stream);
     }
     else {
       if (rpw <= 8) launch_slice_n<false, 8, true>(args, nslices, full, stream);
@@ -667,6 +673,9 @@ static cudaStream_t side_stream()
 
 static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
 {
+  static int tc = -1;
+  if (tc < 0) { const char* e = getenv("LIBXSMM_B200_SPMDM_TC"); tc = (e && *e) ? atoi(e) : 0; }
+  if (tc > 0 && !partial && a.ncols >= 48 && launch_compute_tc(a, stream)) return;   // tensor-core branch (spmdm_compute_tc.cu)
   if (launch_compute_tma(a, partial, stream)) return;   // TMA fast path (spmdm_compute_tma.cu)
   if (a.is_bf16) {
     if (partial) launch_compute_variant<true, true, 4>(a, stream);
