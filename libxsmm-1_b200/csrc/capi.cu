@@ -276,7 +276,7 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   const size_t row_bytes = ((ns * (g.bm + 1) * 2) + 255) & ~(size_t)255;
   const size_t col_bytes = ns * cap * 2, val_bytes = ns * cap * 4;
   c->arena_base = 0; c->staging = 0; c->table = 0;
-  XB_CUDA(cudaMalloc(&c->arena_base, row_bytes + col_bytes + val_bytes));
+  XB_CUDA(cudaMalloc(&c->arena_base, row_bytes + col_bytes + val_bytes + col_bytes));
   // per-tid staging slab for the legacy per-block entries on HOST matrices: an A block, or a B panel
   // (k x bn) followed by a C tile (bm x bn); the reference's slab holds the latter two (:148-155)
   {
@@ -297,6 +297,7 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena.rowidx = (uint16_t*)c->arena_base;
   c->arena.colidx = (uint16_t*)((char*)c->arena_base + row_bytes);
   c->arena.values = (float*)((char*)c->arena_base + row_bytes + col_bytes);
+  c->arena.tcoff = (uint16_t*)((char*)c->arena_base + row_bytes + col_bytes + val_bytes);
   c->table = (libxsmm_CSR_sparseslice*)malloc(sizeof(libxsmm_CSR_sparseslice) * ns);
   for (size_t s = 0; s < ns; ++s) {
     c->table[s].rowidx = c->arena.rowidx + s * (g.bm + 1);

@@ -33,7 +33,22 @@ struct SliceArena {
   uint16_t* rowidx;
   uint16_t* colidx;
   float* values;
+  uint16_t* tcoff;   // auxiliary (not part of the reference's slice), same indexing as colidx: where the nonzero
+                     // goes in the tensor-core branch's shared-memory A tile (xb_tc_pack)
 };
+
+// Tensor-core branch (spmdm_compute_tc.cu): A is rebuilt per k-block as two K-halves (k < 64, k >= 64), each
+// two K-major SWIZZLE_128B chunks of [128 rows x 32 k] fp32 (16 KiB).  For a nonzero at block-local row r
+// and column k: bit 15 = half, bits 0..14 = word offset inside the half (chunk, 8-row group, row, 16-byte
+// unit XOR row, word).  Rows are taken modulo the 128-row tile.
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__ uint16_t xb_tc_pack(int r, int k)
+{
+  const int row = r & 127, kk = k & 31;
+  const uint32_t off = (uint32_t)(((k >> 5) & 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) & 7) << 4) + ((kk & 3) << 2));
+  return (uint16_t)((off >> 2) | ((uint32_t)(k >> 6) << 15));
+}
+#endif
 
 constexpr int kSliceStripRows = 64;   // rows of one slice handled by one CTA of the slicing kernel
 

@@ -25,15 +25,18 @@ namespace xb {
 constexpr int TC_BM = 128;          // rows per CTA (UMMA M)
 constexpr int TC_BN = 128;          // columns per CTA (UMMA N)
 constexpr int TC_KC = 32;           // k per B chunk = one 128-byte swizzle row of fp32
-constexpr int TC_WORKERS = 8;       // worker warps (densify, split, epilogue)
+constexpr int TC_NB = 3;            // B stages
+constexpr int TC_WORKERS = 16;      // worker warps (densify, split, drain, epilogue)
+constexpr int TC_NQ = 16;           // nonzeros a worker thread keeps in registers per k-block
+constexpr int TC_WT = TC_WORKERS * 32;
 constexpr int TC_THREADS = (2 + TC_WORKERS) * 32;
 constexpr int TC_A_CHUNK = TC_BM * 128;             // bytes of one 128 x 32 fp32 K-major tile (16 KiB)
+constexpr int TC_A_HALF = 4 * TC_A_CHUNK;           // one half of a k-block (64 k): hi chunks 0,1 then lo chunks 0,1 (64 KiB)
 constexpr int TC_B_CHUNK = TC_KC * TC_BN * 4;       // bytes of one 32 x 128 fp32 chunk (16 KiB)
-constexpr int TC_SMEM_A_HI = 0;
-constexpr int TC_SMEM_A_LO = 4 * TC_A_CHUNK;                       // 64 KiB
-constexpr int TC_SMEM_B = 8 * TC_A_CHUNK;                          // 128 KiB: stage s -> raw at +s*32K, lo at +s*32K+16K
-constexpr int TC_SMEM_BAR = TC_SMEM_B + 4 * TC_B_CHUNK;            // 192 KiB
-constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 128;
+constexpr int TC_SMEM_A = 0;                                        // two halves, double buffered: 128 KiB
+constexpr int TC_SMEM_B = 2 * TC_A_HALF;                            // stage s: raw at +s*32K, lo at +s*32K+16K
+constexpr int TC_SMEM_BAR = TC_SMEM_B + TC_NB * 2 * TC_B_CHUNK;     // 224 KiB
+constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 256;
 
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
 {
@@ -76,26 +79,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// byte offset of element (row, k) inside the 4 x [128 rows x 128 B] K-major SWIZZLE_128B tile of A
-__device__ __forceinline__ uint32_t tc_a_offset(int row, int k)
-{
-  const int chunk = k >> 5, kk = k & 31;
-  return (uint32_t)(chunk * TC_A_CHUNK + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) & 7) << 4) + ((kk & 3) << 2));
-}
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
 spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeArgs p)
 {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bar = (uint64_t*)(smem + TC_SMEM_BAR);
-  uint64_t* b_full = bar;          // [2] TMA landed (tx bytes)
-  uint64_t* b_split = bar + 2;     // [2] workers wrote b_lo
-  uint64_t* b_free = bar + 4;      // [2] MMAs that read the stage have completed
-  uint64_t* a_ready = bar + 6;     // workers built A for this k-block
-  uint64_t* a_free = bar + 7;      // MMAs of the k-block have completed
-  uint64_t* acc_full = bar + 8;    // [2] the k-block's MMAs into accumulator buffer (kb & 1) have completed
-  uint64_t* acc_free = bar + 10;   // [2] the workers have drained that buffer
-  uint32_t* tmem_slot = (uint32_t*)(bar + 12);
+  uint64_t* b_full = bar;            // [3] TMA landed (tx bytes)
+  uint64_t* b_split = bar + 3;       // [3] workers wrote b_lo
+  uint64_t* b_free = bar + 6;        // [3] MMAs that read the stage have completed
+  uint64_t* a_ready = bar + 9;       // [2] workers built the A half (k 0..63 / 64..127 of the k-block)
+  uint64_t* a_free = bar + 11;       // [2] MMAs that read the A half have completed
+  uint64_t* acc_full = bar + 13;     // [2] the k-block's MMAs into accumulator buffer (kb & 1) have completed
+  uint64_t* acc_free = bar + 15;     // [2] the workers have drained that buffer
+  uint32_t* tmem_slot = (uint32_t*)(bar + 17);
 
   const Geom& g = p.g;
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -106,15 +102,17 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
   if (ml0 >= rows_in_block) return;
   const int tile_rows = min(TC_BM, rows_in_block - ml0);
   const int n0 = (int)blockIdx.x * TC_BN;
-  const int nchunks = g.kb * 4;
+  const int nsteps = g.kb * 2;       // one step = one half k-block = two B chunks
   const uint32_t sbase = smem_u32(smem);
 
   if (0 == tid) {
-    mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1);
-    mbar_init(&b_split[0], TC_WORKERS); mbar_init(&b_split[1], TC_WORKERS);
-    mbar_init(&b_free[0], 1); mbar_init(&b_free[1], 1);
-    mbar_init(a_ready, TC_WORKERS); mbar_init(a_free, 1);
-    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1); mbar_init(&acc_free[0], TC_WORKERS); mbar_init(&acc_free[1], TC_WORKERS);
+#pragma unroll
+    for (int i = 0; i < TC_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_split[i], TC_WORKERS); mbar_init(&b_free[i], 1); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_ready[i], TC_WORKERS); mbar_init(&a_free[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_WORKERS);
+    }
     mbar_fence_init();
   }
   if (1 == warp) {   // TMEM: 2 x 128 columns of fp32 accumulators (one warp allocates and later frees)
@@ -127,11 +125,11 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
   const uint32_t tmem_d = *tmem_slot;
 
   if (0 == warp) {
-    // ---------------- TMA producer: B chunks, two stages ----------------
+    // ---------------- TMA producer: B chunks through a 3-stage ring ----------------
     if (0 == lane) {
       tma_prefetch_desc(&tmB);
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c & 1, f = c >> 1;
+      for (int c = 0; c < nsteps * 2; ++c) {
+        const int s = c % TC_NB, f = c / TC_NB;
         if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
         mbar_arrive_expect_tx(&b_full[s], TC_B_CHUNK);
         unsigned char* dst = smem + TC_SMEM_B + s * 2 * TC_B_CHUNK;
@@ -146,127 +144,157 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = F32, A = B = TF32,
       // A K-major, B MN-major, N = 128, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < g.kb; ++kb) {
+      for (int t = 0; t < nsteps; ++t) {
+        const int kb = t >> 1, h = t & 1;
         // The accumulator of a k-block is drained into registers by the workers (IEEE adds) instead of being
         // carried in TMEM over the whole K loop: the tensor core truncates on every accumulation, and over
         // K/8*3 accumulations that bias would exceed the 1e-5 contract.  Two TMEM buffers alternate.
         const uint32_t tmem_acc = tmem_d + (uint32_t)((kb & 1) * TC_BN);
-        if (kb >= 2) mbar_wait(&acc_free[kb & 1], ((kb >> 1) - 1) & 1);
-        mbar_wait(a_ready, kb & 1);
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = kb * 4 + cc, s = c & 1;
-          mbar_wait(&b_split[s], (c >> 1) & 1);
+        if (0 == h && kb >= 2) mbar_wait(&acc_free[kb & 1], ((kb >> 1) - 1) & 1);
+        mbar_wait(&a_ready[h], kb & 1);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = 2 * t + j, s = c % TC_NB;
+          mbar_wait(&b_split[s], (c / TC_NB) & 1);
           tc_fence_after();
-          const uint32_t a_hi = sbase + TC_SMEM_A_HI + cc * TC_A_CHUNK;
-          const uint32_t a_lo = sbase + TC_SMEM_A_LO + cc * TC_A_CHUNK;
+          const uint32_t a_hi = sbase + TC_SMEM_A + h * TC_A_HALF + j * TC_A_CHUNK;
+          const uint32_t a_lo = a_hi + 2 * TC_A_CHUNK;
           const uint32_t b_hi = sbase + TC_SMEM_B + s * 2 * TC_B_CHUNK;
           const uint32_t b_lo = b_hi + TC_B_CHUNK;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            // A (K-major): 8 k = 32 bytes further inside the swizzled 128-byte rows; 8-row groups 1024 B apart
+            // A (K-major, SWIZZLE_128B): 8 k = 32 bytes further inside the 128-byte rows; 8-row groups 1024 B apart
             const uint64_t dah = tc_smem_desc(a_hi + ks * 32, 16, 1024, 2);
             const uint64_t dal = tc_smem_desc(a_lo + ks * 32, 16, 1024, 2);
             // B (MN-major TF32: only the 128-byte swizzle with 32-byte atoms exists; pinned with tools/umma_probe):
             // atoms of 4 k x 128 B, k groups 512 B apart (SBO), 32-column blocks 4096 B apart (LBO); 8 k = 1024 B
             const uint64_t dbh = tc_smem_desc(b_hi + ks * 1024, TC_KC * 128, 512, 1);
             const uint64_t dbl = tc_smem_desc(b_lo + ks * 1024, TC_KC * 128, 512, 1);
-            tc_mma_tf32(tmem_acc, dah, dbh, idesc, (cc > 0 || ks > 0) ? 1u : 0u);
+            tc_mma_tf32(tmem_acc, dah, dbh, idesc, (h > 0 || j > 0 || ks > 0) ? 1u : 0u);
             tc_mma_tf32(tmem_acc, dah, dbl, idesc, 1u);
             tc_mma_tf32(tmem_acc, dal, dbh, idesc, 1u);
           }
           tc_commit(&b_free[s]);
         }
-        tc_commit(a_free);
-        tc_commit(&acc_full[kb & 1]);
+        tc_commit(&a_free[h]);
+        if (1 == h) tc_commit(&acc_full[kb & 1]);
       }
     }
   }
   else {
-    // ---------------- workers: densify A, split B, epilogue ----------------
+    // ---------------- workers: densify A, split B, drain accumulators, epilogue ----------------
     const int w = warp - 2;                       // 0..7
     const int wt = tid - 64;                      // 0..255
     const size_t cap = (size_t)g.bm * g.bk;
-    // this thread's part of the output: row (quarter*32 + lane), 64 columns; warp w may touch TMEM lanes
-    // 32*(w%4) .. +31, and the two warps that share a lane quarter take 64 columns each
+    // this thread's part of the output: row (quarter*32 + lane), 32 columns; warp w may touch TMEM lanes
+    // 32*(w%4) .. +31, and the four warps that share a lane quarter take 32 columns each
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int chalf = (w >> 2) * 64;              // warps 2..5 -> columns 0..63; warps 6..9 -> 64..127
-    float run[64];
+    const int cgrp = (w >> 2) * 32;
+    float run[32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) run[j] = 0.f;
+    for (int j = 0; j < 32; ++j) run[j] = 0.f;
     auto drain = [&](int kbd) {                   // run += accumulator of k-block kbd
       mbar_wait(&acc_full[kbd & 1], (kbd >> 1) & 1);
       tc_fence_after();
+      uint32_t v[32];
+      tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((kbd & 1) * TC_BN + cgrp), v);
 #pragma unroll
-      for (int cb = 0; cb < 64; cb += 32) {
-        uint32_t v[32];
-        tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((kbd & 1) * TC_BN + chalf + cb), v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) run[cb + j] += __uint_as_float(v[j]);
-      }
+      for (int j = 0; j < 32; ++j) run[j] += __uint_as_float(v[j]);
       tc_fence_before();
       __syncwarp();
       if (0 == lane) mbar_arrive(&acc_free[kbd & 1]);
     };
-    for (int kb = 0; kb < g.kb; ++kb) {
-      // (1) A tile of this k-block: wait until the previous k-block's MMAs are done, zero, scatter
-      if (kb > 0) mbar_wait(a_free, (kb - 1) & 1);
-      {
-        uint4* z = (uint4*)(smem + TC_SMEM_A_HI);
-        for (int i = wt; i < (8 * TC_A_CHUNK) / 16; i += TC_WORKERS * 32) z[i] = make_uint4(0, 0, 0, 0);
+    // The tile's nonzeros of one k-block are one contiguous range of the slice.  Thread wt owns nonzeros
+    // first + wt + i*TC_WT; the first TC_NQ of them are fetched ONCE per k-block into registers (packed
+    // row|column and value), well before they are needed, and scattered twice (k < 64, k >= 64).
+    uint32_t pk[TC_NQ / 2]; float vv[TC_NQ];   // pk: two packed tcoff values (xb_tc_pack) per register
+    int first = 0, last = 0;
+    auto fetch = [&](int kbf) {
+      const int sidx = kbf * g.mb + mbi;
+      const uint16_t* ro = p.sl.rowidx + (size_t)sidx * (g.bm + 1) + ml0;
+      const uint16_t* ri = p.sl.tcoff + sidx * cap;
+      const float* va = p.sl.values + sidx * cap;
+      first = (int)__ldg(ro);
+      last = (int)__ldg(ro + tile_rows);
+      if (last < first) last = (int)__ldg(ro + tile_rows - 1);   // wrapped u16 counter of a full slice: last row reads as empty
+#pragma unroll
+      for (int i = 0; i < TC_NQ; ++i) {
+        const int q = first + wt + i * TC_WT;
+        uint32_t t = 0; vv[i] = 0.f;           // value 0 scatters +0 / +0 into a zeroed tile: harmless for absent entries
+        if (q < last) { t = (uint32_t)__ldg(ri + q); vv[i] = __ldg(va + q); }
+        if (i & 1) pk[i >> 1] |= t << 16; else pk[i >> 1] = t;
       }
-      asm volatile("bar.sync 1, %0;\n" ::"n"(TC_WORKERS * 32) : "memory");   // zero-fill complete before the scatter
+    };
+    fetch(0);
+    for (int t = 0; t < nsteps; ++t) {
+      const int kb = t >> 1, h = t & 1;
+      // (1) A half: wait until the MMAs that read this buffer (previous k-block) are done, zero, scatter.
+      //     The other half is being multiplied meanwhile.
+      if (kb > 0) mbar_wait(&a_free[h], (kb - 1) & 1);
+      unsigned char* abuf = smem + TC_SMEM_A + h * TC_A_HALF;
       {
-        const int s = kb * g.mb + mbi;
-        const uint16_t* ro = p.sl.rowidx + (size_t)s * (g.bm + 1) + ml0;
-        const uint16_t* co = p.sl.colidx + s * cap;
-        const float* va = p.sl.values + s * cap;
-        for (int r = w; r < tile_rows; r += TC_WORKERS) {      // a warp per row: coalesced reads of its nonzeros
-          const int lo = (int)__ldg(ro + r), hi = (int)__ldg(ro + r + 1);   // hi < lo (wrapped counter) = empty row
-          for (int q = lo + lane; q < hi; q += 32) {
-            const int k = (int)__ldg(co + q);
-            const float v = __ldg(va + q);
-            const float vh = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-            const uint32_t off = tc_a_offset(r, k);
-            *(float*)(smem + TC_SMEM_A_HI + off) = vh;
-            *(float*)(smem + TC_SMEM_A_LO + off) = v - vh;
-          }
+        uint4* z = (uint4*)abuf;
+#pragma unroll
+        for (int i = 0; i < TC_A_HALF / 16 / TC_WT; ++i) z[wt + i * TC_WT] = make_uint4(0, 0, 0, 0);
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(TC_WT) : "memory");   // zero-fill complete before the scatter
+      auto put = [&](uint32_t t, float v) {   // t = xb_tc_pack(row, k): half in bit 15, word offset below
+        if ((int)((t >> 15) & 1u) == h) {
+          const uint32_t off = (t & 0x7FFFu) << 2;
+          const float vh = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+          *(float*)(abuf + off) = vh;
+          *(float*)(abuf + 2 * TC_A_CHUNK + off) = v - vh;
         }
+      };
+#pragma unroll
+      for (int i = 0; i < TC_NQ; ++i) {
+        const int q = first + wt + i * TC_WT;
+        if (q < last) put((i & 1) ? (pk[i >> 1] >> 16) : (pk[i >> 1] & 0xFFFFu), vv[i]);
+      }
+      if (first + TC_NQ * TC_WT < last) {   // denser than TC_NQ*TC_WT nonzeros per tile: the rest straight from memory
+        const int sidx = kb * g.mb + mbi;
+        const uint16_t* ri = p.sl.tcoff + sidx * cap;
+        const float* va = p.sl.values + sidx * cap;
+#pragma unroll 2
+        for (int q = first + wt + TC_NQ * TC_WT; q < last; q += TC_WT) put((uint32_t)__ldg(ri + q), __ldg(va + q));
       }
       fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
-      if (0 == lane) mbar_arrive(a_ready);
-      // (2) B chunks of this k-block: b_lo = b - trunc_tf32(b), same (swizzled) addresses
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = kb * 4 + cc, s = c & 1;
-        mbar_wait(&b_full[s], (c >> 1) & 1);
+      if (0 == lane) mbar_arrive(&a_ready[h]);
+      if (1 == h && kb + 1 < g.kb) fetch(kb + 1);   // registers are free again: next k-block's nonzeros, consumed a step later
+      // (2) the two B chunks of this step: b_lo = b - trunc_tf32(b), same (swizzled) addresses
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = 2 * t + j, s = c % TC_NB;
+        mbar_wait(&b_full[s], (c / TC_NB) & 1);
         const uint4* src = (const uint4*)(smem + TC_SMEM_B + s * 2 * TC_B_CHUNK);
         uint4* dst = (uint4*)(smem + TC_SMEM_B + s * 2 * TC_B_CHUNK + TC_B_CHUNK);
 #pragma unroll
-        for (int i = 0; i < TC_B_CHUNK / 16 / (TC_WORKERS * 32); ++i) {
-          const uint4 b = src[wt + i * TC_WORKERS * 32];
+        for (int i = 0; i < TC_B_CHUNK / 16 / TC_WT; ++i) {
+          const uint4 b = src[wt + i * TC_WT];
           uint4 l;
           l.x = __float_as_uint(__uint_as_float(b.x) - __uint_as_float(b.x & 0xFFFFE000u));
           l.y = __float_as_uint(__uint_as_float(b.y) - __uint_as_float(b.y & 0xFFFFE000u));
           l.z = __float_as_uint(__uint_as_float(b.z) - __uint_as_float(b.z & 0xFFFFE000u));
           l.w = __float_as_uint(__uint_as_float(b.w) - __uint_as_float(b.w & 0xFFFFE000u));
-          dst[wt + i * TC_WORKERS * 32] = l;
+          dst[wt + i * TC_WT] = l;
         }
         fence_proxy_async();
         __syncwarp();
         if (0 == lane) mbar_arrive(&b_split[s]);
       }
       // (3) drain the previous k-block's accumulator while this k-block's MMAs run
-      if (kb > 0) drain(kb - 1);
+      if (0 == h && kb > 0) drain(kb - 1);
     }
     drain(g.kb - 1);
     // (4) epilogue: + beta*C, 16-byte streaming stores
     const size_t crow = (size_t)(mbi * g.bm + ml0 + row - p.row_origin);
     if (row < tile_rows) {
-      float* dst = p.c + crow * p.ldc + n0 + chalf;
+      float* dst = p.c + crow * p.ldc + n0 + cgrp;
 #pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        const int col = n0 + chalf + j;
+      for (int j = 0; j < 32; j += 4) {
+        const int col = n0 + cgrp + j;
         float4 o = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
         if (col + 3 < p.ncols) {
           if (0.f != p.beta) {
@@ -278,7 +306,7 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
         else {
           const float e[4] = { o.x, o.y, o.z, o.w };
 #pragma unroll
-          for (int t = 0; t < 4; ++t) if (col + t < p.ncols) dst[j + t] = (0.f != p.beta) ? fmaf(p.beta, dst[j + t], e[t]) : e[t];
+          for (int t2 = 0; t2 < 4; ++t2) if (col + t2 < p.ncols) dst[j + t2] = (0.f != p.beta) ? fmaf(p.beta, dst[j + t2], e[t2]) : e[t2];
         }
       }
     }

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
   uint16_t* ro = p.out.rowidx + (size_t)s * (g.bm + 1);
   uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
   float* va = p.out.values + (size_t)s * g.bm * g.bk;
+  uint16_t* ri = p.out.tcoff + (size_t)s * g.bm * g.bk;
   const uint32_t lt = (1u << lane) - 1u;
   for (int r = warp; r < rcount; r += K1_WARPS) {
     uint32_t pos = base + row_off[r];
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
         const uint32_t q = pos + __popc(bal & lt);
         co[q] = (uint16_t)k;
         va[q] = v;
+        ri[q] = xb_tc_pack(r0 + r, k);
       }
       pos += __popc(bal);
     }
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
   uint16_t* ro = p.out.rowidx + (size_t)s * (g.bm + 1);
   uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
   float* va = p.out.values + (size_t)s * g.bm * g.bk;
+  uint16_t* ri = p.out.tcoff + (size_t)s * g.bm * g.bk;
   const uint32_t lt = (1u << lane) - 1u;
   const int k = lane * 4;
 #pragma unroll
@@ -319,10 +322,11 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
       uint32_t q = pos + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
       if (0 == lane) ro[row_lo + j] = (uint16_t)pos;
       if (m) {   // few lanes hold nonzeros in the sparse regime: one divergent region per row
-        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); ++q; }
-        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); ++q; }
-        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); ++q; }
-        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); }
+        const int rr = row_lo + j;
+        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); ri[q] = xb_tc_pack(rr, k); ++q; }
+        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); ri[q] = xb_tc_pack(rr, k + 1); ++q; }
+        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); ri[q] = xb_tc_pack(rr, k + 2); ++q; }
+        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); ri[q] = xb_tc_pack(rr, k + 3); }
       }
       pos += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     }
@@ -671,11 +675,15 @@ static cudaStream_t side_stream()
   return s;
 }
 
-static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
+static int tc_mode()
 {
   static int tc = -1;
   if (tc < 0) { const char* e = getenv("LIBXSMM_B200_SPMDM_TC"); tc = (e && *e) ? atoi(e) : 0; }
-  if (tc > 0 && !partial && a.ncols >= 48 && launch_compute_tc(a, stream)) return;   // tensor-core branch (spmdm_compute_tc.cu)
+  return tc;
+}
+
+static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
+{
   if (launch_compute_tma(a, partial, stream)) return;   // TMA fast path (spmdm_compute_tma.cu)
   if (a.is_bf16) {
     if (partial) launch_compute_variant<true, true, 4>(a, stream);
@@ -690,6 +698,7 @@ static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
 void launch_compute(const ComputeArgs& args, cudaStream_t stream)
 {
   if (args.ncols <= 0 || args.mb_count <= 0) return;
+  if (tc_mode() > 0 && launch_compute_tc(args, stream)) return;   // tensor-core branch: one launch over all columns
   const int c_lo = args.col_origin, c_hi = args.col_origin + args.ncols;
   const int cut[4] = { c_lo, min(max(args.modes.n_full_end, c_lo), c_hi), min(max(args.modes.tail_from, c_lo), c_hi), c_hi };
   // the narrow last block (at most bn - 1 columns, two small launches) runs on a side stream, forked from
