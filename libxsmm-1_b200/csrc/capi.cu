@@ -151,7 +151,7 @@ static void compute_whole(const libxsmm_spmdm_handle* handle, char transb, char 
   a.ldb = a.transb ? c->g.k : c->g.n;
   a.ldc = a.transc ? c->g.m : c->g.n;
   a.beta = beta; a.g = c->g; a.mb_first = 0; a.mb_count = c->g.mb;
-  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w);
+  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0;
   launch_compute(a, stream);
 }
 
@@ -208,7 +208,7 @@ static void compute_block(const libxsmm_spmdm_handle* handle, char transb, char 
   const bool dev_b = is_device_ptr(b_in), dev_c = is_device_ptr(c_in);
   ComputeArgs a;
   a.sl = c->arena; a.transb = tb; a.transc = tc; a.is_bf16 = is_bf16; a.beta = beta; a.g = g;
-  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w);
+  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0;   // legacy block: no tensor-core twin
   char* slab = c->staging + (size_t)tid * c->staging_per_tid;
   const size_t slab_b_bytes = (((size_t)g.k * g.bn * 4) + 255) & ~(size_t)255;
   float* c_stage = (float*)(slab + slab_b_bytes);
@@ -276,7 +276,8 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   const size_t row_bytes = ((ns * (g.bm + 1) * 2) + 255) & ~(size_t)255;
   const size_t col_bytes = ns * cap * 2, val_bytes = ns * cap * 4;
   c->arena_base = 0; c->staging = 0; c->table = 0;
-  XB_CUDA(cudaMalloc(&c->arena_base, row_bytes + col_bytes + val_bytes + col_bytes));
+  const size_t nnz_bytes = ((ns * 4) + 255) & ~(size_t)255;
+  XB_CUDA(cudaMalloc(&c->arena_base, row_bytes + col_bytes + val_bytes + col_bytes + nnz_bytes));
   // per-tid staging slab for the legacy per-block entries on HOST matrices: an A block, or a B panel
   // (k x bn) followed by a C tile (bm x bn); the reference's slab holds the latter two (:148-155)
   {
@@ -298,6 +299,8 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena.colidx = (uint16_t*)((char*)c->arena_base + row_bytes);
   c->arena.values = (float*)((char*)c->arena_base + row_bytes + col_bytes);
   c->arena.tcoff = (uint16_t*)((char*)c->arena_base + row_bytes + col_bytes + val_bytes);
+  c->arena.slice_nnz = (uint32_t*)((char*)c->arena_base + row_bytes + col_bytes + val_bytes + col_bytes);
+  XB_CUDA(cudaMemset(c->arena.slice_nnz, 0, nnz_bytes));
   c->table = (libxsmm_CSR_sparseslice*)malloc(sizeof(libxsmm_CSR_sparseslice) * ns);
   for (size_t s = 0; s < ns; ++s) {
     c->table[s].rowidx = c->arena.rowidx + s * (g.bm + 1);
@@ -478,7 +481,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
       ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
       ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
       ca.beta = beta_f; ca.g = g; ca.mb_first = 0; ca.mb_count = g.mb;
-      ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes;
+      ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0;
       launch_compute(ca, c->xs[1]);
     }
     XB_CUDA(cudaEventRecord(c->xev[p], c->xs[1]));

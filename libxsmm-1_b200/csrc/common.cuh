@@ -33,6 +33,7 @@ struct SliceArena {
   uint16_t* rowidx;
   uint16_t* colidx;
   float* values;
+  uint32_t* slice_nnz;   // auxiliary: true nonzero count of every slice (the u16 row pointers wrap at 65536)
   uint16_t* tcoff;   // auxiliary (not part of the reference's slice), same indexing as colidx: where the nonzero
                      // goes in the tensor-core branch's shared-memory A tile (xb_tc_pack)
 };
@@ -81,7 +82,28 @@ struct ComputeArgs {
   int col_origin;           // global column that local column 0 corresponds to
   int ncols;                // local columns computed
   ColModes modes;           // in GLOBAL column numbering
+  // sparse / tensor-core twin launches: both kernels are enqueued, each CTA sums slice_nnz and only the
+  // selected kernel does the work (dense <=> total nnz >= tc_min_nnz).  tc_twin = 0: no twin, always run.
+  int tc_twin;
+  unsigned long long tc_min_nnz;
 };
+
+#if defined(__CUDACC__)
+// total nonzero count over all slices, evaluated redundantly by every CTA (ns is a few hundred at most)
+__device__ __forceinline__ unsigned long long xb_total_nnz(const uint32_t* slice_nnz, int ns)
+{
+  __shared__ unsigned long long xb_nnz_s;
+  if (threadIdx.x < 32) {
+    unsigned long long t = 0;
+    for (int i = (int)threadIdx.x; i < ns; i += 32) t += slice_nnz[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    if (0 == threadIdx.x) xb_nnz_s = t;
+  }
+  __syncthreads();
+  return xb_nnz_s;
+}
+#endif
 
 void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream);
 void launch_compute(const ComputeArgs& args, cudaStream_t stream);

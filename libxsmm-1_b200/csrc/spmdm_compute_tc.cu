@@ -94,6 +94,7 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
   uint32_t* tmem_slot = (uint32_t*)(bar + 17);
 
   const Geom& g = p.g;
+  if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // sparse regime: the CUDA-core twin does this multiply
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_per_mb = (g.bm + TC_BM - 1) / TC_BM;
   const int mbi = p.mb_first + (int)blockIdx.y / tiles_per_mb;

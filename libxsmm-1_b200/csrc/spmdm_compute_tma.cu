@@ -92,6 +92,7 @@ spmdm_compute_tma_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeA
   uint64_t* empty = full + STAGES;
 
   const Geom& g = p.g;
+  if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) >= p.tc_min_nnz) return;   // the tensor-core twin does this multiply
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_per_mb = (g.bm + TM - 1) / TM;
   const int mbi = p.mb_first + (int)blockIdx.y / tiles_per_mb;

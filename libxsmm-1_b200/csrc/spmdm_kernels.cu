@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
       pos += __popc(bal);
     }
   }
-  if (strip == nstrips - 1 && 0 == tid) ro[nrows] = (uint16_t)(base + strip_tot[strip]);
+  if (strip == nstrips - 1 && 0 == tid) {
+    ro[nrows] = (uint16_t)(base + strip_tot[strip]);
+    p.out.slice_nnz[s] = base + strip_tot[strip];
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -300,7 +303,10 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
     }
     pos = __shfl_sync(0xffffffffu, inc - t, warp);
     const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    if (0 == tid) p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
+    if (0 == tid) {
+      p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
+      p.out.slice_nnz[s] = total;
+    }
   }
 
   // ---- phase 2: positions and stores -----------------------------------------------------------------------
@@ -323,10 +329,11 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
       if (0 == lane) ro[row_lo + j] = (uint16_t)pos;
       if (m) {   // few lanes hold nonzeros in the sparse regime: one divergent region per row
         const int rr = row_lo + j;
-        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); ri[q] = xb_tc_pack(rr, k); ++q; }
-        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); ri[q] = xb_tc_pack(rr, k + 1); ++q; }
-        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); ri[q] = xb_tc_pack(rr, k + 2); ++q; }
-        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); ri[q] = xb_tc_pack(rr, k + 3); }
+        // tcoff feeds the tensor-core branch, which exists for fp32 inputs only
+        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); if (!BF16) ri[q] = xb_tc_pack(rr, k); ++q; }
+        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); if (!BF16) ri[q] = xb_tc_pack(rr, k + 1); ++q; }
+        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); if (!BF16) ri[q] = xb_tc_pack(rr, k + 2); ++q; }
+        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); if (!BF16) ri[q] = xb_tc_pack(rr, k + 3); }
       }
       pos += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     }
@@ -439,6 +446,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) spmdm_compute_kernel(const Comp
   extern __shared__ __align__(128) unsigned char smem[];
 
   const Geom& g = p.g;
+  if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) >= p.tc_min_nnz) return;   // the tensor-core twin does this multiply
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_per_mb = (g.bm + TM - 1) / TM;
   const int mbi = p.mb_first + (int)blockIdx.y / tiles_per_mb;
@@ -675,11 +683,13 @@ static cudaStream_t side_stream()
   return s;
 }
 
+// LIBXSMM_B200_SPMDM_TC: "0" never use the tensor-core branch, "1" always (when the panel qualifies),
+// unset / anything else: by density -- total nnz >= 7 % of M*K, decided on the device.
 static int tc_mode()
 {
-  static int tc = -1;
-  if (tc < 0) { const char* e = getenv("LIBXSMM_B200_SPMDM_TC"); tc = (e && *e) ? atoi(e) : 0; }
-  return tc;
+  const char* e = getenv("LIBXSMM_B200_SPMDM_TC");
+  if (0 == e || 0 == *e) return 2;
+  return ('0' == *e) ? 0 : (('1' == *e) ? 1 : 2);
 }
 
 static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
@@ -698,7 +708,18 @@ static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
 void launch_compute(const ComputeArgs& args, cudaStream_t stream)
 {
   if (args.ncols <= 0 || args.mb_count <= 0) return;
-  if (tc_mode() > 0 && launch_compute_tc(args, stream)) return;   // tensor-core branch: one launch over all columns
+  // Tensor-core twin (fp32, N/N/N, aligned panels): the dense kernel is enqueued next to the sparse ones and
+  // every CTA of both reads the slices' nonzero counts; only the selected side does the work.
+  ComputeArgs targs = args;
+  const int mode = (0 == args.tc_twin) ? tc_mode() : 0;
+  targs.tc_twin = 0;
+  if (mode > 0) {
+    targs.tc_twin = 1;
+    targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)(0.07 * (double)args.g.m * (double)args.g.k);
+    if (!launch_compute_tc(targs, stream)) targs.tc_twin = 0;
+    else if (1 == mode) return;   // forced: nothing for the sparse kernels to do
+  }
+  const ComputeArgs& args2 = targs;
   const int c_lo = args.col_origin, c_hi = args.col_origin + args.ncols;
   const int cut[4] = { c_lo, min(max(args.modes.n_full_end, c_lo), c_hi), min(max(args.modes.tail_from, c_lo), c_hi), c_hi };
   // the narrow last block (at most bn - 1 columns, two small launches) runs on a side stream, forked from
@@ -716,7 +737,7 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
   for (int part = 2; part >= 0; --part) {
     const int lo = cut[part], hi = cut[part + 1];
     if (hi <= lo) continue;
-    ComputeArgs a = args;
+    ComputeArgs a = args2;
     const size_t esz = args.is_bf16 ? 2 : 4;
     const long long shift = lo - c_lo;
     a.b = (const char*)args.b + (args.transb ? (size_t)shift * args.ldb * esz : (size_t)shift * esz);

@@ -11,6 +11,15 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def cuda_core_path(monkeypatch):
+    """These tests assert BIT equality with the oracle, which holds for the CUDA-core kernels (they keep the
+    reference's rounding sequence).  The tensor-core branch that takes over dense fp32 problems is covered,
+    against the relative-error contract, by tests/test_spmdm_tc_gpu.py."""
+    monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", "0")
+
+
 RTOL_F32 = 1e-5
 RTOL_BF16 = 1e-2
 
