@@ -134,8 +134,11 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
         if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
         mbar_arrive_expect_tx(&b_full[s], TC_B_CHUNK);
         unsigned char* dst = smem + TC_SMEM_B + s * 2 * TC_B_CHUNK;
+        if (p.transb) tma_load_2d(dst, &tmB, c * TC_KC, n0, &b_full[s]);   // B stored n x k: one box of 128 n-rows x 32 k (K-major operand)
+        else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * (TC_KC * 128), &tmB, n0 + 32 * j, c * TC_KC, &b_full[s]);
+          for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * (TC_KC * 128), &tmB, n0 + 32 * j, c * TC_KC, &b_full[s]);
+        }
       }
     }
   }
@@ -144,7 +147,9 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
     if (0 == lane) {
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = F32, A = B = TF32,
       // A K-major, B MN-major, N = 128, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // (B stored n x k, transb = 'T', is a K-major operand: plain SWIZZLE_128B rows of 32 k)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | ((p.transb ? 0u : 1u) << 16) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t b_kstep = p.transb ? 32u : 1024u, b_lbo = p.transb ? 16u : (uint32_t)(TC_KC * 128), b_sbo = p.transb ? 1024u : 512u, b_lay = p.transb ? 2u : 1u;
       for (int t = 0; t < nsteps; ++t) {
         const int kb = t >> 1, h = t & 1;
         // The accumulator of a k-block is drained into registers by the workers (IEEE adds) instead of being
@@ -169,8 +174,8 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
             const uint64_t dal = tc_smem_desc(a_lo + ks * 32, 16, 1024, 2);
             // B (MN-major TF32: only the 128-byte swizzle with 32-byte atoms exists; pinned with tools/umma_probe):
             // atoms of 4 k x 128 B, k groups 512 B apart (SBO), 32-column blocks 4096 B apart (LBO); 8 k = 1024 B
-            const uint64_t dbh = tc_smem_desc(b_hi + ks * 1024, TC_KC * 128, 512, 1);
-            const uint64_t dbl = tc_smem_desc(b_lo + ks * 1024, TC_KC * 128, 512, 1);
+            const uint64_t dbh = tc_smem_desc(b_hi + ks * b_kstep, b_lbo, b_sbo, b_lay);
+            const uint64_t dbl = tc_smem_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lay);
             tc_mma_tf32(tmem_acc, dah, dbh, idesc, (h > 0 || j > 0 || ks > 0) ? 1u : 0u);
             tc_mma_tf32(tmem_acc, dah, dbl, idesc, 1u);
             tc_mma_tf32(tmem_acc, dal, dbh, idesc, 1u);
@@ -289,25 +294,38 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
       if (0 == h && kb > 0) drain(kb - 1);
     }
     drain(g.kb - 1);
-    // (4) epilogue: + beta*C, 16-byte streaming stores
+    // (4) epilogue: + beta*C.  C stored m x n: 16-byte streaming stores along the thread's row; C stored n x m
+    // (transc = 'T'): the 32 lanes of a warp hold 32 consecutive m, so every store instruction is one full line
     const size_t crow = (size_t)(mbi * g.bm + ml0 + row - p.row_origin);
     if (row < tile_rows) {
-      float* dst = p.c + crow * p.ldc + n0 + cgrp;
+      if (p.transc) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = n0 + cgrp + j;
-        float4 o = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
-        if (col + 3 < p.ncols) {
-          if (0.f != p.beta) {
-            const float4 cin = *(const float4*)(dst + j);
-            o.x = fmaf(p.beta, cin.x, o.x); o.y = fmaf(p.beta, cin.y, o.y); o.z = fmaf(p.beta, cin.z, o.z); o.w = fmaf(p.beta, cin.w, o.w);
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + cgrp + j;
+          if (col < p.ncols) {
+            float* dst = p.c + (size_t)col * p.ldc + crow;
+            *dst = (0.f != p.beta) ? fmaf(p.beta, *dst, run[j]) : run[j];
           }
-          st_global_cs_f4(dst + j, o);
         }
-        else {
-          const float e[4] = { o.x, o.y, o.z, o.w };
+      }
+      else {
+        float* dst = p.c + crow * p.ldc + n0 + cgrp;
 #pragma unroll
-          for (int t2 = 0; t2 < 4; ++t2) if (col + t2 < p.ncols) dst[j + t2] = (0.f != p.beta) ? fmaf(p.beta, dst[j + t2], e[t2]) : e[t2];
+        for (int j = 0; j < 32; j += 4) {
+          const int col = n0 + cgrp + j;
+          float4 o = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
+          if (col + 3 < p.ncols) {
+            if (0.f != p.beta) {
+              const float4 cin = *(const float4*)(dst + j);
+              o.x = fmaf(p.beta, cin.x, o.x); o.y = fmaf(p.beta, cin.y, o.y); o.z = fmaf(p.beta, cin.z, o.z); o.w = fmaf(p.beta, cin.w, o.w);
+            }
+            st_global_cs_f4(dst + j, o);
+          }
+          else {
+            const float e[4] = { o.x, o.y, o.z, o.w };
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) if (col + t2 < p.ncols) dst[j + t2] = (0.f != p.beta) ? fmaf(p.beta, dst[j + t2], e[t2]) : e[t2];
+          }
         }
       }
     }
@@ -321,15 +339,18 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
 }
 
 bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
-                              unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows);
+                              unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows, bool atom32);
 
 // returns false when the panel does not qualify (caller falls back to the CUDA-core kernels)
 bool launch_compute_tc(const ComputeArgs& a, cudaStream_t stream)
 {
-  if (a.is_bf16 || a.transb || a.transc) return false;
-  if (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3)) return false;
+  if (a.is_bf16) return false;
+  if (!a.transc && (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3))) return false;
   CUtensorMap map;
-  if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 4, 32, TC_KC)) return false;
+  if (a.transb) {   // B stored n x k: inner dimension k, box 32 k x 128 n, plain 128-byte swizzle
+    if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.g.k, (unsigned long long)a.ncols, (unsigned long long)a.ldb * 4, 32, TC_BN, false)) return false;
+  }
+  else if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 4, 32, TC_KC, true)) return false;
   static bool configured = false;
   if (!configured) {
     XB_CUDA(cudaFuncSetAttribute(spmdm_compute_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));

@@ -321,8 +321,9 @@ bool make_tensor_map_2d(CUtensorMap* map, const void* base, int elem_bytes, unsi
 }
 
 bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
-                              unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows)
+                              unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows, bool atom32)
 {
+  // atom32: 128-byte swizzle with 32-byte atoms (the only layout tcgen05 accepts for MN-major TF32 operands)
   EncodeTiledFn fn = encode_tiled();
   if (0 == fn) return false;
   if (0 != ((uintptr_t)base & 15) || 0 != (row_pitch_bytes & 15) || box_cols * elem_bytes != 128 || box_rows > 256) return false;
@@ -332,7 +333,7 @@ bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes
   const cuuint32_t box[2] = { box_cols, box_rows };
   const cuuint32_t estr[2] = { 1, 1 };
   const CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        (4 == elem_bytes) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return CUDA_SUCCESS == r;
 }
 

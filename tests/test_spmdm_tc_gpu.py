@@ -52,6 +52,25 @@ def test_tc_matches_oracle(gpu, oracle, monkeypatch, mode, M, N, K, density, bet
     gpu.check()
 
 
+@pytest.mark.parametrize("ta,tb,tc", [("T", "N", "T"), ("N", "T", "N"), ("T", "T", "T"), ("N", "N", "T"), ("T", "T", "N")])
+@pytest.mark.parametrize("M,N,K,density,beta", [(260, 200, 300, 0.5, 0.0), (512, 384, 640, 0.2, 0.5), (1024, 256, 512, 0.5, 1.0)])
+def test_tc_transposed_variants(gpu, oracle, monkeypatch, ta, tb, tc, M, N, K, density, beta):
+    """the sample's "weight update" (T/N/T) and "backprop" (N/T/N) variants and the other flag combinations:
+    B stored n x k is a K-major tensor-core operand, C stored n x m is written one full line per instruction."""
+    monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", "1")
+    A, B, C0 = gpu.workloads.spmdm_inputs(M, N, K, density, seed=M + K, transa=ta, transb=tb, transc=tc)
+    g, sl, C = gpu_spmdm(gpu, A, B, C0, M, N, K, ta, tb, tc, beta)
+    og, osl, OC = oracle_spmdm(oracle, g, A, B, C0, ta, tb, tc, float(beta))
+    valid_slices_equal(og, sl, osl)
+    err = rel(C, OC)
+    assert err <= RTOL_F32, "relative error %g" % err
+    monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", "0")
+    _, _, C_cc = gpu_spmdm(gpu, A, B, C0, M, N, K, ta, tb, tc, beta)
+    if K % 4 == 0 or tb == "N":      # the panel qualified for the tensor-core kernel: different rounding sequence
+        assert not np.array_equal(C.view(np.uint32), C_cc.view(np.uint32))
+    gpu.check()
+
+
 def test_sparse_problem_stays_bit_exact_in_auto_mode(gpu, oracle, monkeypatch):
     """below the density threshold the CUDA-core twin runs: same bits as the oracle."""
     monkeypatch.delenv("LIBXSMM_B200_SPMDM_TC", raising=False)
