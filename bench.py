@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--others", default="c1,c3,c4,c5", help="extra workloads reported inside the line (N=1 only); '' = none")
+    ap.add_argument("--others", default="c1,c3,c4,c4-tnt,c4-ntn,c5", help="extra workloads reported inside the line (N=1 only); '' = none")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -108,7 +108,8 @@ __device__ __forceinline__ unsigned long long xb_total_nnz(const uint32_t* slice
 void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream);
 void launch_compute(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tma(const ComputeArgs& args, bool partial, cudaStream_t stream);
-bool launch_compute_tc(const ComputeArgs& args, cudaStream_t stream);   // tcgen05 dense branch; false: does not qualify   // false: panel does not qualify
+bool launch_compute_tc(const ComputeArgs& args, cudaStream_t stream);
+bool launch_compute_mma(const ComputeArgs& args, cudaStream_t stream);   // warp-MMA gather kernel for bf16 slices; false: does not qualify   // tcgen05 dense branch; false: does not qualify   // false: panel does not qualify
 
 // ---- FSSPMDM --------------------------------------------------------------------------------
 struct FsOperator;   // fsspmdm.cu

@@ -381,6 +381,8 @@ bool launch_compute_tma(const ComputeArgs& a, bool partial, cudaStream_t stream)
       case 2: return launch_tma_variant<true, 4, 8, 16, 4, false>(a, stream);
       case 3: return launch_tma_variant<true, 8, 16, 8, 3, false>(a, stream);
       case 4: return launch_tma_variant<true, 8, 8, 8, 3, false>(a, stream);
+      case 5: return launch_tma_variant<true, 8, 4, 32, 3, false>(a, stream);
+      case 6: return launch_tma_variant<true, 8, 4, 24, 3, false>(a, stream);
       default: return launch_tma_variant<true, 8, 8, 16, 3, false>(a, stream);
     }
   }

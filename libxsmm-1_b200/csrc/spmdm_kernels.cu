@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
         const uint32_t q = pos + __popc(bal & lt);
         co[q] = (uint16_t)k;
         va[q] = v;
-        ri[q] = xb_tc_pack(r0 + r, k);
+        ri[q] = p.is_bf16 ? (uint16_t)(r0 + r) : xb_tc_pack(r0 + r, k);
       }
       pos += __popc(bal);
     }
@@ -329,11 +329,12 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
       if (0 == lane) ro[row_lo + j] = (uint16_t)pos;
       if (m) {   // few lanes hold nonzeros in the sparse regime: one divergent region per row
         const int rr = row_lo + j;
-        // tcoff feeds the tensor-core branch, which exists for fp32 inputs only
-        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); if (!BF16) ri[q] = xb_tc_pack(rr, k); ++q; }
-        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); if (!BF16) ri[q] = xb_tc_pack(rr, k + 1); ++q; }
-        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); if (!BF16) ri[q] = xb_tc_pack(rr, k + 2); ++q; }
-        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); if (!BF16) ri[q] = xb_tc_pack(rr, k + 3); }
+        // auxiliary per-nonzero word: fp32 slices -> position in the tcgen05 branch's A tile; bf16 slices -> the
+        // block-local row (the warp-MMA kernel gathers nonzeros of 16 rows into one instruction)
+        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k); ++q; }
+        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 1); ++q; }
+        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 2); ++q; }
+        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 3); }
       }
       pos += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     }
@@ -708,6 +709,12 @@ static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
 void launch_compute(const ComputeArgs& args, cudaStream_t stream)
 {
   if (args.ncols <= 0 || args.mb_count <= 0) return;
+  // bf16 inputs: the warp-level tensor-core gather kernel (opt-in experiment, slower than the CUDA-core kernel
+  // on B200: see spmdm_compute_mma.cu) covers all columns in one launch
+  if (args.is_bf16 && 0 == args.tc_twin) {
+    const char* e = getenv("LIBXSMM_B200_SPMDM_MMA");
+    if (e && '1' == *e && launch_compute_mma(args, stream)) return;
+  }
   // Tensor-core twin (fp32, N/N/N, aligned panels): the dense kernel is enqueued next to the sparse ones and
   // every CTA of both reads the slices' nonzero counts; only the selected side does the work.
   ComputeArgs targs = args;
