@@ -63,7 +63,38 @@ struct SpmdmCtx {
   size_t d_a_bytes, d_b_bytes, d_c_bytes;
   cudaStream_t xs[3];
   cudaEvent_t xev[kExecPanels + 1];
+  // density feedback: the slicing kernels publish the total nonzero count of the last completed pass into
+  // mapped pinned memory; the host uses it (one call late, never for correctness) to avoid enqueueing the
+  // kernel twin that will not be selected and the auxiliary arrays only that twin reads
+  unsigned long long* h_nnz;      // host view (~0 = unknown)
+  unsigned long long* d_nnz;      // device view of the same word
+  unsigned long long* d_acc;      // device counters {sum, slices done}
+  bool aux_written;               // the auxiliary per-nonzero words of the current slices are valid
 };
+
+// 0 unknown (first call), 1 sparse, 2 dense according to the last completed slicing pass (thresholds of
+// launch_compute: 7 % fp32, 1.5 % bf16)
+static int density_hint(const SpmdmCtx* c, int is_bf16)
+{
+  const unsigned long long n = c->h_nnz ? *(volatile unsigned long long*)c->h_nnz : ~0ull;
+  if (~0ull == n) return 0;
+  const double thr = (is_bf16 ? 0.015 : 0.07) * (double)c->g.m * (double)c->g.k;
+  return ((double)n < thr) ? 1 : 2;   // either way the result is correct; a wrong guess only costs speed for one call
+}
+
+static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole)
+{
+  a->acc = c->d_acc; a->host_total = c->d_nnz; a->total_slices = c->g.mb * c->g.kb;
+  a->write_aux = (!whole || 1 != density_hint(c, is_bf16)) ? 1 : 0;
+  if (whole) c->aux_written = (0 != a->write_aux);
+  else c->aux_written = true;
+}
+
+static int compute_policy(const SpmdmCtx* c, int is_bf16)
+{
+  if (!c->aux_written) return 1;      // the slices carry no auxiliary words: CUDA cores only
+  return density_hint(c, is_bf16);
+}
 
 static std::mutex g_reg_mtx;
 static std::unordered_map<const void*, SpmdmCtx*> g_registry;   // keyed by the slice arena address
@@ -137,6 +168,7 @@ static void slices_whole(const libxsmm_spmdm_handle* handle, char transa, const 
   SliceArgs a;
   a.a = d_a; a.transa = is_t(transa); a.lda = a.transa ? c->g.m : c->g.k; a.is_bf16 = is_bf16;
   a.origin_is_block = 0; a.slice0 = 0; a.simd_w = c->simd_w; a.g = c->g; a.out = c->arena;
+  slice_policy(c, &a, is_bf16, true);
   launch_slices(a, c->g.mb * c->g.kb, stream);
 }
 
@@ -151,7 +183,7 @@ static void compute_whole(const libxsmm_spmdm_handle* handle, char transb, char 
   a.ldb = a.transb ? c->g.k : c->g.n;
   a.ldc = a.transc ? c->g.m : c->g.n;
   a.beta = beta; a.g = c->g; a.mb_first = 0; a.mb_count = c->g.mb;
-  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0;
+  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16);
   launch_compute(a, stream);
 }
 
@@ -186,6 +218,7 @@ static void slice_block(const libxsmm_spmdm_handle* handle, char transa, const v
     }
     a.a = slab; a.origin_is_block = 1;
   }
+  slice_policy(c, &a, is_bf16, false);
   launch_slices(a, 1, st);
   XB_CUDA(cudaStreamSynchronize(st));
 }
@@ -208,7 +241,7 @@ static void compute_block(const libxsmm_spmdm_handle* handle, char transb, char 
   const bool dev_b = is_device_ptr(b_in), dev_c = is_device_ptr(c_in);
   ComputeArgs a;
   a.sl = c->arena; a.transb = tb; a.transc = tc; a.is_bf16 = is_bf16; a.beta = beta; a.g = g;
-  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0;   // legacy block: no tensor-core twin
+  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1;   // legacy block: no tensor-core twin
   char* slab = c->staging + (size_t)tid * c->staging_per_tid;
   const size_t slab_b_bytes = (((size_t)g.k * g.bn * 4) + 255) & ~(size_t)255;
   float* c_stage = (float*)(slab + slab_b_bytes);
@@ -301,6 +334,14 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena.tcoff = (uint16_t*)((char*)c->arena_base + row_bytes + col_bytes + val_bytes);
   c->arena.slice_nnz = (uint32_t*)((char*)c->arena_base + row_bytes + col_bytes + val_bytes + col_bytes);
   XB_CUDA(cudaMemset(c->arena.slice_nnz, 0, nnz_bytes));
+  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false;
+  if (cudaSuccess == cudaHostAlloc((void**)&c->h_nnz, sizeof(unsigned long long), cudaHostAllocMapped)) {
+    *c->h_nnz = ~0ull;
+    if (cudaSuccess != cudaHostGetDevicePointer((void**)&c->d_nnz, c->h_nnz, 0)) c->d_nnz = 0;
+  }
+  else { (void)cudaGetLastError(); c->h_nnz = 0; }
+  XB_CUDA(cudaMalloc((void**)&c->d_acc, 2 * sizeof(unsigned long long)));
+  if (c->d_acc) XB_CUDA(cudaMemset(c->d_acc, 0, 2 * sizeof(unsigned long long)));
   c->table = (libxsmm_CSR_sparseslice*)malloc(sizeof(libxsmm_CSR_sparseslice) * ns);
   for (size_t s = 0; s < ns; ++s) {
     c->table[s].rowidx = c->arena.rowidx + s * (g.bm + 1);
@@ -340,6 +381,8 @@ void libxsmm_spmdm_destroy(libxsmm_spmdm_handle* handle)
     if (c->d_c) cudaFree(c->d_c);
     cudaFree(c->arena_base);
     cudaFree(c->staging);
+    if (c->d_acc) cudaFree(c->d_acc);
+    if (c->h_nnz) cudaFreeHost(c->h_nnz);
     free(c->table);
     delete c;
   }
@@ -461,6 +504,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
     SliceArgs sa;
     sa.a = c->d_a; sa.transa = is_t(transa); sa.lda = sa.transa ? g.m : g.k; sa.is_bf16 = is_bf16;
     sa.origin_is_block = 0; sa.slice0 = 0; sa.simd_w = c->simd_w; sa.g = g; sa.out = c->arena;
+    slice_policy(c, &sa, is_bf16, true);
     launch_slices(sa, g.mb * g.kb, c->xs[1]);
   }
   for (int p = 0; p < npanels; ++p) {
@@ -481,7 +525,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
       ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
       ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
       ca.beta = beta_f; ca.g = g; ca.mb_first = 0; ca.mb_count = g.mb;
-      ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0;
+      ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16);
       launch_compute(ca, c->xs[1]);
     }
     XB_CUDA(cudaEventRecord(c->xev[p], c->xs[1]));

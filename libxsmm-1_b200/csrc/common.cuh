@@ -63,7 +63,29 @@ struct SliceArgs {
   int simd_w;           // vector width of the reference instantiation mirrored (NaN rule)
   Geom g;
   SliceArena out;
+  // density feedback for the host (see capi.cu: a lagging hint that only steers which kernels are enqueued):
+  // every slice adds its count to acc[0] and bumps acc[1]; the CTA that completes the set publishes the total
+  // to *host_total (mapped pinned memory) and resets the counters
+  unsigned long long* acc;
+  unsigned long long* host_total;
+  int total_slices;
+  int write_aux;        // 0: skip the auxiliary per-nonzero words (tensor-core kernels will not be enqueued)
 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void xb_publish_nnz(const SliceArgs& p, unsigned long long slice_total)
+{
+  if (0 == p.acc) return;
+  atomicAdd(p.acc, slice_total);
+  __threadfence();
+  const unsigned long long done = atomicAdd(p.acc + 1, 1ull);
+  if (done + 1 == (unsigned long long)p.total_slices) {
+    const unsigned long long total = atomicExch(p.acc, 0ull);
+    p.acc[1] = 0ull;
+    if (p.host_total) { *(volatile unsigned long long*)p.host_total = total; __threadfence_system(); }
+  }
+}
+#endif
 
 // mode boundaries of the reference's narrow last block (compute template :72-76,372-434)
 struct ColModes { int n_full_end; int tail_from; };
@@ -86,6 +108,7 @@ struct ComputeArgs {
   // selected kernel does the work (dense <=> total nnz >= tc_min_nnz).  tc_twin = 0: no twin, always run.
   int tc_twin;
   unsigned long long tc_min_nnz;
+  int tc_hint;      // host's lagging density hint: 0 unknown / borderline (enqueue both twins), 1 clearly sparse (CUDA cores only), 2 clearly dense (tensor cores only)
 };
 
 #if defined(__CUDACC__)
@@ -109,6 +132,7 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream);
 void launch_compute(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tma(const ComputeArgs& args, bool partial, cudaStream_t stream);
 bool launch_compute_tc(const ComputeArgs& args, cudaStream_t stream);
+bool launch_compute_tc16(const ComputeArgs& args, cudaStream_t stream);   // tcgen05 branch for bf16 inputs
 bool launch_compute_mma(const ComputeArgs& args, cudaStream_t stream);   // warp-MMA gather kernel for bf16 slices; false: does not qualify   // tcgen05 dense branch; false: does not qualify   // false: panel does not qualify
 
 // ---- FSSPMDM --------------------------------------------------------------------------------

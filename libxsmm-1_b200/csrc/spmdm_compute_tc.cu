@@ -17,7 +17,7 @@
 // where the relative-error contract (1e-5) is the bar.  It never touches operands the reference would skip
 // in a way that changes finite results: dropped (zero) entries of A are exact zeros in the dense tile.
 #include "common.cuh"
-#include "ptx.cuh"
+#include "tc_common.cuh"
 #include <cstdlib>
 
 namespace xb {
@@ -37,47 +37,6 @@ constexpr int TC_SMEM_A = 0;                                        // two halve
 constexpr int TC_SMEM_B = 2 * TC_A_HALF;                            // stage s: raw at +s*32K, lo at +s*32K+16K
 constexpr int TC_SMEM_BAR = TC_SMEM_B + TC_NB * 2 * TC_B_CHUNK;     // 224 KiB
 constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 256;
-
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
-{
-  // reference for the field layout: CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor)
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;        // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
-  return d;
-}
-
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-  asm volatile(
-    "{\n\t.reg .pred p;\n\t"
-    "setp.ne.b32 p, %4, 0;\n\t"
-    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t* bar)
-{
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
-{
-  asm volatile(
-    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-    : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeArgs p)

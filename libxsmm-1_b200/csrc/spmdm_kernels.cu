@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
         const uint32_t q = pos + __popc(bal & lt);
         co[q] = (uint16_t)k;
         va[q] = v;
-        ri[q] = p.is_bf16 ? (uint16_t)(r0 + r) : xb_tc_pack(r0 + r, k);
+        if (p.write_aux) ri[q] = p.is_bf16 ? (uint16_t)(r0 + r) : xb_tc_pack(r0 + r, k);
       }
       pos += __popc(bal);
     }
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
   if (strip == nstrips - 1 && 0 == tid) {
     ro[nrows] = (uint16_t)(base + strip_tot[strip]);
     p.out.slice_nnz[s] = base + strip_tot[strip];
+    xb_publish_nnz(p, base + strip_tot[strip]);
   }
 }
 
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
     if (0 == tid) {
       p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
       p.out.slice_nnz[s] = total;
+      xb_publish_nnz(p, total);
     }
   }
 
@@ -316,6 +318,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
   uint16_t* ri = p.out.tcoff + (size_t)s * g.bm * g.bk;
   const uint32_t lt = (1u << lane) - 1u;
   const int k = lane * 4;
+  const bool aux = (0 != p.write_aux);
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) {
     if (row_lo + j < row_hi) {     // warp-uniform
@@ -331,10 +334,10 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
         const int rr = row_lo + j;
         // auxiliary per-nonzero word: fp32 slices -> position in the tcgen05 branch's A tile; bf16 slices -> the
         // block-local row (the warp-MMA kernel gathers nonzeros of 16 rows into one instruction)
-        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k); ++q; }
-        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 1); ++q; }
-        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 2); ++q; }
-        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 3); }
+        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); if (aux) ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k); ++q; }
+        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); if (aux) ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 1); ++q; }
+        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); if (aux) ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 2); ++q; }
+        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); if (aux) ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 3); }
       }
       pos += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     }
@@ -685,7 +688,7 @@ static cudaStream_t side_stream()
 }
 
 // LIBXSMM_B200_SPMDM_TC: "0" never use the tensor-core branch, "1" always (when the panel qualifies),
-// unset / anything else: by density -- total nnz >= 7 % of M*K, decided on the device.
+// unset / anything else: by density -- total nnz >= 7 % (fp32) or 1.5 % (bf16) of M*K, decided on the device.
 static int tc_mode()
 {
   const char* e = getenv("LIBXSMM_B200_SPMDM_TC");
@@ -718,12 +721,17 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
   // Tensor-core twin (fp32, N/N/N, aligned panels): the dense kernel is enqueued next to the sparse ones and
   // every CTA of both reads the slices' nonzero counts; only the selected side does the work.
   ComputeArgs targs = args;
-  const int mode = (0 == args.tc_twin) ? tc_mode() : 0;
+  int mode = (0 == args.tc_twin) ? tc_mode() : 0;
+  if (2 == mode && 1 == args.tc_hint) mode = 0;      // clearly sparse last time: do not even enqueue the dense twin
   targs.tc_twin = 0;
+  if (2 == mode && 2 == args.tc_hint) {              // clearly dense last time: the tensor-core kernel alone (correct for any density)
+    if (args.is_bf16 ? launch_compute_tc16(targs, stream) : launch_compute_tc(targs, stream)) return;
+  }
   if (mode > 0) {
     targs.tc_twin = 1;
-    targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)(0.07 * (double)args.g.m * (double)args.g.k);
-    if (!launch_compute_tc(targs, stream)) targs.tc_twin = 0;
+    // crossover measured on B200: fp32 (3xTF32, three MMAs per k-step) 7 %; bf16 (one MMA) ~1 %, switched at 1.5 %
+    targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)((args.is_bf16 ? 0.015 : 0.07) * (double)args.g.m * (double)args.g.k);
+    if (!(args.is_bf16 ? launch_compute_tc16(targs, stream) : launch_compute_tc(targs, stream))) targs.tc_twin = 0;
     else if (1 == mode) return;   // forced: nothing for the sparse kernels to do
   }
   const ComputeArgs& args2 = targs;

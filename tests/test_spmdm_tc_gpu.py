@@ -120,3 +120,33 @@ def test_bf16_warp_mma_gather_kernel(gpu, oracle, monkeypatch, M, N, K, density,
     valid_slices_equal(og, sl, osl)
     assert rel(C, OC) <= 1e-5
     gpu.check()
+
+
+@pytest.mark.parametrize("mode", ["1", "auto"])
+@pytest.mark.parametrize("M,N,K,density,beta,ta,tb,tc", [
+    (512, 512, 512, 0.10, 0, "N", "N", "N"), (512, 512, 512, 0.10, 1, "N", "N", "N"), (300, 208, 256, 0.30, 0, "N", "N", "N"),
+    (4096, 320, 256, 0.05, 0, "N", "N", "N"), (256, 200, 384, 0.20, 0, "T", "N", "T"), (256, 200, 384, 0.20, 0, "N", "T", "N"),
+    (512, 256, 128, 1.00, 0, "N", "N", "N")])
+def test_bf16_tensor_core_branch(gpu, oracle, monkeypatch, mode, M, N, K, density, beta, ta, tb, tc):
+    """bf16 inputs on tcgen05 (kind::f16, exact products, fp32 accumulation in TMEM).  Contract 1e-2 relative;
+    observed 1e-6."""
+    if mode == "auto":
+        monkeypatch.delenv("LIBXSMM_B200_SPMDM_TC", raising=False)
+    else:
+        monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", mode)
+    if density >= 1.0:
+        rng = np.random.default_rng(5)
+        A = gpu.workloads.to_bf16_bits((rng.random((M, K)) + 0.5).astype(np.float32))
+        B = gpu.workloads.to_bf16_bits(rng.random((K, N)).astype(np.float32))
+        C0 = rng.random((M, N)).astype(np.float32)
+    else:
+        A, B, C0 = gpu.workloads.spmdm_inputs(M, N, K, density, dtype="bf16", seed=M + N, transa=ta, transb=tb, transc=tc)
+    g, sl, C = gpu_spmdm(gpu, A, B, C0, M, N, K, ta, tb, tc, beta, True)
+    og, osl, OC = oracle_spmdm(oracle, g, A, B, C0, ta, tb, tc, float(beta))
+    valid_slices_equal(og, sl, osl)
+    assert rel(C, OC) <= 1e-5
+    monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", "0")
+    _, _, C_cc = gpu_spmdm(gpu, A, B, C0, M, N, K, ta, tb, tc, beta, True)
+    np.testing.assert_array_equal(C_cc.view(np.uint32), OC.view(np.uint32))      # the CUDA-core path stays bit exact
+    assert not np.array_equal(C.view(np.uint32), C_cc.view(np.uint32))           # ... and the tensor-core twin really ran
+    gpu.check()
