@@ -438,17 +438,18 @@ def main():
         return float(t.item())
 
     def run(wl_, want_e2e, sample_clocks):
+        # the clock sampler (nvidia-smi every 200 ms) runs from before the warm-up until after the end-to-end
+        # phase: the device-timed region alone lasts only milliseconds
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
         gen = run_spmdm_gpu(xs, wl_, args.steps, args.warmup, want_e2e) if wl_["kind"] == "spmdm" else \
             run_fs_gpu(xs, wl_, args.steps, args.warmup, 1, want_e2e)
         assert next(gen) == "ready"
         barrier()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        if sampler:
-            sampler.start()
-            time.sleep(0.25)
         res = next(gen)
         barrier()
-        clocks = sampler.finish() if sampler else None
         res["total_ms"] = max_over_ranks(res["total_ms"])
         res["flops_all"] = sum_over_ranks(res["flops"])
         res["launches_all"] = int(sum_over_ranks(res["launches"]))
@@ -463,6 +464,7 @@ def main():
             e2e = e
         for _ in gen:
             pass
+        clocks = sampler.finish() if sampler else None
         return res, e2e, clocks
 
     res, e2e, clocks = run(wl, not args.no_e2e, rank == 0)
