@@ -344,6 +344,121 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// K1 wide variant for bf16, transa = 'N', complete 128-column blocks: a lane holds EIGHT consecutive elements
+// (one 16-byte load), so a row is half a warp and a warp works on two rows at a time; the keep test runs on
+// the packed bf16 pairs with carry arithmetic (no widening, no per-element compare).  Same two phases, same
+// outputs, about a third of the instructions of the generic kernel (which is instruction-issue bound).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t k1w_mask8(uint4 w)
+{
+  // per 16-bit half h (sign dropped): kept iff 1 <= h <= 0x7F80, i.e. nonzero and not NaN (ordered compare of the
+  // reference's vector loops: src/libxsmm_spmdm_begin_avx2.h:54); denormals and Inf kept, -0.0 dropped
+  uint32_t m = 0;
+  const uint32_t v[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t t = v[i] & 0x7FFF7FFFu;
+    const uint32_t nz = t + 0x7FFF7FFFu;          // bit 15 / 31 set iff the half is nonzero
+    const uint32_t nan = t + 0x007F007Fu;         // bit 15 / 31 set iff the half is > 0x7F80
+    const uint32_t k = nz & ~nan & 0x80008000u;
+    m |= ((k >> 15) & 1u) << (2 * i);
+    m |= (k >> 31) << (2 * i + 1);
+  }
+  return m;
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const SliceArgs p)
+{
+  __shared__ uint32_t wtot[K1N_WARPS];
+  const Geom& g = p.g;
+  const int s = p.slice0 + (int)blockIdx.x;
+  const int kb = s / g.mb, mbi = s - kb * g.mb;
+  const int nrows = min(g.bm, g.m - mbi * g.bm);
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = lane >> 4, hl = lane & 15;
+  const int rpw = (g.bm + K1N_WARPS - 1) / K1N_WARPS;
+  const int row_lo = warp * rpw, row_hi = min(nrows, row_lo + rpw);
+  const long long origin = p.origin_is_block ? 0ll : ((long long)mbi * g.bm * p.lda + (long long)kb * g.bk);
+  const uint16_t* A = (const uint16_t*)p.a + origin + hl * 8;
+
+  // ---- phase 1: load, test, count ---------------------------------------------------------------------
+  uint4 w[ROWS / 2];
+  uint32_t masks[(ROWS / 2 + 3) / 4];      // 8 bits per iteration
+#pragma unroll
+  for (int j = 0; j < (ROWS / 2 + 3) / 4; ++j) masks[j] = 0;
+#pragma unroll
+  for (int it = 0; it < ROWS / 2; ++it) {
+    const int r = row_lo + 2 * it + half;
+    w[it] = (r < row_hi) ? __ldg((const uint4*)(A + (long long)r * p.lda)) : make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int it = 0; it < ROWS / 2; ++it) masks[it / 4] |= k1w_mask8(w[it]) << (8 * (it % 4));
+  uint32_t mine = 0;
+#pragma unroll
+  for (int j = 0; j < (ROWS / 2 + 3) / 4; ++j) mine += __popc(masks[j]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  if (0 == lane) wtot[warp] = mine;
+  __syncthreads();
+  uint32_t pos;
+  {
+    const uint32_t t = wtot[lane];
+    uint32_t inc = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += u;
+    }
+    pos = __shfl_sync(0xffffffffu, inc - t, warp);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (0 == tid) {
+      p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
+      p.out.slice_nnz[s] = total;
+      xb_publish_nnz(p, total);
+    }
+  }
+
+  // ---- phase 2: positions and stores -----------------------------------------------------------------------
+  uint16_t* ro = p.out.rowidx + (size_t)s * (g.bm + 1);
+  uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
+  float* va = p.out.values + (size_t)s * g.bm * g.bk;
+  uint16_t* ri = p.out.tcoff + (size_t)s * g.bm * g.bk;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t mymask = half ? 0xFFFF0000u : 0x0000FFFFu;
+  const bool aux = (0 != p.write_aux);
+#pragma unroll
+  for (int it = 0; it < ROWS / 2; ++it) {
+    if (row_lo + 2 * it < row_hi) {      // warp-uniform
+      const uint32_t m = (masks[it / 4] >> (8 * (it % 4))) & 255u;
+      const uint32_t nm = __popc(m);      // 0..8
+      const uint32_t b0 = __ballot_sync(0xffffffffu, nm & 1u), b1 = __ballot_sync(0xffffffffu, nm & 2u);
+      const uint32_t b2 = __ballot_sync(0xffffffffu, nm & 4u), b3 = __ballot_sync(0xffffffffu, nm & 8u);
+      const uint32_t lo_tot = __popc(b0 & 0xFFFFu) + 2 * __popc(b1 & 0xFFFFu) + 4 * __popc(b2 & 0xFFFFu) + 8 * __popc(b3 & 0xFFFFu);
+      const uint32_t hi_tot = __popc(b0 >> 16) + 2 * __popc(b1 >> 16) + 4 * __popc(b2 >> 16) + 8 * __popc(b3 >> 16);
+      const uint32_t rowpos = pos + (half ? lo_tot : 0u);
+      const int r = row_lo + 2 * it + half;
+      if (0 == hl && r < row_hi) ro[r] = (uint16_t)rowpos;
+      if (m) {   // few lanes hold nonzeros in the sparse regime
+        const uint32_t pm = lt & mymask;
+        uint32_t q = rowpos + __popc(b0 & pm) + 2 * __popc(b1 & pm) + 4 * __popc(b2 & pm) + 8 * __popc(b3 & pm);
+        const uint32_t v[4] = { w[it].x, w[it].y, w[it].z, w[it].w };
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (m & (1u << e)) {
+            co[q] = (uint16_t)(hl * 8 + e);
+            va[q] = __uint_as_float((e & 1) ? (v[e >> 1] & 0xFFFF0000u) : (v[e >> 1] << 16));
+            if (aux) ri[q] = (uint16_t)r;
+            ++q;
+          }
+        }
+      }
+      pos += lo_tot + hi_tot;
+    }
+  }
+}
+
 template <bool BF16, int ROWS, bool KEEP>
 static void launch_slice_n(const SliceArgs& args, int nslices, bool full, cudaStream_t stream)
 {
@@ -360,6 +475,17 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
     // makes the NaN rule of the scalar remainder unreachable)
     const bool full = (0 == (args.g.k % 128)) && (args.simd_w > 1);
     const int rpw = (args.g.bm + K1N_WARPS - 1) / K1N_WARPS;
+    if (args.is_bf16 && full && !args.origin_is_block && 0 == (args.lda & 7) && 0 == ((uintptr_t)args.a & 15) && 0 == (args.g.k & 7)) {
+      // complete 128-column blocks, 16-byte aligned rows: the wide kernel (a lane holds 8 elements)
+      static int wide = -1;
+      if (wide < 0) { const char* e = getenv("LIBXSMM_B200_K1_WIDE"); wide = (e && '0' == *e) ? 0 : 1; }
+      if (wide) {
+        if (rpw <= 8) spmdm_slice_bf16w_kernel<8><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+        else spmdm_slice_bf16w_kernel<16><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+        XB_CUDA(cudaGetLastError());
+        return;
+      }
+    }
     if (args.is_bf16) {
       static int keep16 = -1;
       if (keep16 < 0) { const char* e = getenv("LIBXSMM_B200_K1_KEEP"); keep16 = (e && '1' == *e) ? 1 : 0; }
