@@ -63,6 +63,7 @@ struct SpmdmCtx {
   size_t d_a_bytes, d_b_bytes, d_c_bytes;
   cudaStream_t xs[3];
   cudaEvent_t xev[kExecPanels + 1];
+  std::vector<cudaEvent_t> xup, xdone;   // per diagonal step of exec_host: uploads landed / tiles computed
   // density feedback: the slicing kernels publish the total nonzero count of the last completed pass into
   // mapped pinned memory; the host uses it (one call late, never for correctness) to avoid enqueueing the
   // kernel twin that will not be selected and the auxiliary arrays only that twin reads
@@ -167,7 +168,7 @@ static void slices_whole(const libxsmm_spmdm_handle* handle, char transa, const 
   if (0 == c) return;
   SliceArgs a;
   a.a = d_a; a.transa = is_t(transa); a.lda = a.transa ? c->g.m : c->g.k; a.is_bf16 = is_bf16;
-  a.origin_is_block = 0; a.slice0 = 0; a.simd_w = c->simd_w; a.g = c->g; a.out = c->arena;
+  a.origin_is_block = 0; a.slice0 = 0; a.slice_step = 1; a.simd_w = c->simd_w; a.g = c->g; a.out = c->arena;
   slice_policy(c, &a, is_bf16, true);
   launch_slices(a, c->g.mb * c->g.kb, stream);
 }
@@ -200,7 +201,7 @@ static void slice_block(const libxsmm_spmdm_handle* handle, char transa, const v
   const int nrows = (g.bm < g.m - mbi * g.bm) ? g.bm : (g.m - mbi * g.bm);
   const int ncols = (g.bk < g.k - kb * g.bk) ? g.bk : (g.k - kb * g.bk);
   SliceArgs a;
-  a.transa = is_t(transa); a.is_bf16 = is_bf16; a.slice0 = block_id; a.simd_w = c->simd_w; a.g = g; a.out = c->arena;
+  a.transa = is_t(transa); a.is_bf16 = is_bf16; a.slice0 = block_id; a.slice_step = 1; a.simd_w = c->simd_w; a.g = g; a.out = c->arena;
   if (is_device_ptr(a_in)) {
     a.a = a_in; a.lda = a.transa ? g.m : g.k; a.origin_is_block = 0;
   }
@@ -376,6 +377,7 @@ void libxsmm_spmdm_destroy(libxsmm_spmdm_handle* handle)
     for (size_t i = 0; i < c->streams.size(); ++i) if (c->streams[i]) { cudaStreamSynchronize(c->streams[i]); cudaStreamDestroy(c->streams[i]); }
     for (int i = 0; i < 3; ++i) if (c->xs[i]) { cudaStreamSynchronize(c->xs[i]); cudaStreamDestroy(c->xs[i]); }
     for (int i = 0; i <= kExecPanels; ++i) if (c->xev[i]) cudaEventDestroy(c->xev[i]);
+    for (size_t i = 0; i < c->xup.size(); ++i) { if (c->xup[i]) cudaEventDestroy(c->xup[i]); if (c->xdone[i]) cudaEventDestroy(c->xdone[i]); }
     if (c->d_a) cudaFree(c->d_a);
     if (c->d_b) cudaFree(c->d_b);
     if (c->d_c) cudaFree(c->d_c);
@@ -485,53 +487,99 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
     for (int i = 0; i < kExecPanels + 1; ++i) XB_CUDA(cudaEventCreateWithFlags(&c->xev[i], cudaEventDisableTiming));
   }
   if (0 == c->d_a || 0 == c->d_b || 0 == c->d_c) return;
-  // Three streams: xs[0] uploads (A first, then the B -- and C -- panels in column order), xs[1] runs the
-  // kernels (slicing, then one compute launch per column panel as soon as that panel has landed),
-  // xs[2] downloads finished C panels.  PCIe is full duplex, so uploads of later panels, the kernels
-  // and the downloads of earlier panels all overlap.  Column panels are contiguous row ranges of B / C
-  // when those are stored transposed, and strided 2-D copies otherwise.
+  // Three streams: xs[0] uploads, xs[1] kernels, xs[2] downloads (PCIe is full duplex).  The problem is cut
+  // into mb row blocks x np column panels.  Diagonal step d uploads A's row block d and B's panel d; that makes
+  // the tiles (d, c <= d) and (r < d, d) computable, so the number of finished C tiles grows quadratically
+  // while the uploads proceed linearly and the download of C (the largest transfer) starts after 1/mb + 1/np
+  // of the inputs instead of after all of A.  Column panels are contiguous row ranges of B / C when those are
+  // stored transposed, strided 2-D copies otherwise.
   const ColModes modes = spmdm_modes(g, c->simd_w);
-  int npanels = kExecPanels;
-  // panel boundaries are multiples of 256 columns so that every launch keeps whole CTA tiles and
-  // the reference's column modes (defined on global column numbers) are unaffected by the split
-  int pw = (((g.n + npanels - 1) / npanels) + 255) / 256 * 256;
+  const bool ta = is_t(transa);
+  int np = kExecPanels;
+  { const char* e = getenv("LIBXSMM_B200_EXEC_PANELS"); if (e && *e) { const int v = atoi(e); if (v >= 1 && v <= 64) np = v; } }
+  // panel boundaries are multiples of 256 columns so that every launch keeps whole CTA tiles and the
+  // reference's column modes (defined on global column numbers) are unaffected by the split
+  int pw = (((g.n + np - 1) / np) + 255) / 256 * 256;
   if (pw <= 0) pw = 256;
-  npanels = (g.n + pw - 1) / pw;
-  XB_CUDA(cudaMemcpyAsync(c->d_a, a, a_bytes, cudaMemcpyHostToDevice, c->xs[0]));
-  XB_CUDA(cudaEventRecord(c->xev[kExecPanels], c->xs[0]));
-  XB_CUDA(cudaStreamWaitEvent(c->xs[1], c->xev[kExecPanels], 0));
-  {
-    SliceArgs sa;
-    sa.a = c->d_a; sa.transa = is_t(transa); sa.lda = sa.transa ? g.m : g.k; sa.is_bf16 = is_bf16;
-    sa.origin_is_block = 0; sa.slice0 = 0; sa.simd_w = c->simd_w; sa.g = g; sa.out = c->arena;
-    slice_policy(c, &sa, is_bf16, true);
-    launch_slices(sa, g.mb * g.kb, c->xs[1]);
+  np = (g.n + pw - 1) / pw;
+  const int nd = (g.mb > np) ? g.mb : np;
+  if ((int)c->xdone.size() < nd) {
+    const size_t old = c->xdone.size();
+    c->xdone.resize((size_t)nd, (cudaEvent_t)0); c->xup.resize((size_t)nd, (cudaEvent_t)0);
+    for (size_t i = old; i < (size_t)nd; ++i) {
+      XB_CUDA(cudaEventCreateWithFlags(&c->xdone[i], cudaEventDisableTiming));
+      XB_CUDA(cudaEventCreateWithFlags(&c->xup[i], cudaEventDisableTiming));
+    }
   }
-  for (int p = 0; p < npanels; ++p) {
-    const int n0 = p * pw, w = (g.n - n0 < pw) ? (g.n - n0) : pw;
-    char* db = (char*)c->d_b; const char* hb = (const char*)b;
-    if (tb) XB_CUDA(cudaMemcpyAsync(db + (size_t)n0 * g.k * esz, hb + (size_t)n0 * g.k * esz, (size_t)w * g.k * esz, cudaMemcpyHostToDevice, c->xs[0]));
-    else XB_CUDA(cudaMemcpy2DAsync(db + (size_t)n0 * esz, (size_t)g.n * esz, hb + (size_t)n0 * esz, (size_t)g.n * esz, (size_t)w * esz, g.k, cudaMemcpyHostToDevice, c->xs[0]));
-    if (0.f != beta_f) {
-      if (tc) XB_CUDA(cudaMemcpyAsync(c->d_c + (size_t)n0 * g.m, c_host + (size_t)n0 * g.m, (size_t)w * g.m * 4, cudaMemcpyHostToDevice, c->xs[0]));
-      else XB_CUDA(cudaMemcpy2DAsync(c->d_c + n0, (size_t)g.n * 4, c_host + n0, (size_t)g.n * 4, (size_t)w * 4, g.m, cudaMemcpyHostToDevice, c->xs[0]));
+  int write_aux = 1; bool first_block = true;
+  // a rectangle of C: row blocks [r0, r0 + rc) x columns [n0, n0 + w)
+  auto rect = [&](int r0, int rc, int n0, int w, int* m0, int* rows) {
+    *m0 = r0 * g.bm;
+    const int mend = ((r0 + rc) * g.bm < g.m) ? (r0 + rc) * g.bm : g.m;
+    *rows = mend - *m0;
+    (void)n0; (void)w;
+  };
+  auto copy_rect = [&](int r0, int rc, int n0, int w, bool up) {
+    int m0, rows; rect(r0, rc, n0, w, &m0, &rows);
+    if (rows <= 0 || w <= 0) return;
+    float* dptr = tc ? (c->d_c + (size_t)n0 * g.m + m0) : (c->d_c + (size_t)m0 * g.n + n0);
+    float* hptr = tc ? (c_host + (size_t)n0 * g.m + m0) : (c_host + (size_t)m0 * g.n + n0);
+    const size_t pitch = (size_t)(tc ? g.m : g.n) * 4, width = (size_t)(tc ? rows : w) * 4, height = (size_t)(tc ? w : rows);
+    if (up) XB_CUDA(cudaMemcpy2DAsync(dptr, pitch, hptr, pitch, width, height, cudaMemcpyHostToDevice, c->xs[0]));
+    else XB_CUDA(cudaMemcpy2DAsync(hptr, pitch, dptr, pitch, width, height, cudaMemcpyDeviceToHost, c->xs[2]));
+  };
+  auto compute_rect = [&](int r0, int rc, int n0, int w) {
+    if (rc <= 0 || w <= 0) return;
+    ComputeArgs ca;
+    ca.sl = c->arena; ca.transb = tb; ca.transc = tc; ca.is_bf16 = is_bf16;
+    ca.ldb = tb ? g.k : g.n; ca.ldc = tc ? g.m : g.n;
+    ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
+    ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
+    ca.beta = beta_f; ca.g = g; ca.mb_first = r0; ca.mb_count = rc;
+    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16);
+    launch_compute(ca, c->xs[1]);
+  };
+  for (int d = 0; d < nd; ++d) {
+    // rectangles that become computable in step d: the new row block against all panels uploaded so far
+    // (including panel d), and the new panel against all earlier row blocks
+    const int row_cols = ((d < np) ? (d + 1) * pw : g.n) < g.n ? ((d < np) ? (d + 1) * pw : g.n) : g.n;   // columns [0, row_cols) of row block d
+    const int col_n0 = d * pw, col_w = (d < np) ? ((g.n - col_n0 < pw) ? (g.n - col_n0) : pw) : 0;      // panel d
+    const int col_rows = (d < g.mb) ? d : g.mb;                                                          // row blocks [0, col_rows) of panel d
+    // ---- uploads of step d ----
+    if (d < g.mb) {
+      const int m0 = d * g.bm, rows = (g.bm < g.m - m0) ? g.bm : (g.m - m0);
+      if (!ta) XB_CUDA(cudaMemcpyAsync((char*)c->d_a + (size_t)m0 * g.k * esz, (const char*)a + (size_t)m0 * g.k * esz, (size_t)rows * g.k * esz, cudaMemcpyHostToDevice, c->xs[0]));
+      else XB_CUDA(cudaMemcpy2DAsync((char*)c->d_a + (size_t)m0 * esz, (size_t)g.m * esz, (const char*)a + (size_t)m0 * esz, (size_t)g.m * esz, (size_t)rows * esz, g.k, cudaMemcpyHostToDevice, c->xs[0]));
     }
-    XB_CUDA(cudaEventRecord(c->xev[p], c->xs[0]));
-    XB_CUDA(cudaStreamWaitEvent(c->xs[1], c->xev[p], 0));
-    {
-      ComputeArgs ca;
-      ca.sl = c->arena; ca.transb = tb; ca.transc = tc; ca.is_bf16 = is_bf16;
-      ca.ldb = tb ? g.k : g.n; ca.ldc = tc ? g.m : g.n;
-      ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
-      ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
-      ca.beta = beta_f; ca.g = g; ca.mb_first = 0; ca.mb_count = g.mb;
-      ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16);
-      launch_compute(ca, c->xs[1]);
+    if (d < np) {
+      char* db = (char*)c->d_b; const char* hb = (const char*)b;
+      if (tb) XB_CUDA(cudaMemcpyAsync(db + (size_t)col_n0 * g.k * esz, hb + (size_t)col_n0 * g.k * esz, (size_t)col_w * g.k * esz, cudaMemcpyHostToDevice, c->xs[0]));
+      else XB_CUDA(cudaMemcpy2DAsync(db + (size_t)col_n0 * esz, (size_t)g.n * esz, hb + (size_t)col_n0 * esz, (size_t)g.n * esz, (size_t)col_w * esz, g.k, cudaMemcpyHostToDevice, c->xs[0]));
     }
-    XB_CUDA(cudaEventRecord(c->xev[p], c->xs[1]));
-    XB_CUDA(cudaStreamWaitEvent(c->xs[2], c->xev[p], 0));
-    if (tc) XB_CUDA(cudaMemcpyAsync(c_host + (size_t)n0 * g.m, c->d_c + (size_t)n0 * g.m, (size_t)w * g.m * 4, cudaMemcpyDeviceToHost, c->xs[2]));
-    else XB_CUDA(cudaMemcpy2DAsync(c_host + n0, (size_t)g.n * 4, c->d_c + n0, (size_t)g.n * 4, (size_t)w * 4, g.m, cudaMemcpyDeviceToHost, c->xs[2]));
+    if (0.f != beta_f) {   // beta != 0: the C rectangles go up before they are needed
+      if (d < g.mb) copy_rect(d, 1, 0, row_cols, true);
+      if (d < np) copy_rect(0, col_rows, col_n0, col_w, true);
+    }
+    XB_CUDA(cudaEventRecord(c->xup[d], c->xs[0]));
+    // ---- kernels of step d: at most one slicing launch and two compute launches ----
+    XB_CUDA(cudaStreamWaitEvent(c->xs[1], c->xup[d], 0));
+    if (d < g.mb) {
+      SliceArgs sa;
+      sa.a = c->d_a; sa.transa = ta; sa.lda = ta ? g.m : g.k; sa.is_bf16 = is_bf16;
+      sa.origin_is_block = 0; sa.slice0 = d; sa.slice_step = g.mb; sa.simd_w = c->simd_w; sa.g = g; sa.out = c->arena;
+      slice_policy(c, &sa, is_bf16, true);
+      if (first_block) { write_aux = sa.write_aux; first_block = false; }
+      sa.write_aux = write_aux;                 // one decision for all row blocks of this multiply
+      c->aux_written = (0 != write_aux);
+      launch_slices(sa, g.kb, c->xs[1]);
+      compute_rect(d, 1, 0, row_cols);
+    }
+    if (d < np) compute_rect(0, col_rows, col_n0, col_w);
+    XB_CUDA(cudaEventRecord(c->xdone[d], c->xs[1]));
+    // ---- downloads of step d ----
+    XB_CUDA(cudaStreamWaitEvent(c->xs[2], c->xdone[d], 0));
+    if (d < g.mb) copy_rect(d, 1, 0, row_cols, false);
+    if (d < np) copy_rect(0, col_rows, col_n0, col_w, false);
   }
   XB_CUDA(cudaStreamSynchronize(c->xs[2]));
   XB_CUDA(cudaStreamSynchronize(c->xs[0]));

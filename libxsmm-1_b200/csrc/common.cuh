@@ -59,7 +59,8 @@ struct SliceArgs {
   int transa;           // 0: A is m x k row-major, 1: A is stored k x m
   int is_bf16;
   int origin_is_block;  // 1: `a` already points at the block's first element (legacy staged block)
-  int slice0;           // slice handled by blockIdx.y == 0
+  int slice0;           // slice handled by the first CTA (cluster) of the launch
+  int slice_step;       // slice of CTA i = slice0 + i*slice_step (1: consecutive slices; mb: all k-blocks of one row block)
   int simd_w;           // vector width of the reference instantiation mirrored (NaN rule)
   Geom g;
   SliceArena out;

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
   __shared__ uint32_t strip_tot[8];
 
   const Geom& g = p.g;
-  const int s = p.slice0 + (int)blockIdx.y;
+  const int s = p.slice0 + (int)blockIdx.y * p.slice_step;
   const int kb = s / g.mb, mbi = s - kb * g.mb;
   const int nrows = min(g.bm, g.m - mbi * g.bm);
   const int ncols = min(g.bk, g.k - kb * g.bk);
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
   typedef typename Raw::raw_t raw_t;
   __shared__ uint32_t wtot[K1N_WARPS];
   const Geom& g = p.g;
-  const int s = p.slice0 + (int)blockIdx.x;
+  const int s = p.slice0 + (int)blockIdx.x * p.slice_step;
   const int kb = s / g.mb, mbi = s - kb * g.mb;
   const int nrows = min(g.bm, g.m - mbi * g.bm);
   const int ncols = min(g.bk, g.k - kb * g.bk);
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
 {
   __shared__ uint32_t wtot[K1N_WARPS];
   const Geom& g = p.g;
-  const int s = p.slice0 + (int)blockIdx.x;
+  const int s = p.slice0 + (int)blockIdx.x * p.slice_step;
   const int kb = s / g.mb, mbi = s - kb * g.mb;
   const int nrows = min(g.bm, g.m - mbi * g.bm);
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;

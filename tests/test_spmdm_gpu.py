@@ -202,23 +202,26 @@ def test_legacy_block_entries_bf16_transposed(gpu, oracle):
         xs.libxsmm_spmdm_destroy(h)
 
 
+@pytest.mark.parametrize("shape", [(384, 1000, 512), (2048, 1100, 256)])
 @pytest.mark.parametrize("dtype,ta,tb,tc,beta", [("f32", "N", "N", "N", 0.0), ("f32", "T", "N", "T", 1.0),
-                                                  ("f32", "N", "T", "N", 0.5), ("bf16", "N", "N", "N", 0)])
-def test_exec_host(gpu, oracle, dtype, ta, tb, tc, beta):
-    """the whole-multiply host entry (upload, slice, compute, download, pipelined by column panels)."""
+                                                  ("f32", "N", "T", "N", 0.5), ("bf16", "N", "N", "N", 0), ("bf16", "T", "T", "T", 1)])
+def test_exec_host(gpu, oracle, shape, dtype, ta, tb, tc, beta):
+    """the whole-multiply host entry: uploads, slicing, compute and downloads pipelined over row blocks x column
+    panels on three streams (the second shape has 8 row blocks and 5 panels, the last one ragged)."""
     xs = gpu
-    M, N, K = 384, 1000, 512
+    M, N, K = shape
     A, B, C0 = xs.workloads.spmdm_inputs(M, N, K, 0.1, dtype=dtype, seed=5, transa=ta, transb=tb, transc=tc)
     h, s = xs.libxsmm_spmdm_init(M, N, K, 1)
     try:
-        C = C0.copy()
         dt = xs.LIBXSMM_SPMDM_DATATYPE_BFLOAT16 if dtype == "bf16" else xs.LIBXSMM_SPMDM_DATATYPE_F32
-        xs.libxsmm_spmdm_exec_host(h, s, dt, ta, tb, tc, A, B, beta, C)
-        xs.check()
         import pyoracle
         g = pyoracle.Geometry(dict(m=h.m, n=h.n, k=h.k, bm=h.bm, bn=h.bn, bk=h.bk, mb=h.mb, nb=h.nb, kb=h.kb))
         og, osl, OC = oracle_spmdm(oracle, g, A, B, C0, ta, tb, tc, float(beta))
-        np.testing.assert_array_equal(C.view(np.uint32), OC.view(np.uint32))
+        for rep in range(2):      # second call: the density hint of the first one is in effect
+            C = C0.copy()
+            xs.libxsmm_spmdm_exec_host(h, s, dt, ta, tb, tc, A, B, beta, C)
+            xs.check()
+            np.testing.assert_array_equal(C.view(np.uint32), OC.view(np.uint32))
     finally:
         xs.libxsmm_spmdm_destroy(h)
 
