@@ -52,6 +52,9 @@ LIBXSMM_API int libxsmm_sfsspmdm_is_sparse(const libxsmm_sfsspmdm* handle);
 /* 1 if the operator was baked into a specialised kernel at create time, 0 = generic kernel. */
 LIBXSMM_API int libxsmm_dfsspmdm_is_baked(const libxsmm_dfsspmdm* handle);
 LIBXSMM_API int libxsmm_sfsspmdm_is_baked(const libxsmm_sfsspmdm* handle);
+/* 1 if execute() of this float operator runs on the tensor cores (dense operators; the reference's dense
+ * SMM branch, src/libxsmm_fsspmdm.c:240-248). */
+LIBXSMM_API int libxsmm_sfsspmdm_is_tensor_core(const libxsmm_sfsspmdm* handle);
 
 /* Sticky error state (the reference entry points return void and are mute unless LIBXSMM_VERBOSE). */
 LIBXSMM_API int libxsmm_b200_last_error(void);

@@ -35,7 +35,7 @@ ADDED_SYMBOLS = [
     "libxsmm_spmdm_exec_host", "libxsmm_spmdm_exec_stream",
     "libxsmm_dfsspmdm_execute_stream", "libxsmm_sfsspmdm_execute_stream",
     "libxsmm_dfsspmdm_is_sparse", "libxsmm_sfsspmdm_is_sparse",
-    "libxsmm_dfsspmdm_is_baked", "libxsmm_sfsspmdm_is_baked",
+    "libxsmm_dfsspmdm_is_baked", "libxsmm_sfsspmdm_is_baked", "libxsmm_sfsspmdm_is_tensor_core",
     "libxsmm_b200_last_error", "libxsmm_b200_last_error_string", "libxsmm_b200_clear_error",
     "libxsmm_b200_launch_count",
     "libxsmm_b200_host_alloc", "libxsmm_b200_host_free",
@@ -122,6 +122,7 @@ def load():
         f.restype = None
         getattr(L, "libxsmm_%sfsspmdm_is_sparse" % p).argtypes = [vp]
         getattr(L, "libxsmm_%sfsspmdm_is_baked" % p).argtypes = [vp]
+    L.libxsmm_sfsspmdm_is_tensor_core.argtypes = [vp]
     L.libxsmm_b200_last_error_string.restype = ctypes.c_char_p
     L.libxsmm_b200_launch_count.restype = ctypes.c_ulonglong
     L.libxsmm_b200_host_alloc.argtypes = [ctypes.c_size_t]
@@ -531,6 +532,10 @@ class Fsspmdm:
     def is_baked(self):
         L = load()
         return bool((L.libxsmm_dfsspmdm_is_baked if self.double else L.libxsmm_sfsspmdm_is_baked)(self.handle))
+
+    @property
+    def is_tensor_core(self):
+        return (not self.double) and bool(load().libxsmm_sfsspmdm_is_tensor_core(self.handle))
 
     def execute(self, B, C):
         (libxsmm_dfsspmdm_execute if self.double else libxsmm_sfsspmdm_execute)(self.handle, B, C)

@@ -672,6 +672,7 @@ int libxsmm_dfsspmdm_is_sparse(const libxsmm_dfsspmdm* handle) { return fs_is_sp
 int libxsmm_sfsspmdm_is_sparse(const libxsmm_sfsspmdm* handle) { return fs_is_sparse_branch((const FsOperator*)handle); }
 int libxsmm_dfsspmdm_is_baked(const libxsmm_dfsspmdm* handle) { return fs_is_baked((const FsOperator*)handle); }
 int libxsmm_sfsspmdm_is_baked(const libxsmm_sfsspmdm* handle) { return fs_is_baked((const FsOperator*)handle); }
+int libxsmm_sfsspmdm_is_tensor_core(const libxsmm_sfsspmdm* handle) { return fs_is_tensor_core((const FsOperator*)handle); }
 
 // =====================================================================================================
 // service

@@ -145,6 +145,7 @@ FsOperator* fs_create(int is_double, int M, int N, int K, int lda, int ldb, int 
 void fs_execute(const FsOperator* op, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream);
 int fs_is_sparse_branch(const FsOperator* o);
 int fs_is_baked(const FsOperator* o);
+int fs_is_tensor_core(const FsOperator* o);
 int fs_needs_c_input(const FsOperator* o);
 int fs_is_double(const FsOperator* o);
 void fs_shape(const FsOperator* o, int* M, int* N, int* K, int* ldb, int* ldc, int* beta_one);

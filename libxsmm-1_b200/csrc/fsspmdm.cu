@@ -12,6 +12,12 @@
 
 namespace xb {
 
+struct FsTc;
+bool fs_tc_supported(int is_double, int M, int K);
+FsTc* fs_tc_build(int M, int K, int lda, int beta_one, const float* a_dense);
+bool fs_tc_launch(const FsTc* t, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream);
+void fs_tc_destroy(FsTc* t);
+
 struct FsOperator {
   // leading fields mirror the reference's private handle (src/libxsmm_main.h:695-715) so that code
   // peeking at M/N/K/ldb/ldc/N_chunksize/a_dense keeps working; a_dense == NULL <=> sparse branch.
@@ -30,6 +36,7 @@ struct FsOperator {
   std::vector<int> rowptr, col;
   std::vector<double> val;
   FsJit* jit;
+  FsTc* tc;            // tensor-core kernel for dense float operators (fsspmdm_tc.cu), or NULL
 };
 
 // ---- branch rule of the reference ------------------------------------------------------------------
@@ -133,7 +140,7 @@ FsOperator* fs_plan(int is_double, int M, int N, int K, int lda, int ldb, int ld
   }
   FsOperator* o = new FsOperator();
   o->M = M; o->N = N; o->K = K; o->ldb = ldb; o->ldc = ldc;
-  o->a_dense = 0; o->kernel = 0; o->jit = 0;
+  o->a_dense = 0; o->kernel = 0; o->jit = 0; o->tc = 0;
   o->is_double = is_double; o->beta_one = (1.0 == beta);
   o->d_rowptr = 0; o->d_col = 0; o->d_val = 0;
   if (is_double) fs_build_csr(*o, (const double*)a_dense, lda); else fs_build_csr(*o, (const float*)a_dense, lda);
@@ -192,9 +199,19 @@ FsOperator* fs_create(int is_double, int M, int N, int K, int lda, int ldb, int 
     XB_CUDA(cudaMalloc(&o->a_dense, packed.size()));
     if (o->a_dense) XB_CUDA(cudaMemcpy(o->a_dense, packed.data(), packed.size(), cudaMemcpyHostToDevice));
   }
+  // Dense float operators: once the FMA pipe, not HBM, bounds the baked kernel (nnz per column above ~7 per
+  // byte moved), the apply is a dense contraction and goes to the tensor cores (3xTF32, fsspmdm_tc.cu).
+  // LIBXSMM_B200_FSSPMDM_TC=1 forces that kernel for every eligible operator, =0 disables it.
+  if (fs_tc_supported(is_double, M, K)) {
+    const char* e = getenv("LIBXSMM_B200_FSSPMDM_TC");
+    const double bytes_per_col = 4.0 * (K + M * (o->beta_one ? 2.0 : 1.0));
+    const bool want = (e && *e) ? ('1' == *e) : ((double)o->nnz > 7.0 * bytes_per_col);   // measured break-even for 150 x 64: ~60 % dense
+    if (want) o->tc = fs_tc_build(M, K, lda, o->beta_one, (const float*)a_dense);
+  }
   // bake the operator into a specialised kernel (the GPU counterpart of the reference's JIT)
-  o->jit = fs_jit_build(is_double, M, K, o->beta_one, o->sparse_branch /*skip empty rows*/,
-                        o->rowptr.data(), o->col.data(), o->val.data());
+  // (not when the tensor-core kernel took the operator: panels it cannot take fall back to the generic kernel)
+  if (0 == o->tc) o->jit = fs_jit_build(is_double, (0 == ((ldb | ldc) & 1)) ? 1 : 0, M, K, o->beta_one, o->sparse_branch /*skip empty rows*/,
+                                       o->rowptr.data(), o->col.data(), o->val.data());
   o->kernel = o->jit;
   if (verbosity() > 0) {
     fprintf(stderr, "LIBXSMM_B200 fsspmdm: %dx%d nnz=%d unique=%d branch=%s kernel=%s\n", M, K, o->nnz, o->n_unique,
@@ -207,6 +224,7 @@ void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, 
 {
   if (0 == o || ncols <= 0) return;
   count_launch(1);
+  if (o->tc && fs_tc_launch(o->tc, dB, dC, ncols, ldb, ldc, stream)) return;
   if (o->jit && fs_jit_launch(o->jit, dB, dC, ncols, ldb, ldc, stream)) return;
   FsDev d;
   d.M = o->M; d.beta_one = o->beta_one; d.skip_empty = o->sparse_branch;
@@ -240,6 +258,7 @@ void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, 
 void fs_destroy(FsOperator* o)
 {
   if (0 == o) return;
+  if (o->tc) fs_tc_destroy(o->tc);
   if (o->jit) fs_jit_destroy(o->jit);
   if (o->d_rowptr) cudaFree(o->d_rowptr);
   if (o->d_col) cudaFree(o->d_col);
@@ -250,6 +269,7 @@ void fs_destroy(FsOperator* o)
 
 int fs_is_sparse_branch(const FsOperator* o) { return o ? o->sparse_branch : 0; }
 int fs_is_baked(const FsOperator* o) { return (o && o->jit) ? 1 : 0; }
+int fs_is_tensor_core(const FsOperator* o) { return (o && o->tc) ? 1 : 0; }
 int fs_needs_c_input(const FsOperator* o)
 {
   if (0 == o) return 0;
@@ -264,7 +284,7 @@ void fs_plan_info(const FsOperator* o, long long* info)
 }
 char* fs_kernel_source(const FsOperator* o)
 {
-  return fs_jit_source(o->is_double, o->M, o->K, o->beta_one, o->sparse_branch, o->rowptr.data(), o->col.data(), o->val.data());
+  return fs_jit_source(o->is_double, (0 == ((o->ldb | o->ldc) & 1)) ? 1 : 0, o->M, o->K, o->beta_one, o->sparse_branch, o->rowptr.data(), o->col.data(), o->val.data());
 }
 void fs_shape(const FsOperator* o, int* M, int* N, int* K, int* ldb, int* ldc, int* beta_one)
 {

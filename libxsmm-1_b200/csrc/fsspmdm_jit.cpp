@@ -20,7 +20,7 @@ namespace xb {
 struct FsJit {
   cudaLibrary_t lib;
   cudaKernel_t kern;
-  cudaKernel_t kern2;   // two columns per thread (float only), or NULL
+  int cols_per_thread;  // 1, or 2 (float, even pitches: 8-byte accesses)
   int block;
 };
 
@@ -82,35 +82,42 @@ void append(std::string& s, const char* fmt, ...)
 void emit_kernel(std::string& s, const char* name, int cpt, int is_double, int M, int K, int beta_one, int skip_empty,
                  const int* rowptr, const int* col, const double* val)
 {
+  // Only scalar variables are emitted (the two columns of the vector form are split right after the load and
+  // joined right before the store): NVRTC's optimiser needs several times longer for thousands of float2 values.
   const char* T = is_double ? "double" : "float";
   char V[16];
   snprintf(V, sizeof(V), "%s%s", T, 2 == cpt ? "2" : "");
+  const char* f = is_double ? "fma" : "fmaf";
   std::vector<char> used(K, 0);
   for (int u = 0; u < rowptr[M]; ++u) used[col[u]] = 1;
   append(s, "extern \"C\" __global__ void __launch_bounds__(%d) %s(const %s* __restrict__ B, %s* __restrict__ C, long long ncols, long long ldb, long long ldc)\n{\n", kBlock, name, T, T);
   append(s, "  const long long n = ((long long)blockIdx.x * %d + threadIdx.x) * %d;\n  if (n >= ncols) return;\n", kBlock, cpt);
-  append(s, "  const %s* __restrict__ b = B + n;\n  %s* __restrict__ c = C + n;\n  %s acc;\n", T, T, V);
-  for (int k = 0; k < K; ++k) if (used[k]) append(s, "  const %s b%d = __ldcs((const %s*)(b + %dLL * ldb));\n", V, k, V, k);
+  append(s, "  const %s* __restrict__ b = B + n;\n  %s* __restrict__ c = C + n;\n  %s ax%s;\n", T, T, T, 2 == cpt ? ", ay" : "");
+  for (int k = 0; k < K; ++k) if (used[k]) {
+    if (2 == cpt) append(s, "  const %s t%d = __ldcs((const %s*)(b + %dLL * ldb)); const %s b%dx = t%d.x, b%dy = t%d.y;\n", V, k, V, k, T, k, k, k, k);
+    else append(s, "  const %s b%dx = __ldcs(b + %dLL * ldb);\n", T, k, k);
+  }
   // beta = 1: the C rows of a group are fetched together ahead of the group's chains, so that their latency
   // is paid once per group instead of once per row (loads cannot be hoisted over the stores by the compiler)
   const int group = beta_one ? (is_double ? 8 : 16) : 1;
   for (int m0 = 0; m0 < M; m0 += group) {
     if (beta_one) {
-      for (int m = m0; m < M && m < m0 + group; ++m)
-        if (rowptr[m + 1] != rowptr[m]) append(s, "  %s c%d = __ldcs((const %s*)(c + %dLL * ldc));\n", V, m, V, m);
+      for (int m = m0; m < M && m < m0 + group; ++m) if (rowptr[m + 1] != rowptr[m]) {
+        if (2 == cpt) append(s, "  const %s u%d = __ldcs((const %s*)(c + %dLL * ldc)); const %s c%dx = u%d.x, c%dy = u%d.y;\n", V, m, V, m, T, m, m, m, m);
+        else append(s, "  const %s c%dx = __ldcs(c + %dLL * ldc);\n", T, m, m);
+      }
     }
     for (int m = m0; m < M && m < m0 + group; ++m) {
       const int lo = rowptr[m], hi = rowptr[m + 1];
       if (hi == lo) {
         if (!skip_empty && !beta_one) {
-          if (2 == cpt) append(s, "  acc.x = 0; acc.y = 0; __stcs((%s*)(c + %dLL * ldc), acc);\n", V, m);
+          if (2 == cpt) append(s, "  __stcs((%s*)(c + %dLL * ldc), make_%s(0, 0));\n", V, m, V);
           else append(s, "  __stcs(c + %dLL * ldc, (%s)0);\n", m, T);
         }
         continue;
       }
-      if (beta_one) append(s, "  acc = c%d;\n", m);
-      else if (2 == cpt) append(s, "  acc.x = 0; acc.y = 0;\n");
-      else append(s, "  acc = 0;\n");
+      if (beta_one) append(s, 2 == cpt ? "  ax = c%dx; ay = c%dy;\n" : "  ax = c%dx;\n", m, m);
+      else append(s, 2 == cpt ? "  ax = 0; ay = 0;\n" : "  ax = 0;\n");
       for (int u = lo; u < hi; ++u) {
         char lit[64];
         if (is_double) {
@@ -123,23 +130,23 @@ void emit_kernel(std::string& s, const char* name, int cpt, int is_double, int M
           memcpy(&bits, &v, 4);
           snprintf(lit, sizeof(lit), "__int_as_float(0x%08x)", (unsigned)bits);
         }
-        const char* f = is_double ? "fma" : "fmaf";
-        if (2 == cpt) append(s, "  acc.x = %s(%s, b%d.x, acc.x); acc.y = %s(%s, b%d.y, acc.y);\n", f, lit, col[u], f, lit, col[u]);
-        else append(s, "  acc = %s(%s, b%d, acc);\n", f, lit, col[u]);
+        if (2 == cpt) append(s, "  ax = %s(%s, b%dx, ax); ay = %s(%s, b%dy, ay);\n", f, lit, col[u], f, lit, col[u]);
+        else append(s, "  ax = %s(%s, b%dx, ax);\n", f, lit, col[u]);
       }
-      append(s, "  __stcs((%s*)(c + %dLL * ldc), acc);\n", V, m);
+      if (2 == cpt) append(s, "  __stcs((%s*)(c + %dLL * ldc), make_%s(ax, ay));\n", V, m, V);
+      else append(s, "  __stcs(c + %dLL * ldc, ax);\n", m);
     }
   }
   s += "}\n";
 }
 
-std::string emit(int is_double, int M, int K, int beta_one, int skip_empty,
+// vec2: emit the two-columns-per-thread form (8-byte accesses; float only) instead of the one-column form
+std::string emit(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
                  const int* rowptr, const int* col, const double* val)
 {
   std::string s;
   s.reserve(160 * (size_t)rowptr[M] + 8192);
-  emit_kernel(s, "fs_baked", 1, is_double, M, K, beta_one, skip_empty, rowptr, col, val);
-  if (!is_double) emit_kernel(s, "fs_baked2", 2, is_double, M, K, beta_one, skip_empty, rowptr, col, val);   // 8-byte accesses
+  emit_kernel(s, "fs_baked", (vec2 && !is_double) ? 2 : 1, is_double, M, K, beta_one, skip_empty, rowptr, col, val);
   return s;
 }
 
@@ -149,7 +156,9 @@ bool supported(int is_double, int M, int K, const int* rowptr, const int* col)
   int nused = 0;
   for (int u = 0; u < rowptr[M]; ++u) if (!used[col[u]]) { used[col[u]] = 1; ++nused; }
   // B rows live in registers: 2 registers per double, 1 per float, out of 255
-  return rowptr[M] > 0 && (is_double ? nused <= 100 : nused <= 200) && rowptr[M] <= 60000;
+  // NVRTC needs ~1 s per 1000 fused multiply-adds of straight-line code and grows faster than linearly:
+  // create() stays within seconds up to ~6000 nonzeros; denser operators use the generic kernel
+  return rowptr[M] > 0 && (is_double ? nused <= 100 : nused <= 200) && rowptr[M] <= 6000;
 }
 
 std::mutex g_cache_mtx;
@@ -157,16 +166,16 @@ std::map<std::string, std::vector<char> > g_cubin_cache;
 
 }  // namespace
 
-char* fs_jit_source(int is_double, int M, int K, int beta_one, int skip_empty,
+char* fs_jit_source(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
                     const int* rowptr, const int* col, const double* val)
 {
-  const std::string s = emit(is_double, M, K, beta_one, skip_empty, rowptr, col, val);
+  const std::string s = emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
   char* out = (char*)malloc(s.size() + 1);
   if (out) memcpy(out, s.c_str(), s.size() + 1);
   return out;
 }
 
-FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty,
+FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
                     const int* rowptr, const int* col, const double* val)
 {
   const char* env = getenv("LIBXSMM_B200_FSSPMDM_JIT");
@@ -174,7 +183,7 @@ FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty,
   if (!supported(is_double, M, K, rowptr, col)) return 0;
   Nvrtc* rt = nvrtc();
   if (0 == rt) { set_error(-2, "fsspmdm: NVRTC (libnvrtc.so.12) not found; using the generic kernel"); return 0; }
-  const std::string src = emit(is_double, M, K, beta_one, skip_empty, rowptr, col, val);
+  const std::string src = emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
   std::vector<char> cubin;
   {
     std::lock_guard<std::mutex> lock(g_cache_mtx);
@@ -204,10 +213,9 @@ FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty,
   }
   FsJit* j = new FsJit();
   j->block = kBlock;
-  j->kern2 = 0;
+  j->cols_per_thread = (vec2 && !is_double) ? 2 : 1;
   cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), 0, 0, 0, 0, 0, 0);
   if (cudaSuccess == e) e = cudaLibraryGetKernel(&j->kern, j->lib, "fs_baked");
-  if (cudaSuccess == e && !is_double) e = cudaLibraryGetKernel(&j->kern2, j->lib, "fs_baked2");
   if (cudaSuccess != e) {
     set_error((int)e, "fsspmdm: loading the baked kernel failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -219,12 +227,13 @@ FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty,
 
 bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream)
 {
-  // the 2-column form needs 8-byte aligned rows: even pitches, even column count, aligned bases
-  const bool two = (0 != j->kern2) && (0 == ((ldb | ldc | ncols) & 1)) && (0 == (((uintptr_t)dB | (uintptr_t)dC) & 7));
-  const long long per_block = (long long)j->block * (two ? 2 : 1);
+  // the 2-column form needs 8-byte aligned rows: even pitches, even column count, aligned bases; a panel that does
+  // not qualify goes to the generic kernel (return false)
+  if (2 == j->cols_per_thread && !((0 == ((ldb | ldc | ncols) & 1)) && (0 == (((uintptr_t)dB | (uintptr_t)dC) & 7)))) return false;
+  const long long per_block = (long long)j->block * j->cols_per_thread;
   const long long blocks = (ncols + per_block - 1) / per_block;
   void* args[] = { (void*)&dB, (void*)&dC, (void*)&ncols, (void*)&ldb, (void*)&ldc };
-  const cudaError_t e = cudaLaunchKernel((const void*)(two ? j->kern2 : j->kern), dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, 0, stream);
+  const cudaError_t e = cudaLaunchKernel((const void*)j->kern, dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, 0, stream);
   if (cudaSuccess != e) { set_error((int)e, "fsspmdm: baked kernel launch failed: %s", cudaGetErrorString(e)); return false; }
   return true;
 }

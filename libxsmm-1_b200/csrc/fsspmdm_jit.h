@@ -8,11 +8,11 @@ namespace xb {
 struct FsJit;
 // returns NULL when the operator is outside what the baked kernel supports (the caller then uses the
 // generic kernel) or when NVRTC is not available (reported through set_error).
-FsJit* fs_jit_build(int is_double, int M, int K, int beta_one, int skip_empty_rows,
+FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int skip_empty_rows,
                     const int* rowptr, const int* col, const double* val);
 bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream);
 void fs_jit_destroy(FsJit* j);
 // the CUDA source that would be compiled (for tests / inspection); caller frees with free()
-char* fs_jit_source(int is_double, int M, int K, int beta_one, int skip_empty_rows,
+char* fs_jit_source(int is_double, int vec2, int M, int K, int beta_one, int skip_empty_rows,
                     const int* rowptr, const int* col, const double* val);
 }  // namespace xb

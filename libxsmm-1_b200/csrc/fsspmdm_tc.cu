@@ -1,0 +1,270 @@
+// K4f: tensor-core branch of sfsspmdm for DENSE fixed operators (fp32, K <= 64, M <= 192), sm_100a.
+//
+// The reference always applies a float operator through its dense SMM kernel (src/libxsmm_fsspmdm.c:240-248,
+// SREG is F64-only: src/libxsmm_main.c:1418).  For sparse operators the create-time baked FMA kernel is already
+// bound by HBM; once the operator is dense enough that the FMA pipe becomes the bound (about half full for
+// 150 x 64), the apply really is a dense contraction and goes to tcgen05:
+//
+//     D[n, m] = sum_k  B[k, n0 + n] * A[m, k]          (128 columns of the panel x M operator rows per tile)
+//
+//   * "A" operand = the B tile as it lies in memory ([k][n], n contiguous -> MN-major TF32 operand, TMA boxes of
+//     32 columns with the 128B/32B-atom swizzle), "B" operand = the operator (K-major, SWIZZLE_128B), resident in
+//     shared memory for the whole persistent CTA.
+//   * 3xTF32: operator hi/lo split once at create time; b_lo = b - trunc(b) by the worker warps per tile.
+//   * accumulator [128 lanes = columns][M_pad TMEM columns], double buffered: the epilogue of tile t (tcgen05.ld:
+//     thread = panel column, registers = operator rows -> every store instruction writes one full 128-byte line
+//     of a C row) overlaps the MMAs of tile t+1.
+// Not the reference's rounding sequence; contract 1e-5 relative (observed ~2e-6; at most 24 accumulations).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <vector>
+#include <cstring>
+
+namespace xb {
+
+constexpr int FT_BN = 128;                  // panel columns per tile (UMMA M)
+constexpr int FT_STAGES = 2;
+constexpr int FT_WORKERS = 4;               // worker warps = the four TMEM lane quarters
+constexpr int FT_THREADS = (2 + FT_WORKERS) * 32;
+constexpr int FT_STAGE_HALF = 64 * FT_BN * 4;          // 32 KiB: 64 k x 128 columns fp32 (raw); the lo copy follows
+constexpr int FT_SMEM_B = 0;                           // stages: raw | lo
+constexpr int FT_SMEM_OP = FT_STAGES * 2 * FT_STAGE_HALF;   // operator: chunk 0 hi, chunk 1 hi, chunk 0 lo, chunk 1 lo (M_pad x 128 B each)
+
+struct FsTcArgs {
+  const float* B; float* C;
+  const unsigned char* op_packed;   // 4 planes of M_pad x 128 B, already swizzled
+  long long ncols, ldb, ldc;
+  int M, M_pad, K, beta_one;
+};
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
+{
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int plane = p.M_pad * 128;
+  unsigned char* sop = smem + FT_SMEM_OP;
+  uint64_t* bar = (uint64_t*)(sop + 4 * plane);
+  uint64_t* b_full = bar;            // [2] TMA landed
+  uint64_t* b_split = bar + 2;       // [2] workers wrote b_lo
+  uint64_t* b_free = bar + 4;        // [2] MMAs that read the stage have completed
+  uint64_t* acc_full = bar + 6;      // [2] tile's MMAs completed
+  uint64_t* acc_free = bar + 8;      // [2] epilogue drained the accumulator
+  uint32_t* tmem_slot = (uint32_t*)(bar + 10);
+
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long ntiles = (p.ncols + FT_BN - 1) / FT_BN;
+  const uint32_t sbase = smem_u32(smem);
+  const int nks = (p.K + 7) / 8;     // k-steps of 8
+
+  if (0 == tid) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&b_full[i], 1); mbar_init(&b_split[i], FT_WORKERS); mbar_init(&b_free[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], FT_WORKERS);
+    }
+    mbar_fence_init();
+  }
+  if (1 == warp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  // the operator (already in UMMA layout) becomes resident
+  for (int i = tid; i < 4 * plane / 16; i += FT_THREADS) ((uint4*)sop)[i] = __ldg((const uint4*)p.op_packed + i);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (0 == warp) {
+    if (0 == lane) {
+      tma_prefetch_desc(&tmB);
+      long long it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = (int)(it & 1);
+        if (it >= 2) mbar_wait(&b_free[s], (uint32_t)(((it >> 1) - 1) & 1));
+        mbar_arrive_expect_tx(&b_full[s], FT_STAGE_HALF);
+        unsigned char* dst = smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * (64 * 128), &tmB, (int)(t * FT_BN) + 32 * j, 0, &b_full[s]);
+      }
+    }
+  }
+  else if (1 == warp) {
+    if (0 == lane) {
+      // D = F32, A = B = TF32, A MN-major (the B tile), B K-major (the operator), M = 128, N = M_pad
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(p.M_pad >> 3) << 17) | ((uint32_t)(FT_BN >> 4) << 24);
+      long long it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = (int)(it & 1), ab = (int)(it & 1);
+        if (it >= 2) mbar_wait(&acc_free[ab], (uint32_t)(((it >> 1) - 1) & 1));
+        mbar_wait(&b_split[s], (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        const uint32_t x_hi = sbase + FT_SMEM_B + s * 2 * FT_STAGE_HALF, x_lo = x_hi + FT_STAGE_HALF;
+        const uint32_t tacc = tmem_d + (uint32_t)(ab * 256);
+        for (int ks = 0; ks < nks; ++ks) {
+          // tile operand (MN-major, 128B/32B-atom swizzle): 8 k = 1024 B; 32-column blocks 64*128 B apart, 4-k groups 512 B
+          const uint64_t dxh = tc_smem_desc(x_hi + ks * 1024, 64 * 128, 512, 1);
+          const uint64_t dxl = tc_smem_desc(x_lo + ks * 1024, 64 * 128, 512, 1);
+          // operator (K-major, SWIZZLE_128B): chunk = ks / 4 (32 k each), 8 k = 32 B inside the 128-byte rows
+          const uint32_t o = sbase + FT_SMEM_OP + (uint32_t)((ks >> 2) * plane + (ks & 3) * 32);
+          const uint64_t doh = tc_smem_desc(o, 16, 1024, 2);
+          const uint64_t dol = tc_smem_desc(o + 2 * plane, 16, 1024, 2);
+          tc_mma_tf32(tacc, dxh, doh, idesc, ks > 0 ? 1u : 0u);
+          tc_mma_tf32(tacc, dxl, doh, idesc, 1u);
+          tc_mma_tf32(tacc, dxh, dol, idesc, 1u);
+        }
+        tc_commit(&b_free[s]);
+        tc_commit(&acc_full[ab]);
+      }
+    }
+  }
+  else {
+    const int wt = tid - 64;                      // 0..127 = TMEM lane = column inside the tile
+    const int quarter = warp & 3;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = (int)(it & 1), ab = (int)(it & 1);
+      // (1) b_lo = b - trunc_tf32(b) for this tile (same swizzled addresses)
+      mbar_wait(&b_full[s], (uint32_t)((it >> 1) & 1));
+      {
+        const uint4* src = (const uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF);
+        uint4* dst = (uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF + FT_STAGE_HALF);
+#pragma unroll 4
+        for (int i = wt; i < FT_STAGE_HALF / 16; i += FT_WORKERS * 32) {
+          const uint4 b = src[i];
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(b.x) - __uint_as_float(b.x & 0xFFFFE000u));
+          l.y = __float_as_uint(__uint_as_float(b.y) - __uint_as_float(b.y & 0xFFFFE000u));
+          l.z = __float_as_uint(__uint_as_float(b.z) - __uint_as_float(b.z & 0xFFFFE000u));
+          l.w = __float_as_uint(__uint_as_float(b.w) - __uint_as_float(b.w & 0xFFFFE000u));
+          dst[i] = l;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (0 == lane) mbar_arrive(&b_split[s]);
+      // (2) epilogue of the PREVIOUS tile while this tile's MMAs run
+      if (it > 0) {
+        const long long tp = t - gridDim.x;
+        const int pb = (int)((it - 1) & 1);
+        mbar_wait(&acc_full[pb], (uint32_t)(((it - 1) >> 1) & 1));
+        tc_fence_after();
+        const long long col = tp * FT_BN + quarter * 32 + lane;
+        for (int m0 = 0; m0 < p.M; m0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pb * 256 + m0), v);
+          if (col < p.ncols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (m0 + j < p.M) {
+                float* dst = p.C + (long long)(m0 + j) * p.ldc + col;
+                const float r = __uint_as_float(v[j]);
+                __stcs(dst, p.beta_one ? (r + __ldcs(dst)) : r);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (0 == lane) mbar_arrive(&acc_free[pb]);
+      }
+    }
+    // (3) epilogue of the last tile
+    if (it > 0) {
+      const long long tp = (long long)blockIdx.x + (it - 1) * gridDim.x;
+      const int pb = (int)((it - 1) & 1);
+      mbar_wait(&acc_full[pb], (uint32_t)(((it - 1) >> 1) & 1));
+      tc_fence_after();
+      const long long col = tp * FT_BN + quarter * 32 + lane;
+      for (int m0 = 0; m0 < p.M; m0 += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pb * 256 + m0), v);
+        if (col < p.ncols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (m0 + j < p.M) {
+              float* dst = p.C + (long long)(m0 + j) * p.ldc + col;
+              const float r = __uint_as_float(v[j]);
+              __stcs(dst, p.beta_one ? (r + __ldcs(dst)) : r);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (1 == warp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(512) : "memory");
+  }
+}
+
+bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
+                              unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows, bool atom32);
+
+// ---- host side ---------------------------------------------------------------------------------------------
+struct FsTc { unsigned char* d_op; int M, M_pad, K, beta_one; size_t smem; int sms; };
+
+static int fs_tc_mpad(int M) { return (M + 15) / 16 * 16; }
+
+// can this operator use the tensor-core kernel at all?
+bool fs_tc_supported(int is_double, int M, int K) { return !is_double && K >= 1 && K <= 64 && M >= 1 && fs_tc_mpad(M) <= 192; }
+
+FsTc* fs_tc_build(int M, int K, int lda, int beta_one, const float* a_dense)
+{
+  FsTc* t = new FsTc();
+  t->M = M; t->K = K; t->M_pad = fs_tc_mpad(M); t->beta_one = beta_one; t->d_op = 0;
+  const int plane = t->M_pad * 128;
+  std::vector<unsigned char> packed((size_t)4 * plane, 0);
+  for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) {
+    const float v = a_dense[(size_t)m * lda + k];
+    unsigned int bits; memcpy(&bits, &v, 4);
+    bits &= 0xFFFFE000u;
+    float hi; memcpy(&hi, &bits, 4);
+    const float lo = v - hi;
+    const int chunk = k >> 5, kk = k & 31;
+    const size_t off = (size_t)chunk * plane + (size_t)(m >> 3) * 1024 + (size_t)(m & 7) * 128 + (size_t)((((kk >> 2) ^ (m & 7)) & 7) << 4) + (size_t)((kk & 3) << 2);
+    memcpy(&packed[off], &hi, 4);
+    memcpy(&packed[(size_t)2 * plane + off], &lo, 4);
+  }
+  XB_CUDA(cudaMalloc((void**)&t->d_op, packed.size()));
+  if (0 == t->d_op) { delete t; return 0; }
+  XB_CUDA(cudaMemcpy(t->d_op, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  t->smem = (size_t)FT_SMEM_OP + (size_t)4 * plane + 256;
+  int dev = 0; cudaDeviceProp prop;
+  t->sms = 148;
+  if (cudaSuccess == cudaGetDevice(&dev) && cudaSuccess == cudaGetDeviceProperties(&prop, dev)) t->sms = prop.multiProcessorCount;
+  static bool configured = false;
+  if (!configured) {
+    XB_CUDA(cudaFuncSetAttribute(fsspmdm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256)));
+    configured = true;
+  }
+  return t;
+}
+
+bool fs_tc_launch(const FsTc* t, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream)
+{
+  if (0 == t || ncols <= 0) return false;
+  if (0 != ((uintptr_t)dB & 15) || 0 != ((ldb * 4) & 15)) return false;
+  CUtensorMap map;
+  if (!make_tensor_map_2d_sw128(&map, dB, 4, (unsigned long long)ncols, (unsigned long long)t->K, (unsigned long long)ldb * 4, 32, 64, true)) return false;
+  FsTcArgs a;
+  a.B = (const float*)dB; a.C = (float*)dC; a.op_packed = t->d_op; a.ncols = ncols; a.ldb = ldb; a.ldc = ldc;
+  a.M = t->M; a.M_pad = t->M_pad; a.K = t->K; a.beta_one = t->beta_one;
+  const long long ntiles = (ncols + FT_BN - 1) / FT_BN;
+  const unsigned grid = (unsigned)(ntiles < t->sms ? ntiles : t->sms);
+  fsspmdm_tc_kernel<<<grid, FT_THREADS, t->smem, stream>>>(map, a);
+  XB_CUDA(cudaGetLastError());
+  return true;
+}
+
+void fs_tc_destroy(FsTc* t)
+{
+  if (0 == t) return;
+  if (t->d_op) cudaFree(t->d_op);
+  delete t;
+}
+
+}  // namespace xb

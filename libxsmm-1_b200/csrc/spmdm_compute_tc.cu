@@ -173,7 +173,7 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
     // The tile's nonzeros of one k-block are one contiguous range of the slice.  Thread wt owns nonzeros
     // first + wt + i*TC_WT; the first TC_NQ of them are fetched ONCE per k-block into registers (packed
     // row|column and value), well before they are needed, and scattered twice (k < 64, k >= 64).
-    uint32_t pk[TC_NQ / 2]; float vv[TC_NQ];   // pk: two packed tcoff values (xb_tc_pack) per register
+    uint32_t pk[TC_NQ]; float vv[TC_NQ];       // raw loads only: nothing here may consume them (no stall on the fetch)
     int first = 0, last = 0;
     auto fetch = [&](int kbf) {
       const int sidx = kbf * g.mb + mbi;
@@ -186,9 +186,8 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
 #pragma unroll
       for (int i = 0; i < TC_NQ; ++i) {
         const int q = first + wt + i * TC_WT;
-        uint32_t t = 0; vv[i] = 0.f;           // value 0 scatters +0 / +0 into a zeroed tile: harmless for absent entries
-        if (q < last) { t = (uint32_t)__ldg(ri + q); vv[i] = __ldg(va + q); }
-        if (i & 1) pk[i >> 1] |= t << 16; else pk[i >> 1] = t;
+        pk[i] = 0; vv[i] = 0.f;
+        if (q < last) { pk[i] = (uint32_t)__ldg(ri + q); vv[i] = __ldg(va + q); }
       }
     };
     fetch(0);
@@ -215,7 +214,7 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
 #pragma unroll
       for (int i = 0; i < TC_NQ; ++i) {
         const int q = first + wt + i * TC_WT;
-        if (q < last) put((i & 1) ? (pk[i >> 1] >> 16) : (pk[i >> 1] & 0xFFFFu), vv[i]);
+        if (q < last) put(pk[i], vv[i]);
       }
       if (first + TC_NQ * TC_WT < last) {   // denser than TC_NQ*TC_WT nonzeros per tile: the rest straight from memory
         const int sidx = kb * g.mb + mbi;

@@ -181,3 +181,45 @@ def test_full_size_properties(gpu, oracle, dtype, logn):
     C, _, _ = run_gpu(xs, a, ones, C0, 0.0)
     rs, _ = oracle_run(oracle, a, np.ones((64, 16), dtype), np.zeros((150, 16), dtype), 0.0)
     assert (C == rs[:, :1]).all()
+
+
+@pytest.mark.parametrize("M,K,density", [(150, 64, 1.0), (150, 64, 0.6), (96, 40, 1.0), (192, 64, 0.9), (17, 5, 1.0)])
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_sfsspmdm_tensor_core_branch(gpu, oracle, monkeypatch, M, K, density, beta):
+    """dense float operators go to tcgen05 (3xTF32): the branch where the reference itself uses its dense SMM
+    kernel and the apply really is a dense contraction.  Contract 1e-5 relative (not the fma-chain rounding)."""
+    xs = gpu
+    monkeypatch.setenv("LIBXSMM_B200_FSSPMDM_TC", "1")
+    a = xs.workloads.fsspmdm_operator(M, K, density, None, np.float32, seed=21)
+    rng = np.random.default_rng(22)
+    ld, N = 4096 + 64, 4096 + 32      # panel of a wider matrix, last 128-column tile partial
+    B = rng.random((K, ld), np.float32); C0 = rng.random((M, ld), np.float32)
+    op = xs.Fsspmdm(a, N, ldb=ld, ldc=ld, beta=beta)
+    try:
+        assert op.is_tensor_core
+        dB = xs.DeviceBuffer.from_numpy(B); dC = xs.DeviceBuffer.from_numpy(C0)
+        op.execute_stream(dB, dC)
+        xs.synchronize()
+        C = dC.to_numpy(np.float32, C0.shape)
+        dB.free(); dC.free()
+    finally:
+        op.destroy()
+    OC = C0.copy()
+    oracle.sfsspmdm_execute(a, B, OC, beta, N=N)
+    err = np.abs(C.astype(np.float64) - OC.astype(np.float64)).max() / np.abs(OC).max()
+    assert err <= RTOL_F32, err
+    same_bits(np.ascontiguousarray(C[:, N:]), np.ascontiguousarray(C0[:, N:]))     # columns beyond N untouched
+    xs.check()
+
+
+def test_sfsspmdm_branch_choice(gpu, monkeypatch):
+    """sparse float operators stay on the baked FMA kernel (HBM-bound), dense ones take the tensor cores."""
+    monkeypatch.delenv("LIBXSMM_B200_FSSPMDM_TC", raising=False)
+    xs = gpu
+    sparse = xs.Fsspmdm(xs.workloads.fsspmdm_operator(150, 64, 0.3, 8, np.float32, seed=1), 1024)
+    dense = xs.Fsspmdm(xs.workloads.fsspmdm_operator(150, 64, 1.0, None, np.float32, seed=1), 1024)
+    wide = xs.Fsspmdm(xs.workloads.fsspmdm_operator(150, 128, 1.0, None, np.float32, seed=1), 1024)   # K > 64: not eligible
+    try:
+        assert not sparse.is_tensor_core and dense.is_tensor_core and not wide.is_tensor_core
+    finally:
+        sparse.destroy(); dense.destroy(); wide.destroy()
