@@ -1,6 +1,7 @@
-// Create-time kernel baking for FSSPMDM through NVRTC (loaded lazily with dlopen so that the
-// library itself loads on machines without a CUDA toolkit; create() then falls back to the generic
-// kernel and records the reason).  The compiled cubin is loaded with the CUDA runtime's library API.
+// Create-time kernel baking for FSSPMDM.  Default: the kernel is emitted as PTX text and assembled by the
+// driver (cudaLibraryLoadData).  Alternative (LIBXSMM_B200_FSSPMDM_JIT=nvrtc): CUDA C++ compiled by NVRTC, loaded
+// lazily with dlopen so that the library itself loads on machines without a CUDA toolkit.  On any failure
+// create() falls back to the generic kernel and records the reason.
 #include "fsspmdm_jit.h"
 #include "common.cuh"
 #include <nvrtc.h>
@@ -150,15 +151,98 @@ std::string emit(int is_double, int vec2, int M, int K, int beta_one, int skip_e
   return s;
 }
 
+// The same kernel as PTX text.  The driver's JIT (ptxas) assembles thousands of straight-line fused
+// multiply-adds in a fraction of the time NVRTC's optimiser needs for the CUDA C++ form (measured: 6.3 s vs
+// well under a second for the 150 x 64 / 30 % float operator), which is what keeps create() interactive.
+std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
+                     const int* rowptr, const int* col, const double* val)
+{
+  const int cpt = (vec2 && !is_double) ? 2 : 1;
+  const int esz = is_double ? 8 : 4;
+  const char* ty = is_double ? "f64" : "f32";
+  std::vector<char> used(K, 0);
+  for (int u = 0; u < rowptr[M]; ++u) used[col[u]] = 1;
+  std::string s;
+  s.reserve(96 * (size_t)rowptr[M] * cpt + 8192);
+  s += ".version 8.6\n.target sm_100a\n.address_size 64\n\n";
+  s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC)\n";
+  append(s, ".maxntid %d, 1, 1\n", kBlock);
+  s += "{\n";
+  s += "  .reg .pred %p;\n  .reg .b32 %r<4>;\n  .reg .b64 %rd<12>;\n";
+  append(s, "  .reg .%s %%bx<%d>, %%by<%d>, %%cx<%d>, %%cy<%d>, %%ax, %%ay;\n", ty, K, K, M, M);
+  s += "  ld.param.u64 %rd0, [pB];\n  ld.param.u64 %rd1, [pC];\n  ld.param.u64 %rd2, [pN];\n  ld.param.u64 %rd3, [pLDB];\n  ld.param.u64 %rd4, [pLDC];\n";
+  s += "  mov.u32 %r0, %ctaid.x;\n  mov.u32 %r1, %tid.x;\n";
+  append(s, "  mul.wide.u32 %%rd5, %%r0, %d;\n  cvt.u64.u32 %%rd6, %%r1;\n  add.s64 %%rd5, %%rd5, %%rd6;\n", kBlock);
+  if (2 == cpt) s += "  shl.b64 %rd5, %rd5, 1;\n";
+  s += "  setp.ge.s64 %p, %rd5, %rd2;\n  @%p bra DONE;\n";
+  append(s, "  mad.lo.s64 %%rd0, %%rd5, %d, %%rd0;\n  mad.lo.s64 %%rd1, %%rd5, %d, %%rd1;\n", esz, esz);   // b = B + n, c = C + n
+  append(s, "  mul.lo.s64 %%rd3, %%rd3, %d;\n  mul.lo.s64 %%rd4, %%rd4, %d;\n", esz, esz);                 // row pitches in bytes
+  for (int k = 0; k < K; ++k) if (used[k]) {
+    append(s, "  mad.lo.s64 %%rd7, %%rd3, %d, %%rd0;\n", k);
+    if (2 == cpt) append(s, "  ld.global.cs.v2.%s {%%bx%d, %%by%d}, [%%rd7];\n", ty, k, k);
+    else append(s, "  ld.global.cs.%s %%bx%d, [%%rd7];\n", ty, k);
+  }
+  const int group = beta_one ? (is_double ? 8 : 16) : 1;
+  for (int m0 = 0; m0 < M; m0 += group) {
+    if (beta_one) {
+      for (int m = m0; m < M && m < m0 + group; ++m) if (rowptr[m + 1] != rowptr[m]) {
+        append(s, "  mad.lo.s64 %%rd8, %%rd4, %d, %%rd1;\n", m);
+        if (2 == cpt) append(s, "  ld.global.cs.v2.%s {%%cx%d, %%cy%d}, [%%rd8];\n", ty, m, m);
+        else append(s, "  ld.global.cs.%s %%cx%d, [%%rd8];\n", ty, m);
+      }
+    }
+    for (int m = m0; m < M && m < m0 + group; ++m) {
+      const int lo = rowptr[m], hi = rowptr[m + 1];
+      const char* zero = is_double ? "0d0000000000000000" : "0f00000000";
+      if (hi == lo) {
+        if (!skip_empty && !beta_one) {
+          append(s, "  mad.lo.s64 %%rd8, %%rd4, %d, %%rd1;\n  mov.%s %%ax, %s;\n", m, ty, zero);
+          if (2 == cpt) append(s, "  st.global.cs.v2.%s [%%rd8], {%%ax, %%ax};\n", ty);
+          else append(s, "  st.global.cs.%s [%%rd8], %%ax;\n", ty);
+        }
+        continue;
+      }
+      if (beta_one) {
+        append(s, "  mov.%s %%ax, %%cx%d;\n", ty, m);
+        if (2 == cpt) append(s, "  mov.%s %%ay, %%cy%d;\n", ty, m);
+      }
+      else {
+        append(s, "  mov.%s %%ax, %s;\n", ty, zero);
+        if (2 == cpt) append(s, "  mov.%s %%ay, %s;\n", ty, zero);
+      }
+      for (int u = lo; u < hi; ++u) {
+        char lit[32];
+        if (is_double) {
+          unsigned long long bits; const double v = val[u];
+          memcpy(&bits, &v, 8);
+          snprintf(lit, sizeof(lit), "0d%016llX", bits);
+        }
+        else {
+          unsigned int bits; const float v = (float)val[u];
+          memcpy(&bits, &v, 4);
+          snprintf(lit, sizeof(lit), "0f%08X", bits);
+        }
+        append(s, "  fma.rn.%s %%ax, %s, %%bx%d, %%ax;\n", ty, lit, col[u]);
+        if (2 == cpt) append(s, "  fma.rn.%s %%ay, %s, %%by%d, %%ay;\n", ty, lit, col[u]);
+      }
+      append(s, "  mad.lo.s64 %%rd8, %%rd4, %d, %%rd1;\n", m);
+      if (2 == cpt) append(s, "  st.global.cs.v2.%s [%%rd8], {%%ax, %%ay};\n", ty);
+      else append(s, "  st.global.cs.%s [%%rd8], %%ax;\n", ty);
+    }
+  }
+  s += "DONE:\n  ret;\n}\n";
+  return s;
+}
+
 bool supported(int is_double, int M, int K, const int* rowptr, const int* col)
 {
   std::vector<char> used(K, 0);
   int nused = 0;
   for (int u = 0; u < rowptr[M]; ++u) if (!used[col[u]]) { used[col[u]] = 1; ++nused; }
   // B rows live in registers: 2 registers per double, 1 per float, out of 255
-  // NVRTC needs ~1 s per 1000 fused multiply-adds of straight-line code and grows faster than linearly:
-  // create() stays within seconds up to ~6000 nonzeros; denser operators use the generic kernel
-  return rowptr[M] > 0 && (is_double ? nused <= 100 : nused <= 200) && rowptr[M] <= 6000;
+  // B rows live in registers (2 registers per double, 1 per float, out of 255); the NVRTC form is additionally
+  // limited to ~6000 nonzeros in fs_jit_build (compile time grows faster than linearly)
+  return rowptr[M] > 0 && (is_double ? nused <= 100 : nused <= 200) && rowptr[M] <= 40000;
 }
 
 std::mutex g_cache_mtx;
@@ -169,7 +253,9 @@ std::map<std::string, std::vector<char> > g_cubin_cache;
 char* fs_jit_source(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
                     const int* rowptr, const int* col, const double* val)
 {
-  const std::string s = emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
+  const char* env = getenv("LIBXSMM_B200_FSSPMDM_JIT");
+  const std::string s = (env && 'n' == *env) ? emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val)
+                                             : emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
   char* out = (char*)malloc(s.size() + 1);
   if (out) memcpy(out, s.c_str(), s.size() + 1);
   return out;
@@ -181,35 +267,45 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
   const char* env = getenv("LIBXSMM_B200_FSSPMDM_JIT");
   if (env && '0' == *env) return 0;
   if (!supported(is_double, M, K, rowptr, col)) return 0;
-  Nvrtc* rt = nvrtc();
-  if (0 == rt) { set_error(-2, "fsspmdm: NVRTC (libnvrtc.so.12) not found; using the generic kernel"); return 0; }
-  const std::string src = emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
-  std::vector<char> cubin;
-  {
-    std::lock_guard<std::mutex> lock(g_cache_mtx);
-    std::map<std::string, std::vector<char> >::const_iterator it = g_cubin_cache.find(src);
-    if (it != g_cubin_cache.end()) cubin = it->second;
+  // default: PTX text assembled by the driver (fast); LIBXSMM_B200_FSSPMDM_JIT=nvrtc: CUDA C++ through NVRTC
+  const bool use_nvrtc = (env && 'n' == *env);
+  std::vector<char> cubin;     // cubin (NVRTC) or NUL-terminated PTX text
+  if (!use_nvrtc) {
+    const std::string ptx = emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
+    cubin.assign(ptx.begin(), ptx.end());
+    cubin.push_back(0);
   }
-  if (cubin.empty()) {
-    nvrtcProgram prog = 0;
-    if (NVRTC_SUCCESS != rt->CreateProgram(&prog, src.c_str(), "fs_baked.cu", 0, 0, 0)) { set_error(-3, "nvrtcCreateProgram failed"); return 0; }
-    const char* opts[] = { "--gpu-architecture=sm_100a", "-lineinfo", "--fmad=false" };
-    const nvrtcResult rc = rt->CompileProgram(prog, 3, opts);
-    if (NVRTC_SUCCESS != rc) {
-      size_t n = 0;
-      std::string log;
-      if (rt->GetProgramLogSize && NVRTC_SUCCESS == rt->GetProgramLogSize(prog, &n) && n > 1) { log.resize(n); rt->GetProgramLog(prog, &log[0]); }
-      set_error(-4, "fsspmdm: NVRTC compile failed (%d): %.300s", (int)rc, log.c_str());
-      rt->DestroyProgram(&prog);
-      return 0;
+  else {
+    if (rowptr[M] > 6000) return 0;
+    Nvrtc* rt = nvrtc();
+    if (0 == rt) { set_error(-2, "fsspmdm: NVRTC (libnvrtc.so.12) not found; using the generic kernel"); return 0; }
+    const std::string src = emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
+    {
+      std::lock_guard<std::mutex> lock(g_cache_mtx);
+      std::map<std::string, std::vector<char> >::const_iterator it = g_cubin_cache.find(src);
+      if (it != g_cubin_cache.end()) cubin = it->second;
     }
-    size_t sz = 0;
-    if (NVRTC_SUCCESS != rt->GetCUBINSize(prog, &sz) || 0 == sz) { set_error(-5, "nvrtcGetCUBINSize failed"); rt->DestroyProgram(&prog); return 0; }
-    cubin.resize(sz);
-    rt->GetCUBIN(prog, cubin.data());
-    rt->DestroyProgram(&prog);
-    std::lock_guard<std::mutex> lock(g_cache_mtx);
-    g_cubin_cache[src] = cubin;
+    if (cubin.empty()) {
+      nvrtcProgram prog = 0;
+      if (NVRTC_SUCCESS != rt->CreateProgram(&prog, src.c_str(), "fs_baked.cu", 0, 0, 0)) { set_error(-3, "nvrtcCreateProgram failed"); return 0; }
+      const char* opts[] = { "--gpu-architecture=sm_100a", "-lineinfo", "--fmad=false" };
+      const nvrtcResult rc = rt->CompileProgram(prog, 3, opts);
+      if (NVRTC_SUCCESS != rc) {
+        size_t n = 0;
+        std::string log;
+        if (rt->GetProgramLogSize && NVRTC_SUCCESS == rt->GetProgramLogSize(prog, &n) && n > 1) { log.resize(n); rt->GetProgramLog(prog, &log[0]); }
+        set_error(-4, "fsspmdm: NVRTC compile failed (%d): %.300s", (int)rc, log.c_str());
+        rt->DestroyProgram(&prog);
+        return 0;
+      }
+      size_t sz = 0;
+      if (NVRTC_SUCCESS != rt->GetCUBINSize(prog, &sz) || 0 == sz) { set_error(-5, "nvrtcGetCUBINSize failed"); rt->DestroyProgram(&prog); return 0; }
+      cubin.resize(sz);
+      rt->GetCUBIN(prog, cubin.data());
+      rt->DestroyProgram(&prog);
+      std::lock_guard<std::mutex> lock(g_cache_mtx);
+      g_cubin_cache[src] = cubin;
+    }
   }
   FsJit* j = new FsJit();
   j->block = kBlock;
