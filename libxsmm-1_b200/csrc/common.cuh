@@ -35,7 +35,8 @@ struct SliceArena {
   float* values;
   uint32_t* slice_nnz;   // auxiliary: true nonzero count of every slice (the u16 row pointers wrap at 65536)
   uint16_t* tcoff;   // auxiliary (not part of the reference's slice), same indexing as colidx: where the nonzero
-                     // goes in the tensor-core branch's shared-memory A tile (xb_tc_pack)
+                     // goes in the tensor-core branch's shared-memory A tile (fp32 slices: xb_tc_pack)
+  uint32_t* tcpk;    // the same memory seen as 32-bit words (bf16 slices: xb_tc16_pack, value and position in one word)
 };
 
 // Tensor-core branch (spmdm_compute_tc.cu): A is rebuilt per k-block as two K-halves (k < 64, k >= 64), each
@@ -48,6 +49,17 @@ __host__ __device__ __forceinline__ uint16_t xb_tc_pack(int r, int k)
   const int row = r & 127, kk = k & 31;
   const uint32_t off = (uint32_t)(((k >> 5) & 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) & 7) << 4) + ((kk & 3) << 2));
   return (uint16_t)((off >> 2) | ((uint32_t)(k >> 6) << 15));
+}
+#endif
+
+// bf16 slices (spmdm_compute_tc16*.cu): the A tile is [128 rows x 64 k] bf16 per K-half, K-major SWIZZLE_128B
+// (16 KiB).  One word per nonzero: bf16 value << 16 | half << 15 | (byte offset inside the half) >> 1.
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__ uint32_t xb_tc16_pack(int r, int k, uint32_t f32_bits)
+{
+  const uint32_t row = (uint32_t)r & 127u, kk = (uint32_t)k & 63u;
+  const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((((kk >> 3) ^ row) & 7u) << 4) + ((kk & 7u) << 1);
+  return (f32_bits & 0xFFFF0000u) | ((((uint32_t)k >> 6) & 1u) << 15) | (off >> 1);
 }
 #endif
 
@@ -109,6 +121,7 @@ struct ComputeArgs {
   // selected kernel does the work (dense <=> total nnz >= tc_min_nnz).  tc_twin = 0: no twin, always run.
   int tc_twin;
   unsigned long long tc_min_nnz;
+  int dbg;          // developer experiments (LIBXSMM_B200_TC16_DBG)
   int tc_hint;      // host's lagging density hint: 0 unknown / borderline (enqueue both twins), 1 clearly sparse (CUDA cores only), 2 clearly dense (tensor cores only)
 };
 
@@ -134,7 +147,7 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tma(const ComputeArgs& args, bool partial, cudaStream_t stream);
 bool launch_compute_tc(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tc16(const ComputeArgs& args, cudaStream_t stream);   // tcgen05 branch for bf16 inputs
-bool launch_compute_mma(const ComputeArgs& args, cudaStream_t stream);   // warp-MMA gather kernel for bf16 slices; false: does not qualify   // tcgen05 dense branch; false: does not qualify   // false: panel does not qualify
+bool launch_compute_tc16p(const ComputeArgs& args, cudaStream_t stream);  // CTA-pair (cta_group::2) persistent form of it
 
 // ---- FSSPMDM --------------------------------------------------------------------------------
 struct FsOperator;   // fsspmdm.cu

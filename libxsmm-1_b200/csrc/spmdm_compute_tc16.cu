@@ -88,7 +88,7 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
     // ---------------- TMA producer ----------------
     if (0 == lane) {
       tma_prefetch_desc(&tmB);
-      for (int t = 0; t < nsteps; ++t) {
+      for (int t = 0; t < ((p.dbg & 8) ? T16_NB : nsteps); ++t) {
         const int s = t % T16_NB, f = t / T16_NB;
         if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
         mbar_arrive_expect_tx(&b_full[s], T16_B_STAGE);
@@ -109,8 +109,8 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
       const uint32_t b_kstep = p.transb ? 32u : 2048u, b_lbo = p.transb ? 16u : (uint32_t)(T16_KH * 128), b_sbo = 1024u;
       for (int t = 0; t < nsteps; ++t) {
         const int ab = t % T16_NA, s = t % T16_NB;
-        mbar_wait(&a_ready[ab], (t / T16_NA) & 1);
-        mbar_wait(&b_full[s], (t / T16_NB) & 1);
+        if (!(p.dbg & 16)) mbar_wait(&a_ready[ab], (t / T16_NA) & 1);
+        if (!(p.dbg & 8) || t < T16_NB) mbar_wait(&b_full[s], (t / T16_NB) & 1);
         tc_fence_after();
         const uint32_t a_base = sbase + T16_SMEM_A + ab * T16_A_HALF;
         const uint32_t b_base = sbase + T16_SMEM_B + s * T16_B_STAGE;
@@ -130,16 +130,11 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
     // ---------------- workers: densify A, epilogue ----------------
     const int wt = tid - 64;                      // 0..127
     const size_t cap = (size_t)g.bm * g.bk;
-    // packed nonzero: bf16 value << 16 | half << 15 | (byte offset inside the 16 KiB half) >> 1
+    // packed nonzero (written by the slicing kernel, xb_tc16_pack): bf16 value << 16 | half << 15 | (byte offset inside the 16 KiB half) >> 1
     uint32_t pk[T16_NQ];
-    auto pack = [&](uint32_t col, uint32_t brow, float v) -> uint32_t {
-      const uint32_t row = (brow - (uint32_t)ml0) & 127u, kk = col & 63u;
-      const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((((kk >> 3) ^ row) & 7u) << 4) + ((kk & 7u) << 1);
-      return (__float_as_uint(v) & 0xFFFF0000u) | ((col >> 6) << 15) | (off >> 1);
-    };
-    // fetch() only ISSUES the loads of the next k-block's nonzeros (raw registers, no use): they are packed a
+    // fetch() only ISSUES the loads of the next k-block's nonzeros (raw registers, no use): they are consumed a
     // step later, so the global-memory latency never stalls a worker
-    uint32_t rc[T16_NQ], rr[T16_NQ]; float rv[T16_NQ];
+    uint32_t rw[T16_NQ];
     int first = 0, last = 0, nfirst = 0, nlast = 0;
     int pf = 0, pl = 0, pm = 0;        // raw row pointers of the k-block after next (first, end, last row's start)
     auto fetch_ptrs = [&](int kbf) {   // issue only
@@ -147,17 +142,14 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
       pf = (int)__ldg(ro); pl = (int)__ldg(ro + tile_rows); pm = (int)__ldg(ro + tile_rows - 1);
     };
     auto fetch = [&](int kbf) {        // uses the pointers issued one k-block earlier; issues the nonzero loads
-      const int sidx = kbf * g.mb + mbi;
-      const uint16_t* co = p.sl.colidx + sidx * cap;
-      const uint16_t* ri = p.sl.tcoff + sidx * cap;      // bf16 slices: block-local row of every nonzero
-      const float* va = p.sl.values + sidx * cap;
+      const uint32_t* pw = p.sl.tcpk + (size_t)(kbf * g.mb + mbi) * cap;
       nfirst = pf;
       nlast = (pl < pf) ? pm : pl;     // wrapped u16 counter of a full slice: last row reads as empty
 #pragma unroll
       for (int i = 0; i < T16_NQ; ++i) {
         const int q = nfirst + wt + i * T16_WT;
-        rc[i] = 0; rr[i] = 0; rv[i] = 0.f;
-        if (q < nlast) { rc[i] = __ldg(co + q); rr[i] = __ldg(ri + q); rv[i] = __ldg(va + q); }
+        rw[i] = 0;
+        if (q < nlast) rw[i] = __ldg(pw + q);
       }
       if (kbf + 1 < g.kb) fetch_ptrs(kbf + 1);
     };
@@ -167,32 +159,29 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
       const int kb = t >> 1, h = t & 1, ab = t % T16_NA;
       if (t >= T16_NA) mbar_wait(&a_free[ab], ((t / T16_NA) - 1) & 1);
       unsigned char* abuf = smem + T16_SMEM_A + ab * T16_A_HALF;
-      {
+      if (!(p.dbg & 1)) {
         uint4* z = (uint4*)abuf;
 #pragma unroll
         for (int i = 0; i < T16_A_HALF / 16 / T16_WT; ++i) z[wt + i * T16_WT] = make_uint4(0, 0, 0, 0);
+        asm volatile("bar.sync 1, %0;\n" ::"n"(T16_WT) : "memory");   // zero-fill complete before the scatter
       }
-      asm volatile("bar.sync 1, %0;\n" ::"n"(T16_WT) : "memory");   // zero-fill complete before the scatter
       if (0 == h) {   // the raw registers fetched a step ago become this k-block's packed nonzeros
         first = nfirst; last = nlast;
 #pragma unroll
-        for (int i = 0; i < T16_NQ; ++i) pk[i] = pack(rc[i], rr[i], rv[i]);
+        for (int i = 0; i < T16_NQ; ++i) pk[i] = rw[i];
         if (kb + 1 < g.kb) fetch(kb + 1);   // the raw registers are free again: two steps of cover for the next k-block's loads
       }
       auto put = [&](uint32_t w) {
-        if ((int)((w >> 15) & 1u) == h) *(uint16_t*)(abuf + ((w & 0x7FFFu) << 1)) = (uint16_t)(w >> 16);
+        if ((int)((w >> 15) & 1u) == h && !(p.dbg & 2)) *(uint16_t*)(abuf + ((w & 0x7FFFu) << 1)) = (uint16_t)(w >> 16);
       };
 #pragma unroll
       for (int i = 0; i < T16_NQ; ++i) {
         if (first + wt + i * T16_WT < last) put(pk[i]);
       }
       if (first + T16_NQ * T16_WT < last) {   // denser than T16_NQ*T16_WT nonzeros per tile: the rest straight from memory
-        const int sidx = kb * g.mb + mbi;
-        const uint16_t* co = p.sl.colidx + sidx * cap;
-        const uint16_t* ri = p.sl.tcoff + sidx * cap;
-        const float* va = p.sl.values + sidx * cap;
+        const uint32_t* pw = p.sl.tcpk + (size_t)(kb * g.mb + mbi) * cap;
 #pragma unroll 4
-        for (int q = first + wt + T16_NQ * T16_WT; q < last; q += T16_WT) put(pack(__ldg(co + q), __ldg(ri + q), __ldg(va + q)));
+        for (int q = first + wt + T16_NQ * T16_WT; q < last; q += T16_WT) put(__ldg(pw + q));
       }
       fence_proxy_async();
       __syncwarp();
@@ -208,7 +197,7 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
     for (int cb = 0; cb < T16_BN; cb += 32) {
       uint32_t v[32];
       tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, v);
-      if (row < tile_rows) {
+      if (row < tile_rows && !(p.dbg & 4)) {
         if (p.transc) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -271,7 +260,8 @@ bool launch_compute_tc16(const ComputeArgs& a, cudaStream_t stream)
   const int tiles_per_mb = (a.g.bm + T16_BM - 1) / T16_BM;
   const dim3 grid((unsigned)((a.ncols + T16_BN - 1) / T16_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
-  spmdm_compute_tc16_kernel<<<grid, T16_THREADS, T16_SMEM_BYTES, stream>>>(map, a);
+  ComputeArgs a2 = a; { const char* e = getenv("LIBXSMM_B200_TC16_DBG"); a2.dbg = e ? atoi(e) : 0; }
+  spmdm_compute_tc16_kernel<<<grid, T16_THREADS, T16_SMEM_BYTES, stream>>>(map, a2);
   XB_CUDA(cudaGetLastError());
   return true;
 }

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
   uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
   float* va = p.out.values + (size_t)s * g.bm * g.bk;
   uint16_t* ri = p.out.tcoff + (size_t)s * g.bm * g.bk;
+  uint32_t* rk = p.out.tcpk + (size_t)s * g.bm * g.bk;
   const uint32_t lt = (1u << lane) - 1u;
   for (int r = warp; r < rcount; r += K1_WARPS) {
     uint32_t pos = base + row_off[r];
@@ -167,7 +168,10 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
         const uint32_t q = pos + __popc(bal & lt);
         co[q] = (uint16_t)k;
         va[q] = v;
-        if (p.write_aux) ri[q] = p.is_bf16 ? (uint16_t)(r0 + r) : xb_tc_pack(r0 + r, k);
+        if (p.write_aux) {
+          if (p.is_bf16) rk[q] = xb_tc16_pack(r0 + r, k, __float_as_uint(v));
+          else ri[q] = xb_tc_pack(r0 + r, k);
+        }
       }
       pos += __popc(bal);
     }
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
   uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
   float* va = p.out.values + (size_t)s * g.bm * g.bk;
   uint16_t* ri = p.out.tcoff + (size_t)s * g.bm * g.bk;
+  uint32_t* rk = p.out.tcpk + (size_t)s * g.bm * g.bk;
   const uint32_t lt = (1u << lane) - 1u;
   const int k = lane * 4;
   const bool aux = (0 != p.write_aux);
@@ -332,12 +337,11 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
       if (0 == lane) ro[row_lo + j] = (uint16_t)pos;
       if (m) {   // few lanes hold nonzeros in the sparse regime: one divergent region per row
         const int rr = row_lo + j;
-        // auxiliary per-nonzero word: fp32 slices -> position in the tcgen05 branch's A tile; bf16 slices -> the
-        // block-local row (the warp-MMA kernel gathers nonzeros of 16 rows into one instruction)
-        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); if (aux) ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k); ++q; }
-        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); if (aux) ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 1); ++q; }
-        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); if (aux) ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 2); ++q; }
-        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); if (aux) ri[q] = BF16 ? (uint16_t)rr : xb_tc_pack(rr, k + 3); }
+        // auxiliary per-nonzero word: position in the tcgen05 branch's A tile (bf16 slices: value and position)
+        if (m & 1u) { co[q] = (uint16_t)k; va[q] = __uint_as_float(v.x); if (aux) { if (BF16) rk[q] = xb_tc16_pack(rr, k, v.x); else ri[q] = xb_tc_pack(rr, k); } ++q; }
+        if (m & 2u) { co[q] = (uint16_t)(k + 1); va[q] = __uint_as_float(v.y); if (aux) { if (BF16) rk[q] = xb_tc16_pack(rr, k + 1, v.y); else ri[q] = xb_tc_pack(rr, k + 1); } ++q; }
+        if (m & 4u) { co[q] = (uint16_t)(k + 2); va[q] = __uint_as_float(v.z); if (aux) { if (BF16) rk[q] = xb_tc16_pack(rr, k + 2, v.z); else ri[q] = xb_tc_pack(rr, k + 2); } ++q; }
+        if (m & 8u) { co[q] = (uint16_t)(k + 3); va[q] = __uint_as_float(v.w); if (aux) { if (BF16) rk[q] = xb_tc16_pack(rr, k + 3, v.w); else ri[q] = xb_tc_pack(rr, k + 3); } }
       }
       pos += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     }
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
   uint16_t* ro = p.out.rowidx + (size_t)s * (g.bm + 1);
   uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
   float* va = p.out.values + (size_t)s * g.bm * g.bk;
-  uint16_t* ri = p.out.tcoff + (size_t)s * g.bm * g.bk;
+  uint32_t* rk = p.out.tcpk + (size_t)s * g.bm * g.bk;
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t mymask = half ? 0xFFFF0000u : 0x0000FFFFu;
   const bool aux = (0 != p.write_aux);
@@ -448,8 +452,9 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
         for (int e = 0; e < 8; ++e) {
           if (m & (1u << e)) {
             co[q] = (uint16_t)(hl * 8 + e);
-            va[q] = __uint_as_float((e & 1) ? (v[e >> 1] & 0xFFFF0000u) : (v[e >> 1] << 16));
-            if (aux) ri[q] = (uint16_t)r;
+            const uint32_t vb = (e & 1) ? (v[e >> 1] & 0xFFFF0000u) : (v[e >> 1] << 16);
+            va[q] = __uint_as_float(vb);
+            if (aux) rk[q] = xb_tc16_pack(r, hl * 8 + e, vb);
             ++q;
           }
         }
@@ -822,6 +827,15 @@ static int tc_mode()
   return ('0' == *e) ? 0 : (('1' == *e) ? 1 : 2);
 }
 
+// bf16 tensor-core branch: the CTA-pair kernel (K4p), the single-CTA kernel (K4h) when LIBXSMM_B200_TC16_PAIR=0
+static bool launch_tc_bf16(const ComputeArgs& a, cudaStream_t stream)
+{
+  static int pair = -1;
+  if (pair < 0) { const char* e = getenv("LIBXSMM_B200_TC16_PAIR"); pair = (e && '0' == *e) ? 0 : 1; }
+  if (pair && launch_compute_tc16p(a, stream)) return true;
+  return launch_compute_tc16(a, stream);
+}
+
 static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
 {
   if (launch_compute_tma(a, partial, stream)) return;   // TMA fast path (spmdm_compute_tma.cu)
@@ -838,12 +852,6 @@ static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
 void launch_compute(const ComputeArgs& args, cudaStream_t stream)
 {
   if (args.ncols <= 0 || args.mb_count <= 0) return;
-  // bf16 inputs: the warp-level tensor-core gather kernel (opt-in experiment, slower than the CUDA-core kernel
-  // on B200: see spmdm_compute_mma.cu) covers all columns in one launch
-  if (args.is_bf16 && 0 == args.tc_twin) {
-    const char* e = getenv("LIBXSMM_B200_SPMDM_MMA");
-    if (e && '1' == *e && launch_compute_mma(args, stream)) return;
-  }
   // Tensor-core twin (fp32, N/N/N, aligned panels): the dense kernel is enqueued next to the sparse ones and
   // every CTA of both reads the slices' nonzero counts; only the selected side does the work.
   ComputeArgs targs = args;
@@ -851,13 +859,13 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
   if (2 == mode && 1 == args.tc_hint) mode = 0;      // clearly sparse last time: do not even enqueue the dense twin
   targs.tc_twin = 0;
   if (2 == mode && 2 == args.tc_hint) {              // clearly dense last time: the tensor-core kernel alone (correct for any density)
-    if (args.is_bf16 ? launch_compute_tc16(targs, stream) : launch_compute_tc(targs, stream)) return;
+    if (args.is_bf16 ? launch_tc_bf16(targs, stream) : launch_compute_tc(targs, stream)) return;
   }
   if (mode > 0) {
     targs.tc_twin = 1;
     // crossover measured on B200: fp32 (3xTF32, three MMAs per k-step) 7 %; bf16 (one MMA) ~1 %, switched at 1.5 %
     targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)((args.is_bf16 ? 0.015 : 0.07) * (double)args.g.m * (double)args.g.k);
-    if (!(args.is_bf16 ? launch_compute_tc16(targs, stream) : launch_compute_tc(targs, stream))) targs.tc_twin = 0;
+    if (!(args.is_bf16 ? launch_tc_bf16(targs, stream) : launch_compute_tc(targs, stream))) targs.tc_twin = 0;
     else if (1 == mode) return;   // forced: nothing for the sparse kernels to do
   }
   const ComputeArgs& args2 = targs;

@@ -18,7 +18,6 @@ def cuda_core_path(monkeypatch):
     reference's rounding sequence).  The tensor-core branch that takes over dense fp32 problems is covered,
     against the relative-error contract, by tests/test_spmdm_tc_gpu.py."""
     monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", "0")
-    monkeypatch.setenv("LIBXSMM_B200_SPMDM_MMA", "0")
 
 
 RTOL_F32 = 1e-5
