@@ -63,6 +63,8 @@ LIBXSMM_API void libxsmm_b200_clear_error(void);
 
 /* Number of kernels this library has launched so far in this process. */
 LIBXSMM_API unsigned long long libxsmm_b200_launch_count(void);
+/* name of the kernel the last spmdm compute / fsspmdm execute call enqueued for the bulk of its work (static string) */
+LIBXSMM_API const char* libxsmm_b200_last_compute_kernel(void);
 
 /* Page-locked host memory for callers that want full PCIe speed on the host-pointer paths. */
 LIBXSMM_API void* libxsmm_b200_host_alloc(size_t bytes);

@@ -37,7 +37,7 @@ ADDED_SYMBOLS = [
     "libxsmm_dfsspmdm_is_sparse", "libxsmm_sfsspmdm_is_sparse",
     "libxsmm_dfsspmdm_is_baked", "libxsmm_sfsspmdm_is_baked", "libxsmm_sfsspmdm_is_tensor_core",
     "libxsmm_b200_last_error", "libxsmm_b200_last_error_string", "libxsmm_b200_clear_error",
-    "libxsmm_b200_launch_count",
+    "libxsmm_b200_launch_count", "libxsmm_b200_last_compute_kernel",
     "libxsmm_b200_host_alloc", "libxsmm_b200_host_free",
     "libxsmm_b200_device_alloc", "libxsmm_b200_device_free",
     "libxsmm_b200_memcpy_h2d", "libxsmm_b200_memcpy_d2h", "libxsmm_b200_memset",
@@ -125,6 +125,7 @@ def load():
     L.libxsmm_sfsspmdm_is_tensor_core.argtypes = [vp]
     L.libxsmm_b200_last_error_string.restype = ctypes.c_char_p
     L.libxsmm_b200_launch_count.restype = ctypes.c_ulonglong
+    L.libxsmm_b200_last_compute_kernel.restype = ctypes.c_char_p
     L.libxsmm_b200_host_alloc.argtypes = [ctypes.c_size_t]
     L.libxsmm_b200_host_alloc.restype = vp
     L.libxsmm_b200_host_free.argtypes = [vp]
@@ -188,6 +189,10 @@ def check():
 
 def launch_count():
     return int(load().libxsmm_b200_launch_count())
+
+
+def last_compute_kernel():
+    return load().libxsmm_b200_last_compute_kernel().decode()
 
 
 def synchronize():

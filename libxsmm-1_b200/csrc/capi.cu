@@ -44,6 +44,8 @@ void set_error(int code, const char* fmt, ...)
 }
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+static std::atomic<const char*> g_last_compute("");
+void note_compute_kernel(const char* name) { g_last_compute.store(name, std::memory_order_relaxed); }
 
 // ---- SPMDM context -----------------------------------------------------------------------------------
 constexpr int kExecPanels = 8;   // column panels of the pipelined host path (libxsmm_spmdm_exec_host)
@@ -74,12 +76,12 @@ struct SpmdmCtx {
 };
 
 // 0 unknown (first call), 1 sparse, 2 dense according to the last completed slicing pass (thresholds of
-// launch_compute: 7 % fp32, 1.5 % bf16)
+// launch_compute: kTcDensityF32 / kTcDensityBf16)
 static int density_hint(const SpmdmCtx* c, int is_bf16)
 {
   const unsigned long long n = c->h_nnz ? *(volatile unsigned long long*)c->h_nnz : ~0ull;
   if (~0ull == n) return 0;
-  const double thr = (is_bf16 ? 0.015 : 0.07) * (double)c->g.m * (double)c->g.k;
+  const double thr = (is_bf16 ? xb::kTcDensityBf16 : xb::kTcDensityF32) * (double)c->g.m * (double)c->g.k;
   return ((double)n < thr) ? 1 : 2;   // either way the result is correct; a wrong guess only costs speed for one call
 }
 
@@ -512,6 +514,10 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
       XB_CUDA(cudaEventCreateWithFlags(&c->xup[i], cudaEventDisableTiming));
     }
   }
+  // LIBXSMM_B200_EXEC_TRACE=1: per-step timeline (developer aid; timing events on all three streams)
+  static const bool trace = [] { const char* e = getenv("LIBXSMM_B200_EXEC_TRACE"); return e && '1' == *e; }();
+  std::vector<cudaEvent_t> tev;
+  if (trace) { tev.resize((size_t)(3 * nd + 1)); for (size_t i = 0; i < tev.size(); ++i) XB_CUDA(cudaEventCreate(&tev[i])); XB_CUDA(cudaEventRecord(tev[3 * nd], c->xs[0])); }
   int write_aux = 1; bool first_block = true;
   // a rectangle of C: row blocks [r0, r0 + rc) x columns [n0, n0 + w)
   auto rect = [&](int r0, int rc, int n0, int w, int* m0, int* rows) {
@@ -554,14 +560,16 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
     }
     if (d < np) {
       char* db = (char*)c->d_b; const char* hb = (const char*)b;
-      if (tb) XB_CUDA(cudaMemcpyAsync(db + (size_t)col_n0 * g.k * esz, hb + (size_t)col_n0 * g.k * esz, (size_t)col_w * g.k * esz, cudaMemcpyHostToDevice, c->xs[0]));
-      else XB_CUDA(cudaMemcpy2DAsync(db + (size_t)col_n0 * esz, (size_t)g.n * esz, hb + (size_t)col_n0 * esz, (size_t)g.n * esz, (size_t)col_w * esz, g.k, cudaMemcpyHostToDevice, c->xs[0]));
+      cudaStream_t sb = c->xs[0];
+      if (tb) XB_CUDA(cudaMemcpyAsync(db + (size_t)col_n0 * g.k * esz, hb + (size_t)col_n0 * g.k * esz, (size_t)col_w * g.k * esz, cudaMemcpyHostToDevice, sb));
+      else XB_CUDA(cudaMemcpy2DAsync(db + (size_t)col_n0 * esz, (size_t)g.n * esz, hb + (size_t)col_n0 * esz, (size_t)g.n * esz, (size_t)col_w * esz, g.k, cudaMemcpyHostToDevice, sb));
     }
     if (0.f != beta_f) {   // beta != 0: the C rectangles go up before they are needed
       if (d < g.mb) copy_rect(d, 1, 0, row_cols, true);
       if (d < np) copy_rect(0, col_rows, col_n0, col_w, true);
     }
     XB_CUDA(cudaEventRecord(c->xup[d], c->xs[0]));
+    if (trace) XB_CUDA(cudaEventRecord(tev[3 * d], c->xs[0]));
     // ---- kernels of step d: at most one slicing launch and two compute launches ----
     XB_CUDA(cudaStreamWaitEvent(c->xs[1], c->xup[d], 0));
     if (d < g.mb) {
@@ -577,13 +585,23 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
     }
     if (d < np) compute_rect(0, col_rows, col_n0, col_w);
     XB_CUDA(cudaEventRecord(c->xdone[d], c->xs[1]));
+    if (trace) XB_CUDA(cudaEventRecord(tev[3 * d + 1], c->xs[1]));
     // ---- downloads of step d ----
     XB_CUDA(cudaStreamWaitEvent(c->xs[2], c->xdone[d], 0));
     if (d < g.mb) copy_rect(d, 1, 0, row_cols, false);
     if (d < np) copy_rect(0, col_rows, col_n0, col_w, false);
+    if (trace) XB_CUDA(cudaEventRecord(tev[3 * d + 2], c->xs[2]));
   }
   XB_CUDA(cudaStreamSynchronize(c->xs[2]));
   XB_CUDA(cudaStreamSynchronize(c->xs[0]));
+  if (trace) {
+    for (int d = 0; d < nd; ++d) {
+      float t[3] = { 0, 0, 0 };
+      for (int i = 0; i < 3; ++i) (void)cudaEventElapsedTime(&t[i], tev[3 * nd], tev[3 * d + i]);
+      fprintf(stderr, "exec_host step %2d: uploaded %7.3f ms  computed %7.3f ms  downloaded %7.3f ms\n", d, t[0], t[1], t[2]);
+    }
+    for (size_t i = 0; i < tev.size(); ++i) cudaEventDestroy(tev[i]);
+  }
 }
 
 // =====================================================================================================
@@ -682,6 +700,7 @@ int libxsmm_b200_last_error(void) { std::lock_guard<std::mutex> lock(g_err_mtx);
 const char* libxsmm_b200_last_error_string(void) { return g_err_msg; }
 void libxsmm_b200_clear_error(void) { std::lock_guard<std::mutex> lock(g_err_mtx); g_err_code = 0; g_err_msg[0] = 0; }
 unsigned long long libxsmm_b200_launch_count(void) { return g_launches.load(); }
+const char* libxsmm_b200_last_compute_kernel(void) { return g_last_compute.load(); }
 
 void* libxsmm_b200_host_alloc(size_t bytes)
 {

@@ -10,6 +10,7 @@ namespace xb {
 void set_error(int code, const char* fmt, ...);
 int verbosity();
 void count_launch(int n);
+void note_compute_kernel(const char* name);   // which spmdm compute / fsspmdm kernel the last call enqueued (reported by bench.py)
 
 #define XB_CUDA(call)                                                                      \
   do {                                                                                     \
@@ -102,6 +103,11 @@ __device__ __forceinline__ void xb_publish_nnz(const SliceArgs& p, unsigned long
 
 // mode boundaries of the reference's narrow last block (compute template :72-76,372-434)
 struct ColModes { int n_full_end; int tail_from; };
+
+// Density (nnz / (M*K)) from which the tensor-core twin takes over, measured on B200: fp32 (3xTF32, three MMAs per
+// k-step) 7 %; bf16 0.5 % (the CTA-pair kernel costs ~104 us for 4096^3 at any density, the CUDA-core kernel 177 us
+// at 1 % and proportionally less below).
+constexpr double kTcDensityF32 = 0.07, kTcDensityBf16 = 0.005;
 
 struct ComputeArgs {
   SliceArena sl;

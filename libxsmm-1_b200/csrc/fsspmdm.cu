@@ -224,8 +224,9 @@ void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, 
 {
   if (0 == o || ncols <= 0) return;
   count_launch(1);
-  if (o->tc && fs_tc_launch(o->tc, dB, dC, ncols, ldb, ldc, stream)) return;
-  if (o->jit && fs_jit_launch(o->jit, dB, dC, ncols, ldb, ldc, stream)) return;
+  if (o->tc && fs_tc_launch(o->tc, dB, dC, ncols, ldb, ldc, stream)) { note_compute_kernel("fs_tc_kernel"); return; }
+  if (o->jit && fs_jit_launch(o->jit, dB, dC, ncols, ldb, ldc, stream)) { note_compute_kernel("fs_baked"); return; }
+  note_compute_kernel("fs_generic_kernel");
   FsDev d;
   d.M = o->M; d.beta_one = o->beta_one; d.skip_empty = o->sparse_branch;
   d.ldb = ldb; d.ldc = ldc; d.rowptr = o->d_rowptr; d.col = o->d_col; d.val = o->d_val;

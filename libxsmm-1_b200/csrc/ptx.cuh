@@ -29,9 +29,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
   uint32_t ok;
   asm volatile(
     "{\n\t.reg .pred p;\n\t"
-    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
     "selp.u32 %0, 1, 0, p;\n\t}\n"
-    : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680) : "memory");   // suspend-time hint: the thread sleeps in the
+  // barrier unit until the phase completes instead of polling (a polling loop competes with the memory instructions of the working warps)
   return 0 != ok;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)

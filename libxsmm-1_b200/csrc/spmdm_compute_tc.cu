@@ -317,6 +317,7 @@ bool launch_compute_tc(const ComputeArgs& a, cudaStream_t stream)
   const int tiles_per_mb = (a.g.bm + TC_BM - 1) / TC_BM;
   const dim3 grid((unsigned)((a.ncols + TC_BN - 1) / TC_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
+  note_compute_kernel("spmdm_compute_tc_kernel");
   spmdm_compute_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
   XB_CUDA(cudaGetLastError());
   return true;

@@ -260,6 +260,7 @@ bool launch_compute_tc16(const ComputeArgs& a, cudaStream_t stream)
   const int tiles_per_mb = (a.g.bm + T16_BM - 1) / T16_BM;
   const dim3 grid((unsigned)((a.ncols + T16_BN - 1) / T16_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
+  note_compute_kernel("spmdm_compute_tc16_kernel");
   ComputeArgs a2 = a; { const char* e = getenv("LIBXSMM_B200_TC16_DBG"); a2.dbg = e ? atoi(e) : 0; }
   spmdm_compute_tc16_kernel<<<grid, T16_THREADS, T16_SMEM_BYTES, stream>>>(map, a2);
   XB_CUDA(cudaGetLastError());

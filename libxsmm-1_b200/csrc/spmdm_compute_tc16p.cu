@@ -112,6 +112,7 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   uint64_t* acc_empty = acc_full + 2;       // [2]  leader: the epilogue warps of both CTAs drained the accumulator
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
+  unsigned long long gt0; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt0)); const long long ck0 = clock64();
   const Geom& g = p.g;
   if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // uniform over the grid
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -136,8 +137,15 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
     return t;
   };
 
-  // A buffers start out zero (they are only ever patched), history empty
-  for (int i = tid; i < (P_NA * P_A_BUF) / 16; i += P_THREADS) ((uint4*)(smem + P_SMEM_A))[i] = make_uint4(0, 0, 0, 0);
+  // Work list of this pair: q full tiles, then -- when the remaining tiles are at most half as many as the pairs --
+  // one HALF tile (128 of the 256 columns), so that the last round costs half a tile instead of a whole one
+  // (4096^3 on 74 pairs: 256 tiles = 3 rounds + 34 tiles -> 68 half tiles; makespan 3.5 instead of 4 tiles).
+  const int wq = total / npairs, wrem = total - wq * npairs;
+  const bool wsplit = !p.transb && wrem > 0 && 2 * wrem <= npairs;
+  const int nwork = wq + ((wsplit ? (pair < 2 * wrem) : (pair < wrem)) ? 1 : 0);
+  auto work_idx = [&](int i) -> int { return i < wq ? pair + i * npairs : wq * npairs + (wsplit ? (pair >> 1) : pair); };
+  auto work_half = [&](int i) -> int { return (i < wq || !wsplit) ? -1 : (pair & 1); };
+
   if (0 == tid) {
 #pragma unroll
     for (int i = 0; i < P_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_free[i], 1); }
@@ -151,12 +159,12 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
   }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  if (p.dbg & 64 && 0 == pair && 0 == tid) printf("rank %u prologue %lld clk\n", rank, clock64() - ck0);
 
   if (0 == warp) {
     // ---------------- TMA producer: this CTA's 128 columns of every B stage ----------------
@@ -164,18 +172,19 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       tma_prefetch_desc(&tmB);
       uint32_t gs = 0;
       long long w_prod = 0; const long long t_start = clock64();
-      for (int idx = pair; idx < total; idx += npairs) {
-        const int n0 = (idx / pair_m) * P_BN + (int)rank * P_BNH;
+      for (int wi = 0; wi < nwork; ++wi) {
+        const int idx = work_idx(wi), half = work_half(wi);
+        const int n0 = (idx / pair_m) * P_BN + (half < 0 ? (int)rank * P_BNH : half * P_BNH + (int)rank * (P_BNH / 2));
         for (int t = 0; t < 2 * nkb; ++t, ++gs) {
           const uint32_t s = gs % P_NB, f = gs / P_NB;
           if (f > 0) { const long long c0 = clock64(); mbar_wait(&b_free[s], (f - 1) & 1); w_prod += clock64() - c0; }
-          if (0 == rank) mbar_arrive_expect_tx(&b_full[s], 2 * P_B_STAGE);
+          if (0 == rank) mbar_arrive_expect_tx(&b_full[s], half < 0 ? 2 * P_B_STAGE : P_B_STAGE);
           const uint32_t lbar = map_to_cta(&b_full[s], 0);
           unsigned char* dst = smem + P_SMEM_B + s * P_B_STAGE;
           if (p.transb) tma_load_2d_pair(dst, &tmB, t * P_KH, n0, lbar);             // B stored n x k: 128 n-rows x 64 k
           else {
             tma_load_2d_pair(dst, &tmB, n0, t * P_KH, lbar);                         // 64 k-rows x 64 columns
-            tma_load_2d_pair(dst + P_KH * 128, &tmB, n0 + 64, t * P_KH, lbar);
+            if (half < 0) tma_load_2d_pair(dst + P_KH * 128, &tmB, n0 + 64, t * P_KH, lbar);
           }
         }
       }
@@ -190,8 +199,10 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       const uint32_t b_kstep = p.transb ? 32u : 2048u, b_lbo = p.transb ? 16u : (uint32_t)(P_KH * 128), b_sbo = 1024u;
       uint32_t gs = 0, gk = 0, it = 0;
       long long w_a = 0, w_b = 0, w_e = 0; const long long t_start = clock64();
-      for (int idx = pair; idx < total; idx += npairs, ++it) {
+      for (int wi = 0; wi < nwork; ++wi, ++it) {
         const uint32_t acc = it & 1;
+        // a half tile is the same instruction with N = 128: each CTA stages one 64-column block
+        const uint32_t idesc_w = (work_half(wi) < 0) ? idesc : ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(P_BNH >> 3) << 17));
         if (it >= 2) { const long long c0 = clock64(); mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1); w_e += clock64() - c0; }
         tc_fence_after();
         const uint32_t tacc = tmem_d + acc * P_BN;
@@ -209,7 +220,7 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t da = tc_smem_desc(a_base + ks * 32, 16, 1024, 2);
               const uint64_t db = tc_smem_desc(b_base + ks * b_kstep, b_lbo, b_sbo, 2);
-              tc_mma_bf16_pair(tacc, da, db, idesc, (kbi > 0 || h > 0 || ks > 0) ? 1u : 0u);
+              tc_mma_bf16_pair(tacc, da, db, idesc_w, (kbi > 0 || h > 0 || ks > 0) ? 1u : 0u);
             }
             tc_commit_pair(&b_free[s]);
           }
@@ -235,12 +246,12 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
     // Cursor over this group's k-blocks, in the order the tensor core consumes them.  Row pointers are loaded
     // four group-steps ahead, the nonzeros two (raw registers, not touched until the step that uses them): no
     // global-memory latency sits between a buffer being released and being handed back.
-    int c_idx = pair, c_kb = grp, c_rows = 0, c_sidx = 0;
+    int c_wi = 0, c_kb = grp, c_rows = 0, c_sidx = 0;
     const uint16_t* c_ro = p.sl.rowidx;
     auto seat = [&]() {                // (idx, kb) -> pointers; the divisions run once per tile
       c_rows = 0; c_ro = p.sl.rowidx; c_sidx = 0;
-      if (c_idx < total) {
-        const PairTile t = tile_of(c_idx);
+      if (c_wi < nwork) {
+        const PairTile t = tile_of(work_idx(c_wi));
         c_sidx = c_kb * g.mb + t.mbi;
         c_ro = p.sl.rowidx + (size_t)c_sidx * (g.bm + 1) + t.ml0;
         c_rows = t.rows;
@@ -250,11 +261,11 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       c_kb += P_NG;
       if (c_kb < nkb) { c_sidx += P_NG * g.mb; c_ro += (size_t)P_NG * g.mb * (g.bm + 1); }
       else {
-        while (c_kb >= nkb && c_idx < total) { c_kb -= nkb; c_idx += npairs; }
+        while (c_kb >= nkb && c_wi < nwork) { c_kb -= nkb; ++c_wi; }
         seat();
       }
     };
-    while (c_kb >= nkb && c_idx < total) { c_kb -= nkb; c_idx += npairs; }
+    while (c_kb >= nkb && c_wi < nwork) { c_kb -= nkb; ++c_wi; }
     seat();
     struct Ptr { int pf, sidx; };
     // rw: the slicing kernel's word per nonzero (xb_tc16_pack: bf16 value << 16 | half << 15 | position), hw: the
@@ -280,7 +291,7 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       fetch_ptrs(P);
     };
     long long w_f = 0, sg0 = 0, sg1 = 0, sg2 = 0, sg3 = 0, sg4 = 0; const long long t_start = clock64();
-    const uint32_t gk_end = (uint32_t)((total - pair + npairs - 1) / npairs) * (uint32_t)nkb;
+    const uint32_t gk_end = (uint32_t)nwork * (uint32_t)nkb;
     auto step = [&](uint32_t gk, Raw& R, Ptr& P) {
       if (gk >= gk_end) return;
       const uint32_t j = gk % P_NA;
@@ -333,6 +344,15 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
 #pragma unroll
     for (int i = 0; i < P_NQ; ++i) { ra.hw[i] = 0; rb.hw[i] = 0; }
     fetch_ptrs(pa); fetch_ptrs(pb);            // k-blocks 0 and 1 of this group
+    // The A buffers start out zero and are only ever patched.  Each group wipes the two buffers it owns while its
+    // first loads are in flight (and while the TMA producer is already filling the B ring).
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      uint4* z = (uint4*)(smem + P_SMEM_A + (grp + b * P_NG) * P_A_BUF);
+#pragma unroll 4
+      for (int i = 0; i < P_A_BUF / 16 / P_BM; ++i) z[wt + i * P_BM] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(P_BM) : "memory");
     fetch(ra, pa); fetch(rb, pb);              // their nonzeros; pa / pb now hold the pointers of k-blocks 2 and 3
     for (uint32_t gk = (uint32_t)grp; gk < gk_end; gk += 2 * P_NG) {
       step(gk, ra, pa);
@@ -347,14 +367,16 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
     const uint32_t lead_empty0 = map_to_cta(&acc_empty[0], 0);
     uint32_t it = 0;
     long long w_x = 0; const long long t_start = clock64();
-    for (int idx = pair; idx < total; idx += npairs, ++it) {
-      const PairTile t = tile_of(idx);
+    for (int wi = 0; wi < nwork; ++wi, ++it) {
+      PairTile t = tile_of(work_idx(wi));
+      const int half = work_half(wi), ncw = half < 0 ? P_BN : P_BNH;
+      if (half > 0) t.n0 += P_BNH;
       const uint32_t acc = it & 1;
       { const long long c0 = clock64(); mbar_wait(&acc_full[acc], (it >> 1) & 1); w_x += clock64() - c0; }
       tc_fence_after();
       const size_t crow = (size_t)(t.mbi * g.bm + t.ml0 + row - p.row_origin);
 #pragma unroll 1
-      for (int cb = 0; cb < P_BN; cb += 32) {
+      for (int cb = 0; cb < ncw; cb += 32) {
         uint32_t v[32];
         tc_ld32(tmem_d + acc * P_BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, v);
         if (row < t.rows) {
@@ -368,7 +390,9 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
               }
             }
           }
-          else {
+        }
+        if (!p.transc) {   // thread = row: 16-byte streaming stores (a lane-transposed, line-per-instruction variant measured 6 % slower)
+          if (row < t.rows) {
             float* dst = p.c + crow * p.ldc + t.n0 + cb;
 #pragma unroll
             for (int jj = 0; jj < 32; jj += 4) {
@@ -398,6 +422,7 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbg & 64 && 0 == pair && 0 == tid) { unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt1)); printf("rank %u CTA: %llu ns, %lld clk\n", rank, gt1 - gt0, clock64() - ck0); }
   cluster_sync_all();      // the peer's shared memory and barriers stay alive until every MMA and remote arrive has landed
   if (1 == warp) {
     tc_fence_after();
@@ -432,6 +457,7 @@ bool launch_compute_tc16p(const ComputeArgs& a, cudaStream_t stream)
   if (total <= 0) return true;
   const int pairs = total < pairs_max ? total : pairs_max;
   count_launch(1);
+  note_compute_kernel("spmdm_compute_tc16p_kernel");
   ComputeArgs a2 = a; { const char* e = getenv("LIBXSMM_B200_TC16_DBG"); a2.dbg = e ? atoi(e) : 0; }
   spmdm_compute_tc16p_kernel<<<dim3(2u * (unsigned)pairs), P_THREADS, P_SMEM_BYTES, stream>>>(map, a2);
   XB_CUDA(cudaGetLastError());

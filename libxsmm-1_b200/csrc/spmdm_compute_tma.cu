@@ -356,6 +356,7 @@ static bool launch_tma_variant(const ComputeArgs& a, cudaStream_t stream)
   const int tiles_per_mb = (a.g.bm + TM - 1) / TM;
   const dim3 grid((unsigned)((a.ncols + BN - 1) / BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
+  if (!PARTIAL) note_compute_kernel("spmdm_compute_tma_kernel");
   kern<<<grid, CW * 32, smem, stream>>>(map, a);
   XB_CUDA(cudaGetLastError());
   return true;

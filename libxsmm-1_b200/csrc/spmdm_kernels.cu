@@ -802,6 +802,7 @@ static void launch_compute_variant(const ComputeArgs& a, cudaStream_t stream)
   const int tiles_per_mb = (a.g.bm + TM - 1) / TM;
   const dim3 grid((unsigned)((a.ncols + BN - 1) / BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
+  if (!PARTIAL) note_compute_kernel("spmdm_compute_kernel");
   kern<<<grid, K2_THREADS, smem, stream>>>(a);
   XB_CUDA(cudaGetLastError());
 }
@@ -819,7 +820,7 @@ static cudaStream_t side_stream()
 }
 
 // LIBXSMM_B200_SPMDM_TC: "0" never use the tensor-core branch, "1" always (when the panel qualifies),
-// unset / anything else: by density -- total nnz >= 7 % (fp32) or 1.5 % (bf16) of M*K, decided on the device.
+// unset / anything else: by density -- total nnz >= 7 % (fp32) or 0.5 % (bf16) of M*K (common.cuh), decided on the device.
 static int tc_mode()
 {
   const char* e = getenv("LIBXSMM_B200_SPMDM_TC");
@@ -830,9 +831,8 @@ static int tc_mode()
 // bf16 tensor-core branch: the CTA-pair kernel (K4p), the single-CTA kernel (K4h) when LIBXSMM_B200_TC16_PAIR=0
 static bool launch_tc_bf16(const ComputeArgs& a, cudaStream_t stream)
 {
-  static int pair = -1;
-  if (pair < 0) { const char* e = getenv("LIBXSMM_B200_TC16_PAIR"); pair = (e && '0' == *e) ? 0 : 1; }
-  if (pair && launch_compute_tc16p(a, stream)) return true;
+  const char* e = getenv("LIBXSMM_B200_TC16_PAIR");
+  if (!(e && '0' == *e) && launch_compute_tc16p(a, stream)) return true;
   return launch_compute_tc16(a, stream);
 }
 
@@ -863,8 +863,7 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
   }
   if (mode > 0) {
     targs.tc_twin = 1;
-    // crossover measured on B200: fp32 (3xTF32, three MMAs per k-step) 7 %; bf16 (one MMA) ~1 %, switched at 1.5 %
-    targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)((args.is_bf16 ? 0.015 : 0.07) * (double)args.g.m * (double)args.g.k);
+    targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)((args.is_bf16 ? kTcDensityBf16 : kTcDensityF32) * (double)args.g.m * (double)args.g.k);
     if (!(args.is_bf16 ? launch_tc_bf16(targs, stream) : launch_compute_tc(targs, stream))) targs.tc_twin = 0;
     else if (1 == mode) return;   // forced: nothing for the sparse kernels to do
   }

@@ -137,3 +137,23 @@ def test_bf16_tensor_core_branch(gpu, oracle, monkeypatch, mode, M, N, K, densit
     np.testing.assert_array_equal(C_cc.view(np.uint32), OC.view(np.uint32))      # the CUDA-core path stays bit exact
     assert not np.array_equal(C.view(np.uint32), C_cc.view(np.uint32))           # ... and the tensor-core twin really ran
     gpu.check()
+
+
+@pytest.mark.parametrize("density,beta,pair", [(0.01, 0, "1"), (0.01, 1, "1"), (0.05, 0, "1"), (0.30, 0, "1"), (0.01, 0, "0")])
+def test_bf16_full_size_c2(gpu, monkeypatch, density, beta, pair):
+    """BASELINE C2 (bf16, 4096^3) on the tensor cores -- 256 pair tiles on 74 CTA pairs: three whole rounds and a
+    last round of half tiles -- against the order-preserving CUDA-core kernels on the same device buffers
+    (those are bit-exact against the oracle at the sizes the oracle can do), every output element."""
+    M = N = K = 4096
+    A, B, C0 = gpu.workloads.spmdm_inputs(M, N, K, density, dtype="bf16", seed=7)
+    monkeypatch.setenv("LIBXSMM_B200_TC16_PAIR", pair)
+    monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", "1")
+    _, _, C_tc = gpu_spmdm(gpu, A, B, C0, M, N, K, beta=beta, bf16=True)
+    monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", "0")
+    _, _, C_cc = gpu_spmdm(gpu, A, B, C0, M, N, K, beta=beta, bf16=True)
+    assert rel(C_tc, C_cc) <= 1e-5
+    assert not np.array_equal(C_tc.view(np.uint32), C_cc.view(np.uint32))
+    rows = np.arange(0, M, 37)
+    want = gpu.workloads.from_bf16_bits(A[rows]).astype(np.float64) @ gpu.workloads.from_bf16_bits(B).astype(np.float64) + beta * C0[rows]
+    assert rel(C_tc[rows], want) <= 1e-5
+    gpu.check()
