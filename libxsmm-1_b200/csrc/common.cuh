@@ -127,7 +127,6 @@ struct ComputeArgs {
   // selected kernel does the work (dense <=> total nnz >= tc_min_nnz).  tc_twin = 0: no twin, always run.
   int tc_twin;
   unsigned long long tc_min_nnz;
-  int dbg;          // developer experiments (LIBXSMM_B200_TC16_DBG)
   int tc_hint;      // host's lagging density hint: 0 unknown / borderline (enqueue both twins), 1 clearly sparse (CUDA cores only), 2 clearly dense (tensor cores only)
 };
 

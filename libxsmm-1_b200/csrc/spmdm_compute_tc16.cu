@@ -88,7 +88,7 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
     // ---------------- TMA producer ----------------
     if (0 == lane) {
       tma_prefetch_desc(&tmB);
-      for (int t = 0; t < ((p.dbg & 8) ? T16_NB : nsteps); ++t) {
+      for (int t = 0; t < nsteps; ++t) {
         const int s = t % T16_NB, f = t / T16_NB;
         if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
         mbar_arrive_expect_tx(&b_full[s], T16_B_STAGE);
@@ -109,8 +109,8 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
       const uint32_t b_kstep = p.transb ? 32u : 2048u, b_lbo = p.transb ? 16u : (uint32_t)(T16_KH * 128), b_sbo = 1024u;
       for (int t = 0; t < nsteps; ++t) {
         const int ab = t % T16_NA, s = t % T16_NB;
-        if (!(p.dbg & 16)) mbar_wait(&a_ready[ab], (t / T16_NA) & 1);
-        if (!(p.dbg & 8) || t < T16_NB) mbar_wait(&b_full[s], (t / T16_NB) & 1);
+        mbar_wait(&a_ready[ab], (t / T16_NA) & 1);
+        mbar_wait(&b_full[s], (t / T16_NB) & 1);
         tc_fence_after();
         const uint32_t a_base = sbase + T16_SMEM_A + ab * T16_A_HALF;
         const uint32_t b_base = sbase + T16_SMEM_B + s * T16_B_STAGE;
@@ -159,7 +159,7 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
       const int kb = t >> 1, h = t & 1, ab = t % T16_NA;
       if (t >= T16_NA) mbar_wait(&a_free[ab], ((t / T16_NA) - 1) & 1);
       unsigned char* abuf = smem + T16_SMEM_A + ab * T16_A_HALF;
-      if (!(p.dbg & 1)) {
+      {
         uint4* z = (uint4*)abuf;
 #pragma unroll
         for (int i = 0; i < T16_A_HALF / 16 / T16_WT; ++i) z[wt + i * T16_WT] = make_uint4(0, 0, 0, 0);
@@ -172,7 +172,7 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
         if (kb + 1 < g.kb) fetch(kb + 1);   // the raw registers are free again: two steps of cover for the next k-block's loads
       }
       auto put = [&](uint32_t w) {
-        if ((int)((w >> 15) & 1u) == h && !(p.dbg & 2)) *(uint16_t*)(abuf + ((w & 0x7FFFu) << 1)) = (uint16_t)(w >> 16);
+        if ((int)((w >> 15) & 1u) == h) *(uint16_t*)(abuf + ((w & 0x7FFFu) << 1)) = (uint16_t)(w >> 16);
       };
 #pragma unroll
       for (int i = 0; i < T16_NQ; ++i) {
@@ -197,7 +197,7 @@ spmdm_compute_tc16_kernel(const __grid_constant__ CUtensorMap tmB, const Compute
     for (int cb = 0; cb < T16_BN; cb += 32) {
       uint32_t v[32];
       tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, v);
-      if (row < tile_rows && !(p.dbg & 4)) {
+      if (row < tile_rows) {
         if (p.transc) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -261,8 +261,7 @@ bool launch_compute_tc16(const ComputeArgs& a, cudaStream_t stream)
   const dim3 grid((unsigned)((a.ncols + T16_BN - 1) / T16_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
   note_compute_kernel("spmdm_compute_tc16_kernel");
-  ComputeArgs a2 = a; { const char* e = getenv("LIBXSMM_B200_TC16_DBG"); a2.dbg = e ? atoi(e) : 0; }
-  spmdm_compute_tc16_kernel<<<grid, T16_THREADS, T16_SMEM_BYTES, stream>>>(map, a2);
+  spmdm_compute_tc16_kernel<<<grid, T16_THREADS, T16_SMEM_BYTES, stream>>>(map, a);
   XB_CUDA(cudaGetLastError());
   return true;
 }

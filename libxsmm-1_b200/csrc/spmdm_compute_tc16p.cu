@@ -20,7 +20,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
-#include <cstdio>
 
 namespace xb {
 
@@ -112,7 +111,6 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   uint64_t* acc_empty = acc_full + 2;       // [2]  leader: the epilogue warps of both CTAs drained the accumulator
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
-  unsigned long long gt0; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt0)); const long long ck0 = clock64();
   const Geom& g = p.g;
   if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // uniform over the grid
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -164,20 +162,18 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
-  if (p.dbg & 64 && 0 == pair && 0 == tid) printf("rank %u prologue %lld clk\n", rank, clock64() - ck0);
 
   if (0 == warp) {
     // ---------------- TMA producer: this CTA's 128 columns of every B stage ----------------
     if (0 == lane) {
       tma_prefetch_desc(&tmB);
       uint32_t gs = 0;
-      long long w_prod = 0; const long long t_start = clock64();
       for (int wi = 0; wi < nwork; ++wi) {
         const int idx = work_idx(wi), half = work_half(wi);
         const int n0 = (idx / pair_m) * P_BN + (half < 0 ? (int)rank * P_BNH : half * P_BNH + (int)rank * (P_BNH / 2));
         for (int t = 0; t < 2 * nkb; ++t, ++gs) {
           const uint32_t s = gs % P_NB, f = gs / P_NB;
-          if (f > 0) { const long long c0 = clock64(); mbar_wait(&b_free[s], (f - 1) & 1); w_prod += clock64() - c0; }
+          if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
           if (0 == rank) mbar_arrive_expect_tx(&b_full[s], half < 0 ? 2 * P_B_STAGE : P_B_STAGE);
           const uint32_t lbar = map_to_cta(&b_full[s], 0);
           unsigned char* dst = smem + P_SMEM_B + s * P_B_STAGE;
@@ -188,7 +184,6 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
           }
         }
       }
-      if (p.dbg & 64 && 0 == pair) printf("rank %u producer: wait b_free %lld of %lld clk\n", rank, w_prod, clock64() - t_start);
     }
   }
   else if (1 == warp) {
@@ -198,21 +193,20 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.transb ? 0u : 1u) << 16) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)((2 * P_BM) >> 4) << 24);
       const uint32_t b_kstep = p.transb ? 32u : 2048u, b_lbo = p.transb ? 16u : (uint32_t)(P_KH * 128), b_sbo = 1024u;
       uint32_t gs = 0, gk = 0, it = 0;
-      long long w_a = 0, w_b = 0, w_e = 0; const long long t_start = clock64();
       for (int wi = 0; wi < nwork; ++wi, ++it) {
         const uint32_t acc = it & 1;
         // a half tile is the same instruction with N = 128: each CTA stages one 64-column block
         const uint32_t idesc_w = (work_half(wi) < 0) ? idesc : ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(P_BNH >> 3) << 17));
-        if (it >= 2) { const long long c0 = clock64(); mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1); w_e += clock64() - c0; }
+        if (it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);
         tc_fence_after();
         const uint32_t tacc = tmem_d + acc * P_BN;
         for (int kbi = 0; kbi < nkb; ++kbi, ++gk) {
           const uint32_t j = gk % P_NA;
-          { const long long c0 = clock64(); mbar_wait(&a_ready[j], (gk / P_NA) & 1); w_a += clock64() - c0; }
+          mbar_wait(&a_ready[j], (gk / P_NA) & 1);
 #pragma unroll
           for (int h = 0; h < 2; ++h, ++gs) {
             const uint32_t s = gs % P_NB;
-            { const long long c0 = clock64(); mbar_wait(&b_full[s], (gs / P_NB) & 1); w_b += clock64() - c0; }
+            mbar_wait(&b_full[s], (gs / P_NB) & 1);
             tc_fence_after();
             const uint32_t a_base = sbase + P_SMEM_A + j * P_A_BUF + h * P_A_HALF;
             const uint32_t b_base = sbase + P_SMEM_B + s * P_B_STAGE;
@@ -228,7 +222,6 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
         }
         tc_commit_pair(&acc_full[acc]);
       }
-      if (p.dbg & 64 && 0 == pair) printf("mma: wait a_ready %lld b_full %lld acc_empty %lld of %lld clk, %u tiles\n", w_a, w_b, w_e, clock64() - t_start, it);
     }
   }
   else if (warp < 2 + 4 * P_NG) {
@@ -290,13 +283,11 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       }
       fetch_ptrs(P);
     };
-    long long w_f = 0, sg0 = 0, sg1 = 0, sg2 = 0, sg3 = 0, sg4 = 0; const long long t_start = clock64();
     const uint32_t gk_end = (uint32_t)nwork * (uint32_t)nkb;
     auto step = [&](uint32_t gk, Raw& R, Ptr& P) {
       if (gk >= gk_end) return;
       const uint32_t j = gk % P_NA;
-      if (gk >= P_NA) { const long long c0 = clock64(); mbar_wait(&a_free[j], ((gk / P_NA) - 1) & 1); w_f += clock64() - c0; }
-      const long long c1 = clock64();
+      if (gk >= P_NA) mbar_wait(&a_free[j], ((gk / P_NA) - 1) & 1);
       unsigned char* abuf = smem + P_SMEM_A + j * P_A_BUF;
       // clear what the previous k-block left in the buffer (same register set: NA = 2 * NG); a dense one is wiped
       if (R.n_old > P_NQ * P_BM) {
@@ -313,7 +304,6 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       }
       asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(P_BM) : "memory");   // another thread may write where this one cleared
       // this k-block's nonzeros
-      const long long c2 = clock64(); sg0 += c2 - c1;
       const int n = R.last - R.first;
 #pragma unroll
       for (int i = 0; i < P_NQ; ++i) {
@@ -330,14 +320,10 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
 #pragma unroll 4
         for (int q = R.first + wt + P_NQ * P_BM; q < R.last; q += P_BM) { const uint32_t w = __ldg(pw + q); *addr_of(abuf, w) = (uint16_t)(w >> 16); }
       }
-      const long long c3 = clock64(); sg1 += c3 - c2;
       fence_proxy_async();
-      const long long c4 = clock64(); sg2 += c4 - c3;
       __syncwarp();
       if (0 == lane) mbar_arrive_cluster(lead_ready0 + j * 8);
-      const long long c5 = clock64(); sg3 += c5 - c4;
       fetch(R, P);                   // after the hand-over: refill this set for the step after next
-      sg4 += clock64() - c5;
     };
     Ptr pa, pb; Raw ra, rb;
     ra.n_old = 0; rb.n_old = 0;
@@ -358,7 +344,6 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       step(gk, ra, pa);
       step(gk + P_NG, rb, pb);
     }
-    if (p.dbg & 64 && 0 == pair && 0 == wt) printf("rank %u worker group %d: wait a_free %lld of %lld clk; unscatter %lld scatter %lld fence %lld arrive %lld fetch %lld\n", rank, grp, w_f, clock64() - t_start, sg0, sg1, sg2, sg3, sg4);
   }
   else {
     // ---------------- epilogue: warp owns TMEM lanes 32*(warp % 4) .. +31 of this CTA ----------------
@@ -366,13 +351,12 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
     const int row = quarter * 32 + lane;
     const uint32_t lead_empty0 = map_to_cta(&acc_empty[0], 0);
     uint32_t it = 0;
-    long long w_x = 0; const long long t_start = clock64();
     for (int wi = 0; wi < nwork; ++wi, ++it) {
       PairTile t = tile_of(work_idx(wi));
       const int half = work_half(wi), ncw = half < 0 ? P_BN : P_BNH;
       if (half > 0) t.n0 += P_BNH;
       const uint32_t acc = it & 1;
-      { const long long c0 = clock64(); mbar_wait(&acc_full[acc], (it >> 1) & 1); w_x += clock64() - c0; }
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const size_t crow = (size_t)(t.mbi * g.bm + t.ml0 + row - p.row_origin);
 #pragma unroll 1
@@ -418,11 +402,9 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
       __syncwarp();
       if (0 == lane) mbar_arrive_cluster(lead_empty0 + acc * 8);
     }
-    if (p.dbg & 64 && 0 == pair && 0 == lane && 0 == quarter) printf("rank %u epilogue: wait acc_full %lld of %lld clk\n", rank, w_x, clock64() - t_start);
   }
   tc_fence_before();
   __syncthreads();
-  if (p.dbg & 64 && 0 == pair && 0 == tid) { unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt1)); printf("rank %u CTA: %llu ns, %lld clk\n", rank, gt1 - gt0, clock64() - ck0); }
   cluster_sync_all();      // the peer's shared memory and barriers stay alive until every MMA and remote arrive has landed
   if (1 == warp) {
     tc_fence_after();
@@ -458,8 +440,7 @@ bool launch_compute_tc16p(const ComputeArgs& a, cudaStream_t stream)
   const int pairs = total < pairs_max ? total : pairs_max;
   count_launch(1);
   note_compute_kernel("spmdm_compute_tc16p_kernel");
-  ComputeArgs a2 = a; { const char* e = getenv("LIBXSMM_B200_TC16_DBG"); a2.dbg = e ? atoi(e) : 0; }
-  spmdm_compute_tc16p_kernel<<<dim3(2u * (unsigned)pairs), P_THREADS, P_SMEM_BYTES, stream>>>(map, a2);
+  spmdm_compute_tc16p_kernel<<<dim3(2u * (unsigned)pairs), P_THREADS, P_SMEM_BYTES, stream>>>(map, a);
   XB_CUDA(cudaGetLastError());
   return true;
 }

@@ -448,15 +448,14 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
         const uint32_t pm = lt & mymask;
         uint32_t q = rowpos + __popc(b0 & pm) + 2 * __popc(b1 & pm) + 4 * __popc(b2 & pm) + 8 * __popc(b3 & pm);
         const uint32_t v[4] = { w[it].x, w[it].y, w[it].z, w[it].w };
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (m & (1u << e)) {
-            co[q] = (uint16_t)(hl * 8 + e);
-            const uint32_t vb = (e & 1) ? (v[e >> 1] & 0xFFFF0000u) : (v[e >> 1] << 16);
-            va[q] = __uint_as_float(vb);
-            if (aux) rk[q] = xb_tc16_pack(r, hl * 8 + e, vb);
-            ++q;
-          }
+        // one trip per kept element of the fullest lane (1-2 in the sparse regime) instead of eight predicated slots
+        for (uint32_t mm = m; mm; mm &= mm - 1u, ++q) {
+          const int e = __ffs((int)mm) - 1;
+          const uint32_t pr = (e & 4) ? ((e & 2) ? v[3] : v[2]) : ((e & 2) ? v[1] : v[0]);
+          const uint32_t vb = (e & 1) ? (pr & 0xFFFF0000u) : (pr << 16);
+          co[q] = (uint16_t)(hl * 8 + e);
+          va[q] = __uint_as_float(vb);
+          if (aux) rk[q] = xb_tc16_pack(r, hl * 8 + e, vb);
         }
       }
       pos += lo_tot + hi_tot;
