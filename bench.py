@@ -401,7 +401,7 @@ def main():
         r = cpu_reference(wl, budget_s=0.0, reps_min=args.steps + args.warmup, reps_max=args.steps + args.warmup)
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": wl["dtype"], "data": "synthetic",
+                "dtype": "f32" if wl["dtype"] in ("f32", "bf16") else "f64", "data": "synthetic",
                 "config": {"workload": wl["desc"], "note": "reference CPU path on this host; one rank only"},
                 "cpu_baseline": {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -495,7 +495,7 @@ def main():
                      "kernel_ms": res["kernel_ms"], "parts": res["parts"]},
         "clocks": clocks,
     }
-    if "tc16" in res["kernel_name"] and res.get("dense_flops"):
+    if res["kernel_name"].startswith("spmdm_compute_tc16") and res.get("dense_flops"):
         # the bf16 tensor-core kernels multiply the densified slices: their own pipe utilisation, for the reader --
         # the roofline above stays the algorithmic (HBM) one of the sparse product
         tp, tsrc = tensor_peak()
@@ -509,12 +509,22 @@ def main():
                        "api": "libxsmm_spmdm_exec_host" if wl["kind"] == "spmdm" else "libxsmm_[sd]fsspmdm_execute (host pointers)"}
     if world == 1 and rank == 0 and args.others:
         others = {}
-        for name in [n for n in args.others.split(",") if n and n != args.workload]:
+        names = [n for n in args.others.split(",") if n and n != args.workload]
+        if wl["kind"] == "spmdm":
+            names.insert(0, args.workload + "@cuda-cores")     # same workload, LIBXSMM_B200_SPMDM_TC=0: the order-preserving (bit-exact) kernels only
+        for name in names:
             try:
-                r2, _, _ = run(WORKLOADS[name], False, False)
+                forced = name.endswith("@cuda-cores")
+                if forced:
+                    os.environ["LIBXSMM_B200_SPMDM_TC"] = "0"
+                try:
+                    r2, _, _ = run(WORKLOADS[name.split("@")[0]], False, False)
+                finally:
+                    if forced:
+                        os.environ.pop("LIBXSMM_B200_SPMDM_TC", None)
                 ms2 = r2["total_ms"] / args.steps
                 ach2 = r2["kernel_bytes"] / (r2["kernel_ms"] * 1e6)
-                others[name] = {"workload": WORKLOADS[name]["desc"], "value": r2["flops"] / (ms2 * 1e6), "unit": "GFLOP/s", "ms_per_step": ms2,
+                others[name] = {"workload": WORKLOADS[name.split("@")[0]]["desc"] + (" [LIBXSMM_B200_SPMDM_TC=0]" if forced else ""), "value": r2["flops"] / (ms2 * 1e6), "unit": "GFLOP/s", "ms_per_step": ms2,
                                 "hbm_gbs": r2["step_bytes"] / (ms2 * 1e6), "kernel": r2["kernel_name"], "kernel_ms": r2["kernel_ms"],
                                 "kernel_hbm_gbs": ach2, "kernel_hbm_frac": ach2 / peak, "parts": r2["parts"], "gpu_launches": r2["launches"]}
             except Exception as ex:      # a secondary workload must never take the headline down

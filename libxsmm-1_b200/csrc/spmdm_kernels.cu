@@ -893,6 +893,8 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
     a.ncols = hi - lo;
     launch_part(a, 1 == part, (0 == part) ? stream : side);
   }
+  if (args2.tc_twin > 0) note_compute_kernel(args.is_bf16 ? "twin: spmdm_compute_tc16p_kernel | spmdm_compute_tma_kernel (selected on the device by nnz)"
+                                                          : "twin: spmdm_compute_tc_kernel | spmdm_compute_tma_kernel (selected on the device by nnz)");
   if (narrow) {
     XB_CUDA(cudaEventRecord(join, side));
     XB_CUDA(cudaStreamWaitEvent(stream, join, 0));
