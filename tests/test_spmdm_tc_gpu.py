@@ -157,3 +157,29 @@ def test_bf16_full_size_c2(gpu, monkeypatch, density, beta, pair):
     want = gpu.workloads.from_bf16_bits(A[rows]).astype(np.float64) @ gpu.workloads.from_bf16_bits(B).astype(np.float64) + beta * C0[rows]
     assert rel(C_tc[rows], want) <= 1e-5
     gpu.check()
+
+
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("M,N,K,density,beta,threads", [
+    (300, 204, 260, 0.30, 1, 1),        # ragged M, partial 256-column tile, K tail (260 = 2 * 128 + 4)
+    (2048, 256, 200, 0.02, 0, 56),      # bm = 245 (balance loop): CTA tiles of 128 + 117 rows, pairs span row blocks
+    (33, 8, 129, 0.40, 0, 1),           # one partial tile, second k-block holds a single column
+    (1536, 520, 384, 0.002, 0, 1),      # nearly empty slices (most k-blocks of a tile hold no nonzero)
+    (640, 256, 128, 1.00, 0, 1),        # full slices: u16 counter wraps in the first row block, dense fallback of the workers
+])
+def test_bf16_tensor_core_shapes(gpu, oracle, monkeypatch, pair, M, N, K, density, beta, threads):
+    """geometry corners of the bf16 tensor-core kernels (CTA-pair and single-CTA), forced on."""
+    monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", "1")
+    monkeypatch.setenv("LIBXSMM_B200_TC16_PAIR", pair)
+    if density >= 1.0:
+        rng = np.random.default_rng(5)
+        A = gpu.workloads.to_bf16_bits((rng.random((M, K)) + 0.5).astype(np.float32))
+        B = gpu.workloads.to_bf16_bits(rng.random((K, N)).astype(np.float32))
+        C0 = rng.random((M, N)).astype(np.float32)
+    else:
+        A, B, C0 = gpu.workloads.spmdm_inputs(M, N, K, density, dtype="bf16", seed=M + K)
+    g, sl, C = gpu_spmdm(gpu, A, B, C0, M, N, K, "N", "N", "N", beta, True, threads)
+    og, osl, OC = oracle_spmdm(oracle, g, A, B, C0, "N", "N", "N", float(beta))
+    valid_slices_equal(og, sl, osl)
+    assert rel(C, OC) <= 1e-5
+    gpu.check()
