@@ -374,6 +374,9 @@ def cpu_reference(wl, budget_s, reps_min=1, reps_max=50):
 
 # ------------------------------------------------------------------------------------------------------
 def main():
+    # exactly ONE line on stdout: libraries that write to file descriptor 1 (NCCL prints its version there) are sent to stderr
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -405,7 +408,7 @@ def main():
                 "config": {"workload": wl["desc"], "note": "reference CPU path on this host; one rank only"},
                 "cpu_baseline": {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return 0
 
     if args.gpus > 1 and world == 1:      # convenience: re-launch under torchrun like the driver does
@@ -538,7 +541,7 @@ def main():
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": host_cores(), "kind": "reference", "sample": "failed: %r" % (ex,)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,2 +1,4 @@
-timeout 120 python tools/time_spmdm.py c2 30 2>&1 | tail -2
-timeout 900 python -m pytest tests/test_spmdm_tc_gpu.py -m gpu -x -q 2>&1 | tail -3
+for v in 4 8 12 16; do
+LIBXSMM_B200_EXEC_PANELS=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --others "" 2>/dev/null | tail -1 | python -c "
+import json,sys; r=json.loads(sys.stdin.read()); print('panels=$v', round(r['value']), r['e2e']['ms_per_step'], round(r['e2e']['value']))"
+done
