@@ -75,28 +75,31 @@ struct SpmdmCtx {
   bool aux_written;               // the auxiliary per-nonzero words of the current slices are valid
 };
 
-// 0 unknown (first call), 1 sparse, 2 dense according to the last completed slicing pass (thresholds of
-// launch_compute: kTcDensityF32 / kTcDensityBf16)
-static int density_hint(const SpmdmCtx* c, int is_bf16)
+// 0 unknown (first call), 1 sparse, 2 dense according to the last completed slicing pass and the thresholds of
+// launch_compute (common.cuh: tc_density_threshold)
+static int density_hint(const SpmdmCtx* c, int is_bf16, bool transb, bool transc)
 {
   const unsigned long long n = c->h_nnz ? *(volatile unsigned long long*)c->h_nnz : ~0ull;
   if (~0ull == n) return 0;
-  const double thr = (is_bf16 ? xb::kTcDensityBf16 : xb::kTcDensityF32) * (double)c->g.m * (double)c->g.k;
+  const double thr = xb::tc_density_threshold(0 != is_bf16, transb, transc) * (double)c->g.m * (double)c->g.k;
   return ((double)n < thr) ? 1 : 2;   // either way the result is correct; a wrong guess only costs speed for one call
 }
 
 static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole)
 {
   a->acc = c->d_acc; a->host_total = c->d_nnz; a->total_slices = c->g.mb * c->g.kb;
-  a->write_aux = (!whole || 1 != density_hint(c, is_bf16)) ? 1 : 0;
+  // the orientation of the multiply that will consume the slices is not known here: the auxiliary words are
+  // skipped only when no orientation would take the tensor-core side (bf16: transposed panels always do)
+  const bool skip = whole && !is_bf16 && 1 == density_hint(c, is_bf16, true, false);
+  a->write_aux = skip ? 0 : 1;
   if (whole) c->aux_written = (0 != a->write_aux);
   else c->aux_written = true;
 }
 
-static int compute_policy(const SpmdmCtx* c, int is_bf16)
+static int compute_policy(const SpmdmCtx* c, int is_bf16, bool transb, bool transc)
 {
   if (!c->aux_written) return 1;      // the slices carry no auxiliary words: CUDA cores only
-  return density_hint(c, is_bf16);
+  return density_hint(c, is_bf16, transb, transc);
 }
 
 static std::mutex g_reg_mtx;
@@ -186,7 +189,7 @@ static void compute_whole(const libxsmm_spmdm_handle* handle, char transb, char 
   a.ldb = a.transb ? c->g.k : c->g.n;
   a.ldc = a.transc ? c->g.m : c->g.n;
   a.beta = beta; a.g = c->g; a.mb_first = 0; a.mb_count = c->g.mb;
-  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16);
+  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16, 0 != a.transb, 0 != a.transc);
   launch_compute(a, stream);
 }
 
@@ -543,7 +546,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
     ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
     ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
     ca.beta = beta_f; ca.g = g; ca.mb_first = r0; ca.mb_count = rc;
-    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16);
+    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16, tb, tc);
     launch_compute(ca, c->xs[1]);
   };
   for (int d = 0; d < nd; ++d) {

@@ -104,10 +104,16 @@ __device__ __forceinline__ void xb_publish_nnz(const SliceArgs& p, unsigned long
 // mode boundaries of the reference's narrow last block (compute template :72-76,372-434)
 struct ColModes { int n_full_end; int tail_from; };
 
-// Density (nnz / (M*K)) from which the tensor-core twin takes over, measured on B200: fp32 (3xTF32, three MMAs per
-// k-step) 7 %; bf16 0.5 % (the CTA-pair kernel costs ~104 us for 4096^3 at any density, the CUDA-core kernel 177 us
-// at 1 % and proportionally less below).
-constexpr double kTcDensityF32 = 0.07, kTcDensityBf16 = 0.005;
+// Density (nnz / (M*K)) from which the tensor-core twin takes over, measured on B200 (2048^3 and 4096^3):
+//   bf16: the CTA-pair kernel costs the same at any density and orientation (93 us for 4096^3, 28 us for 2048^3); the
+//         TMA CUDA-core kernel (N/N/N) is ahead of it below ~0.5 %, the generic one (transb / transc) never is.
+//   fp32: 3xTF32 costs ~170 us for 2048^3; the TMA kernel is ahead below ~7 %, the generic one below ~5 % (transc)
+//         / ~1 % (transb).
+inline double tc_density_threshold(bool is_bf16, bool transb, bool transc)
+{
+  if (is_bf16) return (transb || transc) ? 0.0 : 0.005;
+  return transb ? 0.01 : (transc ? 0.05 : 0.07);
+}
 
 struct ComputeArgs {
   SliceArena sl;

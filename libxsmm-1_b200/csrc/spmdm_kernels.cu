@@ -819,7 +819,7 @@ static cudaStream_t side_stream()
 }
 
 // LIBXSMM_B200_SPMDM_TC: "0" never use the tensor-core branch, "1" always (when the panel qualifies),
-// unset / anything else: by density -- total nnz >= 7 % (fp32) or 0.5 % (bf16) of M*K (common.cuh), decided on the device.
+// unset / anything else: by density -- total nnz >= tc_density_threshold() of M*K (common.cuh), decided on the device.
 static int tc_mode()
 {
   const char* e = getenv("LIBXSMM_B200_SPMDM_TC");
@@ -862,7 +862,7 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
   }
   if (mode > 0) {
     targs.tc_twin = 1;
-    targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)((args.is_bf16 ? kTcDensityBf16 : kTcDensityF32) * (double)args.g.m * (double)args.g.k);
+    targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)(tc_density_threshold(0 != args.is_bf16, 0 != args.transb, 0 != args.transc) * (double)args.g.m * (double)args.g.k);
     if (!(args.is_bf16 ? launch_tc_bf16(targs, stream) : launch_compute_tc(targs, stream))) targs.tc_twin = 0;
     else if (1 == mode) return;   // forced: nothing for the sparse kernels to do
   }
