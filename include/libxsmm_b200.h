@@ -100,6 +100,26 @@ LIBXSMM_API void* libxsmm_b200_graph_end(void* stream);
 LIBXSMM_API int libxsmm_b200_graph_launch(void* graph_exec, void* stream);
 LIBXSMM_API void libxsmm_b200_graph_destroy(void* graph_exec);
 
+/* Fused caller step: C = A.B (+ beta.C) on DEVICE matrices in ONE stream-ordered call -- handle lookup, slice
+ * creation and compute.  This is the wrapper TensorFlow's sparse_matmul_op keeps around the reference
+ * (reference documentation/tensorflow.md:241-250; in-tree model samples/spmdm/spmdm.c:74-154): handles are cached
+ * by (M, N, K, max_threads, stream), at most 16, least recently used evicted.  Arguments as
+ * libxsmm_spmdm_exec_stream; returns 0 or the library's error code. */
+LIBXSMM_API int libxsmm_b200_sparse_matmul(libxsmm_spmdm_datatype datatype, char transa, char transb, char transc,
+  int M, int N, int K, int max_threads, const void* d_a, const void* d_b, const void* beta, float* d_c, void* stream);
+LIBXSMM_API int libxsmm_b200_sparse_matmul_cache_entries(void);
+LIBXSMM_API void libxsmm_b200_sparse_matmul_cache_clear(void);
+
+/* MatrixMarket coordinate files (the operator format of samples/pyfr/mats and samples/edge/mats; reference reader
+ * src/generator_spgemm_csr_reader.c:46-169): read into CSR (malloc'ed arrays, release with libxsmm_b200_csr_free;
+ * returns 0 or a negative error code), or straight into a fixed operator (lda = K = columns of the file, alpha = 1).
+ * Host-only parsing; create_mtx then calls the ordinary create(). */
+LIBXSMM_API int libxsmm_b200_csr_read_mtx(const char* path, unsigned int** row_ptr, unsigned int** col_idx, double** values,
+  unsigned int* rows, unsigned int* cols, unsigned int* nnz);
+LIBXSMM_API void libxsmm_b200_csr_free(unsigned int* row_ptr, unsigned int* col_idx, double* values);
+LIBXSMM_API libxsmm_dfsspmdm* libxsmm_b200_dfsspmdm_create_mtx(const char* path, int N, int ldb, int ldc, double beta, int* M, int* K);
+LIBXSMM_API libxsmm_sfsspmdm* libxsmm_b200_sfsspmdm_create_mtx(const char* path, int N, int ldb, int ldc, float beta, int* M, int* K);
+
 /* Host-only planning entries (no CUDA call is made; they work on a machine without a GPU).
  * geometry: the block geometry libxsmm_spmdm_init would choose (reference src/libxsmm_spmdm.c:552-608)
  *   for bn = 48 | 96 | 6; geom[9] = m n k bm bn bk mb nb kb.  Returns 0 on success.

@@ -49,6 +49,8 @@ ADDED_SYMBOLS = [
     "libxsmm_b200_spmdm_geometry", "libxsmm_b200_fsspmdm_plan", "libxsmm_b200_fsspmdm_kernel_source",
     "libxsmm_b200_free_string",
     "libxsmm_b200_graph_begin", "libxsmm_b200_graph_end", "libxsmm_b200_graph_launch", "libxsmm_b200_graph_destroy",
+    "libxsmm_b200_sparse_matmul", "libxsmm_b200_sparse_matmul_cache_entries", "libxsmm_b200_sparse_matmul_cache_clear",
+    "libxsmm_b200_csr_read_mtx", "libxsmm_b200_csr_free", "libxsmm_b200_dfsspmdm_create_mtx", "libxsmm_b200_sfsspmdm_create_mtx",
 ]
 
 
@@ -420,6 +422,48 @@ def libxsmm_spmdm_exec_stream(handle, slices, datatype, transa, transb, transc, 
                                      _addr(d_a), _addr(d_b), ctypes.addressof(be), _addr(d_c), _sptr(stream))
 
 
+def libxsmm_b200_sparse_matmul(datatype, transa, transb, transc, M, N, K, max_threads, d_a, d_b, beta, d_c, stream=None):
+    """Fused caller step (handle cache + slice creation + compute in one stream-ordered call); returns the error code."""
+    be = _beta_box(datatype, beta)
+    L = load()
+    L.libxsmm_b200_sparse_matmul.restype = ctypes.c_int
+    L.libxsmm_b200_sparse_matmul.argtypes = [ctypes.c_int, ctypes.c_char, ctypes.c_char, ctypes.c_char, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    return int(L.libxsmm_b200_sparse_matmul(datatype, _c(transa), _c(transb), _c(transc), M, N, K, max_threads,
+                                            _addr(d_a), _addr(d_b), ctypes.addressof(be), _addr(d_c), _sptr(stream)))
+
+
+def sparse_matmul_cache_entries():
+    return int(load().libxsmm_b200_sparse_matmul_cache_entries())
+
+
+def sparse_matmul_cache_clear():
+    load().libxsmm_b200_sparse_matmul_cache_clear()
+
+
+def csr_read_mtx(path):
+    """MatrixMarket coordinate file -> (row_ptr, col_idx, values, rows, cols) through the library's reader (host only).
+    Raises ValueError with the library's message on a malformed file."""
+    L = load()
+    rp, ci, va = ctypes.POINTER(ctypes.c_uint)(), ctypes.POINTER(ctypes.c_uint)(), ctypes.POINTER(ctypes.c_double)()
+    nr, nc, ne = ctypes.c_uint(0), ctypes.c_uint(0), ctypes.c_uint(0)
+    L.libxsmm_b200_csr_read_mtx.restype = ctypes.c_int
+    rc = L.libxsmm_b200_csr_read_mtx(os.fsencode(path), ctypes.byref(rp), ctypes.byref(ci), ctypes.byref(va),
+                                     ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(ne))
+    if 0 != rc:
+        code, msg = last_error()
+        clear_error()
+        raise ValueError("csr_read_mtx failed (%d): %s" % (rc, msg))
+    try:
+        row_ptr = np.ctypeslib.as_array(rp, shape=(nr.value + 1,)).copy()
+        col_idx = np.ctypeslib.as_array(ci, shape=(ne.value,)).copy()
+        values = np.ctypeslib.as_array(va, shape=(ne.value,)).copy()
+    finally:
+        L.libxsmm_b200_csr_free.restype = None
+        L.libxsmm_b200_csr_free(rp, ci, va)
+    return row_ptr, col_idx, values, int(nr.value), int(nc.value)
+
+
 # ======================================================================================================
 # FSSPMDM -- reference include/libxsmm_fsspmdm.h:41-57
 # ======================================================================================================
@@ -527,6 +571,29 @@ class Fsspmdm:
             clear_error()
             raise ValueError("fsspmdm_create failed: %s" % msg)
         clear_error()   # a missing NVRTC is reported but not fatal (generic kernel)
+
+    @classmethod
+    def from_mtx(cls, path, N, ldb=None, ldc=None, beta=0.0, double=True):
+        """the operator of a MatrixMarket file (libxsmm_b200_[sd]fsspmdm_create_mtx)."""
+        require_gpu()
+        L = load()
+        self = cls.__new__(cls)
+        self.double, self.N = bool(double), N
+        self.ldb = N if ldb is None else ldb
+        self.ldc = N if ldc is None else ldc
+        m, k = ctypes.c_int(0), ctypes.c_int(0)
+        f = L.libxsmm_b200_dfsspmdm_create_mtx if double else L.libxsmm_b200_sfsspmdm_create_mtx
+        f.restype = ctypes.c_void_p
+        f.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double if double else ctypes.c_float,
+                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        self.handle = f(os.fsencode(path), N, self.ldb, self.ldc, float(beta), ctypes.byref(m), ctypes.byref(k))
+        if not self.handle:
+            code, msg = last_error()
+            clear_error()
+            raise ValueError("fsspmdm_create_mtx failed: %s" % msg)
+        clear_error()
+        self.M, self.K = int(m.value), int(k.value)
+        return self
 
     @property
     def is_sparse(self):

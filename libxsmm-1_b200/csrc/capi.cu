@@ -12,6 +12,7 @@
 #include <climits>
 #include <mutex>
 #include <unordered_map>
+#include <map>
 #include <vector>
 
 namespace xb {
@@ -784,5 +785,151 @@ char* libxsmm_b200_fsspmdm_kernel_source(int is_double, int M, int N, int K, int
 }
 
 void libxsmm_b200_free_string(char* s) { free(s); }
+
+// ---- MatrixMarket operators ----------------------------------------------------
+// Same file convention as the reference's reader (src/generator_spgemm_csr_reader.c:46-169 and the PyFR driver's
+// copy, samples/pyfr/pyfr_driver_asp_reg.c:47-158): '%' comment lines, one "rows cols nnz" line, then nnz lines
+// "row col value" with 1-based indices; rows without entries are allowed.  The reference assumes the entries
+// are sorted by row; here they are bucketed by row (stable), which is the identity on sorted files.
+int libxsmm_b200_csr_read_mtx(const char* path, unsigned int** row_ptr, unsigned int** col_idx, double** values,
+                              unsigned int* rows, unsigned int* cols, unsigned int* nnz)
+{
+  if (0 == path || 0 == row_ptr || 0 == col_idx || 0 == values || 0 == rows || 0 == cols || 0 == nnz) return -1;
+  *row_ptr = 0; *col_idx = 0; *values = 0; *rows = *cols = *nnz = 0;
+  FILE* f = fopen(path, "r");
+  if (0 == f) { set_error(-40, "csr_read_mtx: cannot open %s", path); return -40; }
+  char line[1024];
+  unsigned int nr = 0, nc = 0, ne = 0;
+  bool header = false;
+  std::vector<unsigned int> er, ec;
+  std::vector<double> ev;
+  int rc = 0;
+  while (0 == rc && 0 != fgets(line, (int)sizeof(line), f)) {
+    if (strlen(line) + 1 >= sizeof(line)) { rc = -41; break; }                  // over-long line (reference: CSR_READ_LEN)
+    const char* q = line;
+    while (' ' == *q || '\t' == *q) ++q;
+    if ('%' == *q || '\n' == *q || '\r' == *q || 0 == *q) continue;
+    if (!header) {
+      if (3 != sscanf(q, "%u %u %u", &nr, &nc, &ne) || 0 == nr || 0 == nc || 0 == ne) { rc = -42; break; }   // reference: CSR_READ_DESC
+      header = true;
+      er.reserve(ne); ec.reserve(ne); ev.reserve(ne);
+    }
+    else {
+      unsigned int r = 0, cidx = 0; double v = 0;
+      if (3 != sscanf(q, "%u %u %lf", &r, &cidx, &v)) { rc = -43; break; }                                      // reference: CSR_READ_ELEMS
+      if (0 == r || 0 == cidx || r > nr || cidx > nc) { rc = -44; break; }
+      er.push_back(r - 1); ec.push_back(cidx - 1); ev.push_back(v);
+    }
+  }
+  fclose(f);
+  if (0 == rc && (!header || er.size() != (size_t)ne)) rc = -45;                                                 // reference: CSR_LEN
+  if (0 != rc) { set_error(rc, "csr_read_mtx: %s is not a valid MatrixMarket coordinate file (code %d)", path, rc); return rc; }
+  unsigned int* rp = (unsigned int*)malloc(sizeof(unsigned int) * ((size_t)nr + 1));
+  unsigned int* ci = (unsigned int*)malloc(sizeof(unsigned int) * ne);
+  double* va = (double*)malloc(sizeof(double) * ne);
+  if (0 == rp || 0 == ci || 0 == va) { free(rp); free(ci); free(va); set_error(-46, "csr_read_mtx: out of memory"); return -46; }
+  memset(rp, 0, sizeof(unsigned int) * ((size_t)nr + 1));
+  for (unsigned int i = 0; i < ne; ++i) ++rp[er[i] + 1];
+  for (unsigned int i = 0; i < nr; ++i) rp[i + 1] += rp[i];
+  std::vector<unsigned int> fill(rp, rp + nr);
+  for (unsigned int i = 0; i < ne; ++i) { const unsigned int d = fill[er[i]]++; ci[d] = ec[i]; va[d] = ev[i]; }
+  *row_ptr = rp; *col_idx = ci; *values = va; *rows = nr; *cols = nc; *nnz = ne;
+  return 0;
+}
+
+void libxsmm_b200_csr_free(unsigned int* row_ptr, unsigned int* col_idx, double* values) { free(row_ptr); free(col_idx); free(values); }
+
+// operator file -> dense row-major A (lda = cols) -> the ordinary create(); duplicates in the file overwrite like
+// the drivers' own densification (samples/pyfr/pyfr_driver_asp_reg.c:226-238)
+static void* fsspmdm_create_mtx(int is_double, const char* path, int N, int ldb, int ldc, double beta, int* M_out, int* K_out)
+{
+  unsigned int *rp = 0, *ci = 0, nr = 0, nc = 0, ne = 0; double* va = 0;
+  if (0 != libxsmm_b200_csr_read_mtx(path, &rp, &ci, &va, &nr, &nc, &ne)) return 0;
+  void* h = 0;
+  if (is_double) {
+    std::vector<double> a((size_t)nr * nc, 0.0);
+    for (unsigned int r = 0; r < nr; ++r) for (unsigned int j = rp[r]; j < rp[r + 1]; ++j) a[(size_t)r * nc + ci[j]] = va[j];
+    h = libxsmm_dfsspmdm_create((int)nr, N, (int)nc, (int)nc, ldb, ldc, 1.0, beta, a.data());
+  }
+  else {
+    std::vector<float> a((size_t)nr * nc, 0.f);
+    for (unsigned int r = 0; r < nr; ++r) for (unsigned int j = rp[r]; j < rp[r + 1]; ++j) a[(size_t)r * nc + ci[j]] = (float)va[j];
+    h = libxsmm_sfsspmdm_create((int)nr, N, (int)nc, (int)nc, ldb, ldc, 1.f, (float)beta, a.data());
+  }
+  if (M_out) *M_out = (int)nr;
+  if (K_out) *K_out = (int)nc;
+  libxsmm_b200_csr_free(rp, ci, va);
+  return h;
+}
+libxsmm_dfsspmdm* libxsmm_b200_dfsspmdm_create_mtx(const char* path, int N, int ldb, int ldc, double beta, int* M, int* K)
+{ return (libxsmm_dfsspmdm*)fsspmdm_create_mtx(1, path, N, ldb, ldc, beta, M, K); }
+libxsmm_sfsspmdm* libxsmm_b200_sfsspmdm_create_mtx(const char* path, int N, int ldb, int ldc, float beta, int* M, int* K)
+{ return (libxsmm_sfsspmdm*)fsspmdm_create_mtx(0, path, N, ldb, ldc, (double)beta, M, K); }
+
+// ---- fused caller step ----------------------------------------------------------
+// What TensorFlow's sparse_matmul_op builds around the reference (documentation/tensorflow.md:241-250): a cache of
+// handles keyed by the problem shape, and slice creation + compute as one call.  Here the key also holds the stream,
+// because a handle's slice arena must not be shared by multiplies that may run concurrently.
+struct MatmulKey {
+  int m, n, k, threads; void* stream;
+  bool operator<(const MatmulKey& o) const {
+    if (m != o.m) return m < o.m; if (n != o.n) return n < o.n; if (k != o.k) return k < o.k;
+    if (threads != o.threads) return threads < o.threads; return stream < o.stream;
+  }
+};
+struct MatmulEntry { libxsmm_spmdm_handle handle; libxsmm_CSR_sparseslice* slices; unsigned long long last_use; };
+static std::mutex g_mm_mtx;
+static std::map<MatmulKey, MatmulEntry*> g_mm_cache;
+static unsigned long long g_mm_clock = 0;
+static const size_t kMatmulCacheMax = 16;
+
+int libxsmm_b200_sparse_matmul(libxsmm_spmdm_datatype datatype, char transa, char transb, char transc, int M, int N, int K,
+  int max_threads, const void* d_a, const void* d_b, const void* beta, float* d_c, void* stream)
+{
+  if (M <= 0 || N <= 0 || K <= 0 || 0 == d_a || 0 == d_b || 0 == d_c || 0 == beta) { set_error(-50, "sparse_matmul: bad argument"); return -50; }
+  if (max_threads < 1) max_threads = 1;
+  MatmulEntry* e = 0;
+  {
+    std::lock_guard<std::mutex> lock(g_mm_mtx);
+    const MatmulKey key = { M, N, K, max_threads, stream };
+    std::map<MatmulKey, MatmulEntry*>::iterator it = g_mm_cache.find(key);
+    if (it == g_mm_cache.end()) {
+      if (g_mm_cache.size() >= kMatmulCacheMax) {      // evict the least recently used handle (its stream is drained first)
+        std::map<MatmulKey, MatmulEntry*>::iterator old = g_mm_cache.begin();
+        for (std::map<MatmulKey, MatmulEntry*>::iterator j = g_mm_cache.begin(); j != g_mm_cache.end(); ++j) if (j->second->last_use < old->second->last_use) old = j;
+        XB_CUDA(cudaStreamSynchronize((cudaStream_t)old->first.stream));
+        libxsmm_spmdm_destroy(&old->second->handle);
+        delete old->second;
+        g_mm_cache.erase(old);
+      }
+      e = new MatmulEntry();
+      memset(&e->handle, 0, sizeof(e->handle)); e->slices = 0;
+      libxsmm_spmdm_init(M, N, K, max_threads, &e->handle, &e->slices);
+      if (0 == e->handle.base_ptr_scratch_A) { delete e; return -51; }
+      g_mm_cache[key] = e;
+    }
+    else e = it->second;
+    e->last_use = ++g_mm_clock;
+  }
+  libxsmm_spmdm_exec_stream(&e->handle, e->slices, datatype, transa, transb, transc, d_a, d_b, beta, d_c, stream);
+  return libxsmm_b200_last_error();
+}
+
+int libxsmm_b200_sparse_matmul_cache_entries(void)
+{
+  std::lock_guard<std::mutex> lock(g_mm_mtx);
+  return (int)g_mm_cache.size();
+}
+
+void libxsmm_b200_sparse_matmul_cache_clear(void)
+{
+  std::lock_guard<std::mutex> lock(g_mm_mtx);
+  for (std::map<MatmulKey, MatmulEntry*>::iterator j = g_mm_cache.begin(); j != g_mm_cache.end(); ++j) {
+    (void)cudaStreamSynchronize((cudaStream_t)j->first.stream);
+    libxsmm_spmdm_destroy(&j->second->handle);
+    delete j->second;
+  }
+  g_mm_cache.clear();
+}
 
 }  // extern "C"
