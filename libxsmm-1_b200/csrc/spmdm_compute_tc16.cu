@@ -2,15 +2,15 @@
 //
 //   C[128 rows, 256 cols] = beta*C + sum_kb densify(slice(kb, mb))[128 x 128] * B[kb*128 .. +128, 256 cols]
 //
-// bf16 x bf16 products are exact in the tensor core, so there is no operand split: one tcgen05.mma
-// (kind::f16, M = 128, N = 256, K = 16) per 16 k.  Its time does not depend on the density: measured on B200,
-// 4096^3: 176 us (tensor pipe 41 % busy; the step is bound by shared-memory traffic: 32 KiB of TMA writes,
-// 48 KiB of operand reads and 16 KiB of zero-fill per 64 k) -- break-even with the CUDA-core kernel (which pays
-// 8 FFMA + 8 bf16 unpack operations per nonzero and 256 columns) at ~1 % density, ahead of it above.
+// The single-CTA predecessor of the CTA-pair kernel (spmdm_compute_tc16p.cu), kept as its fallback and for comparison
+// (LIBXSMM_B200_TC16_PAIR=0).  bf16 x bf16 products are exact in the tensor core, so there is no operand split: one
+// tcgen05.mma (kind::f16, M = 128, N = 256, K = 16) per 16 k; the time does not depend on the density.  Measured on
+// B200, 4096^3: 164 us (K4p: 93 us).  With its stages switched off one at a time: MMA + TMA alone 128 us (B crosses
+// L2 -> SM once per 128 output rows: 1.07 GB at 8.4 TB/s), zero-fill + its barrier 13 us, the epilogue 25 us.
 //   * A: the slice block is scattered into a zeroed K-major SWIZZLE_128B tile, one 64-k half at a time
 //     (128 rows x 128 B = 16 KiB), four buffers deep so that the workers run ahead of the tensor core (the
-//     rebuild -> multiply -> release cycle of one buffer is latency bound).  A thread keeps its share of the k-block's nonzeros in registers (one packed word
-//     each: bf16 value | half | position) and scatters them twice.
+//     rebuild -> multiply -> release cycle of one buffer is latency bound).  A thread keeps its share of the k-block's nonzeros in registers (the slicing kernel's packed
+//     word: bf16 value | half | position) and scatters them once per half.
 //   * B: 64 x 256 tiles by TMA (four boxes of 64 columns, SWIZZLE_128B; MN-major operand: pinned with
 //     tools/umma_probe/probe16.cu) through a 4-stage ring; for transb = 'T' (B stored n x k) one box of
 //     256 rows x 64 k, a K-major operand.

@@ -136,8 +136,9 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   };
 
   // Work list of this pair: q full tiles, then -- when the remaining tiles are at most half as many as the pairs --
-  // one HALF tile (128 of the 256 columns), so that the last round costs half a tile instead of a whole one
-  // (4096^3 on 74 pairs: 256 tiles = 3 rounds + 34 tiles -> 68 half tiles; makespan 3.5 instead of 4 tiles).
+  // one HALF tile (128 of the 256 columns), so that no pair idles through the last round (4096^3 on 74 pairs:
+  // 256 tiles = 3 rounds + 34 tiles -> 68 half tiles).  Measured gain 4 us of 108, not the 12 a half-cost round would
+  // give: a half tile needs its k-blocks at twice the rate and is bound by the densifying warps, not the tensor core.
   const int wq = total / npairs, wrem = total - wq * npairs;
   const bool wsplit = !p.transb && wrem > 0 && 2 * wrem <= npairs;
   const int nwork = wq + ((wsplit ? (pair < 2 * wrem) : (pair < wrem)) ? 1 : 0);
