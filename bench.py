@@ -66,6 +66,25 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """N > 1 ranks share one host: run this rank (and first-touch its page-locked buffers) on the CPUs NVML reports as
+    local to its GPU, what `numactl` would do for a multi-GPU job.  Best effort; returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return "rank bound to %d GPU-local CPUs" % len(use)
+        return "GPU-local CPUs = allowed set (%d)" % len(allowed)
+    except Exception as ex:
+        return "not bound (%s)" % type(ex).__name__
+
+
 def tensor_peak():
     """dense bf16 TFLOP/s (cuBLAS, burst: the kernel is timed alone) for the tensor-core kernels' own utilisation figure."""
     try:
@@ -426,6 +445,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     xs.load().libxsmm_b200_set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
 
     def barrier():
         if dist is not None:
@@ -488,7 +508,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if wl["dtype"] in ("f32", "bf16") else "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "per_gpu": "one N-column panel per rank, A replicated, no collective on the data path",
-                   "global_N": (wl["N"] * world), "inputs": "bf16" if wl["dtype"] == "bf16" else wl["dtype"],
+                   "global_N": (wl["N"] * world), **({"numa": numa} if numa else {}), "inputs": "bf16" if wl["dtype"] == "bf16" else wl["dtype"],
                    "l2_policy": "inputs larger than L2: ring of %d A/B/C sets = %.0f MB, a different set every step" % (res["ring_sets"], res["ring_bytes"] / 1e6),
                    "geometry": res["geo"], "nnz": res["nnz"], "step": "createSparseSlice (all blocks) + compute (all blocks)" if wl["kind"] == "spmdm" else "execute"},
         "hbm_gbs": res["step_bytes"] * world / (ms_per_step * 1e6),
