@@ -45,6 +45,26 @@ void set_error(int code, const char* fmt, ...)
 }
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+void ensure_smem_optin(const void* kernel, int bytes)
+{
+  static std::mutex mtx;
+  static std::map<std::pair<const void*, int>, int> done;     // (kernel, device) -> bytes granted
+  int dev = 0;
+  if (cudaSuccess != cudaGetDevice(&dev)) { (void)cudaGetLastError(); return; }
+  std::lock_guard<std::mutex> lock(mtx);
+  int& have = done[std::make_pair(kernel, dev)];
+  if (have >= bytes) return;
+  XB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  have = bytes;
+}
+
+int device_sm_count()
+{
+  int dev = 0, sms = 0;
+  if (cudaSuccess != cudaGetDevice(&dev) || cudaSuccess != cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) { (void)cudaGetLastError(); return 148; }
+  return sms > 0 ? sms : 148;
+}
 static std::atomic<const char*> g_last_compute("");
 void note_compute_kernel(const char* name) { g_last_compute.store(name, std::memory_order_relaxed); }
 

@@ -10,6 +10,10 @@ namespace xb {
 void set_error(int code, const char* fmt, ...);
 int verbosity();
 void count_launch(int n);
+// Opt-in to more than 48 KiB of dynamic shared memory, once per (kernel, device); callers may race (the legacy
+// *_thread entries are called from OpenMP regions) and a process may drive several devices.
+void ensure_smem_optin(const void* kernel, int bytes);
+int device_sm_count();
 void note_compute_kernel(const char* name);   // which spmdm compute / fsspmdm kernel the last call enqueued (reported by bench.py)
 
 #define XB_CUDA(call)                                                                      \

@@ -236,11 +236,7 @@ FsTc* fs_tc_build(int M, int K, int lda, int beta_one, const float* a_dense)
   int dev = 0; cudaDeviceProp prop;
   t->sms = 148;
   if (cudaSuccess == cudaGetDevice(&dev) && cudaSuccess == cudaGetDeviceProperties(&prop, dev)) t->sms = prop.multiProcessorCount;
-  static bool configured = false;
-  if (!configured) {
-    XB_CUDA(cudaFuncSetAttribute(fsspmdm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256)));
-    configured = true;
-  }
+  ensure_smem_optin((const void*)fsspmdm_tc_kernel, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256));
   return t;
 }
 

@@ -309,11 +309,7 @@ bool launch_compute_tc(const ComputeArgs& a, cudaStream_t stream)
     if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.g.k, (unsigned long long)a.ncols, (unsigned long long)a.ldb * 4, 32, TC_BN, false)) return false;
   }
   else if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 4, 32, TC_KC, true)) return false;
-  static bool configured = false;
-  if (!configured) {
-    XB_CUDA(cudaFuncSetAttribute(spmdm_compute_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    configured = true;
-  }
+  ensure_smem_optin((const void*)spmdm_compute_tc_kernel, TC_SMEM_BYTES);
   const int tiles_per_mb = (a.g.bm + TC_BM - 1) / TC_BM;
   const dim3 grid((unsigned)((a.ncols + TC_BN - 1) / TC_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);

@@ -252,11 +252,7 @@ bool launch_compute_tc16(const ComputeArgs& a, cudaStream_t stream)
     if (!make_tensor_map_2d_sw128(&map, a.b, 2, (unsigned long long)a.g.k, (unsigned long long)a.ncols, (unsigned long long)a.ldb * 2, 64, T16_BN, false)) return false;
   }
   else if (!make_tensor_map_2d_sw128(&map, a.b, 2, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 2, 64, T16_KH, false)) return false;
-  static bool configured = false;
-  if (!configured) {
-    XB_CUDA(cudaFuncSetAttribute(spmdm_compute_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM_BYTES));
-    configured = true;
-  }
+  ensure_smem_optin((const void*)spmdm_compute_tc16_kernel, T16_SMEM_BYTES);
   const int tiles_per_mb = (a.g.bm + T16_BM - 1) / T16_BM;
   const dim3 grid((unsigned)((a.ncols + T16_BN - 1) / T16_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);

@@ -426,14 +426,8 @@ bool launch_compute_tc16p(const ComputeArgs& a, cudaStream_t stream)
     if (!make_tensor_map_2d_sw128(&map, a.b, 2, (unsigned long long)a.g.k, (unsigned long long)a.ncols, (unsigned long long)a.ldb * 2, 64, P_BNH, false)) return false;
   }
   else if (!make_tensor_map_2d_sw128(&map, a.b, 2, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 2, 64, P_KH, false)) return false;
-  static int pairs_max = 0;
-  if (0 == pairs_max) {
-    int dev = 0, sms = 0;
-    XB_CUDA(cudaGetDevice(&dev));
-    XB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    XB_CUDA(cudaFuncSetAttribute(spmdm_compute_tc16p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    pairs_max = sms / 2 > 0 ? sms / 2 : 1;
-  }
+  ensure_smem_optin((const void*)spmdm_compute_tc16p_kernel, P_SMEM_BYTES);
+  const int pairs_max = device_sm_count() / 2 > 0 ? device_sm_count() / 2 : 1;
   const int tiles_per_mb = (a.g.bm + P_BM - 1) / P_BM;
   const int pair_m = (a.mb_count * tiles_per_mb + 1) / 2;
   const int total = pair_m * ((a.ncols + P_BN - 1) / P_BN);

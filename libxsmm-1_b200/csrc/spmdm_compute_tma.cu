@@ -348,11 +348,7 @@ static bool launch_tma_variant(const ComputeArgs& a, cudaStream_t stream)
   if (!make_tensor_map_2d(&map, a.b, ESZ, (unsigned long long)a.ncols, (unsigned long long)a.g.k,
                           (unsigned long long)a.ldb * ESZ, BN, 128)) return false;
   auto kern = spmdm_compute_tma_kernel<BF16, VEC, R, CW, STAGES, PARTIAL>;
-  static bool configured = false;
-  if (!configured) {
-    XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  ensure_smem_optin((const void*)kern, (int)smem);
   const int tiles_per_mb = (a.g.bm + TM - 1) / TM;
   const dim3 grid((unsigned)((a.ncols + BN - 1) / BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
@@ -368,8 +364,7 @@ bool launch_compute_tma(const ComputeArgs& a, bool partial, cudaStream_t stream)
 {
   if (a.transb || a.transc) return false;
   if (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3)) return false;
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("LIBXSMM_B200_K2_VARIANT"); variant = (e && *e) ? atoi(e) : 0; }
+  static const int variant = [] { const char* e = getenv("LIBXSMM_B200_K2_VARIANT"); return (e && *e) ? atoi(e) : 0; }();
   if (partial) {   // at most bn - 1 columns: one narrow column tile, many short row tiles
     return a.is_bf16 ? launch_tma_variant<true, 4, 4, 8, 4, true>(a, stream) : launch_tma_variant<false, 2, 4, 8, 4, true>(a, stream);
   }

@@ -481,8 +481,7 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
     const int rpw = (args.g.bm + K1N_WARPS - 1) / K1N_WARPS;
     if (args.is_bf16 && full && !args.origin_is_block && 0 == (args.lda & 7) && 0 == ((uintptr_t)args.a & 15) && 0 == (args.g.k & 7)) {
       // complete 128-column blocks, 16-byte aligned rows: the wide kernel (a lane holds 8 elements)
-      static int wide = -1;
-      if (wide < 0) { const char* e = getenv("LIBXSMM_B200_K1_WIDE"); wide = (e && '0' == *e) ? 0 : 1; }
+      static const int wide = [] { const char* e = getenv("LIBXSMM_B200_K1_WIDE"); return (e && '0' == *e) ? 0 : 1; }();
       if (wide) {
         if (rpw <= 8) spmdm_slice_bf16w_kernel<8><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
         else spmdm_slice_bf16w_kernel<16><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
@@ -491,8 +490,7 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
       }
     }
     if (args.is_bf16) {
-      static int keep16 = -1;
-      if (keep16 < 0) { const char* e = getenv("LIBXSMM_B200_K1_KEEP"); keep16 = (e && '1' == *e) ? 1 : 0; }
+      static const int keep16 = [] { const char* e = getenv("LIBXSMM_B200_K1_KEEP"); return (e && '1' == *e) ? 1 : 0; }();
       if (rpw <= 8) launch_slice_n<true, 8, true>(args, nslices, full, stream);
       else if (keep16) launch_slice_n<true, 16, true>(args, nslices, full, stream);
       else launch_slice_n<true, 16, false>(args, nslices, full, stream);
@@ -793,11 +791,7 @@ static void launch_compute_variant(const ComputeArgs& a, cudaStream_t stream)
   const size_t cstage = (size_t)TM * (BN + 1) * 4;
   const size_t smem = tiles > cstage ? tiles : cstage;
   auto kern = spmdm_compute_kernel<BF16, PARTIAL, RPW>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  ensure_smem_optin((const void*)kern, (int)smem);
   const int tiles_per_mb = (a.g.bm + TM - 1) / TM;
   const dim3 grid((unsigned)((a.ncols + BN - 1) / BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
