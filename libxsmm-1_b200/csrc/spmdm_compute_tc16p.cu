@@ -376,7 +376,7 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
             }
           }
         }
-        if (!p.transc) {   // thread = row: 16-byte streaming stores (a lane-transposed, line-per-instruction variant measured 6 % slower)
+        if (!p.transc) {   // thread = row: 16-byte streaming stores (measured slower: a lane-transposed line-per-instruction variant, +6 %; 32-byte STG.256 stores, +4 %)
           if (row < t.rows) {
             float* dst = p.c + crow * p.ldc + t.n0 + cb;
 #pragma unroll
