@@ -13,7 +13,7 @@
 //   * 3xTF32: operator hi/lo split once at create time; b_lo = b - trunc(b) by the worker warps per tile.
 //   * accumulator [128 lanes = columns][M_pad TMEM columns], double buffered: the epilogue of tile t (tcgen05.ld:
 //     thread = panel column, registers = operator rows -> every store instruction writes one full 128-byte line
-//     of a C row) overlaps the MMAs of tile t+1.
+//     of a C row) overlaps the MMAs of tile t+1.  22 warps: TMA, MMA, four for b_lo, sixteen for the epilogue.
 // Not the reference's rounding sequence; contract 1e-5 relative (observed ~2e-6; at most 24 accumulations).
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -24,8 +24,9 @@ namespace xb {
 
 constexpr int FT_BN = 128;                  // panel columns per tile (UMMA M)
 constexpr int FT_STAGES = 2;
-constexpr int FT_WORKERS = 4;               // worker warps = the four TMEM lane quarters
-constexpr int FT_THREADS = (2 + FT_WORKERS) * 32;
+constexpr int FT_WORKERS = 4;               // warps that write b_lo for the next tile
+constexpr int FT_EPI = 16;                  // epilogue warps: four per TMEM lane quarter, taking the 32-row chunks of the operator in turn
+constexpr int FT_THREADS = (2 + FT_WORKERS + FT_EPI) * 32;
 constexpr int FT_STAGE_HALF = 64 * FT_BN * 4;          // 32 KiB: 64 k x 128 columns fp32 (raw); the lo copy follows
 constexpr int FT_SMEM_B = 0;                           // stages: raw | lo
 constexpr int FT_SMEM_OP = FT_STAGES * 2 * FT_STAGE_HALF;   // operator: chunk 0 hi, chunk 1 hi, chunk 0 lo, chunk 1 lo (M_pad x 128 B each)
@@ -60,7 +61,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       mbar_init(&b_full[i], 1); mbar_init(&b_split[i], FT_WORKERS); mbar_init(&b_free[i], 1);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], FT_WORKERS);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], FT_EPI);
     }
     mbar_fence_init();
   }
@@ -87,6 +88,12 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
         unsigned char* dst = smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF;
 #pragma unroll
         for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * (64 * 128), &tmB, (int)(t * FT_BN) + 32 * j, 0, &b_full[s]);
+        // the tile this CTA will need after the two in flight: into L2 now (the ring is only two stages deep)
+        const long long tn = t + 2 * (long long)gridDim.x;
+        if (tn < ntiles) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_prefetch_l2_2d(&tmB, (int)(tn * FT_BN) + 32 * j, 0);
+        }
       }
     }
   }
@@ -119,67 +126,45 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
       }
     }
   }
-  else {
-    const int wt = tid - 64;                      // 0..127 = TMEM lane = column inside the tile
-    const int quarter = warp & 3;
+  else if (warp < 2 + FT_WORKERS) {
+    // ---------------- b_lo = b - trunc_tf32(b) for every tile (same swizzled addresses) ----------------
+    const int wt = tid - 64;                      // 0..127
     long long it = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int s = (int)(it & 1), ab = (int)(it & 1);
-      // (1) b_lo = b - trunc_tf32(b) for this tile (same swizzled addresses)
+      const int s = (int)(it & 1);
       mbar_wait(&b_full[s], (uint32_t)((it >> 1) & 1));
-      {
-        const uint4* src = (const uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF);
-        uint4* dst = (uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF + FT_STAGE_HALF);
+      const uint4* src = (const uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF);
+      uint4* dst = (uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF + FT_STAGE_HALF);
 #pragma unroll 4
-        for (int i = wt; i < FT_STAGE_HALF / 16; i += FT_WORKERS * 32) {
-          const uint4 b = src[i];
-          uint4 l;
-          l.x = __float_as_uint(__uint_as_float(b.x) - __uint_as_float(b.x & 0xFFFFE000u));
-          l.y = __float_as_uint(__uint_as_float(b.y) - __uint_as_float(b.y & 0xFFFFE000u));
-          l.z = __float_as_uint(__uint_as_float(b.z) - __uint_as_float(b.z & 0xFFFFE000u));
-          l.w = __float_as_uint(__uint_as_float(b.w) - __uint_as_float(b.w & 0xFFFFE000u));
-          dst[i] = l;
-        }
+      for (int i = wt; i < FT_STAGE_HALF / 16; i += FT_WORKERS * 32) {
+        const uint4 b = src[i];
+        uint4 l;
+        l.x = __float_as_uint(__uint_as_float(b.x) - __uint_as_float(b.x & 0xFFFFE000u));
+        l.y = __float_as_uint(__uint_as_float(b.y) - __uint_as_float(b.y & 0xFFFFE000u));
+        l.z = __float_as_uint(__uint_as_float(b.z) - __uint_as_float(b.z & 0xFFFFE000u));
+        l.w = __float_as_uint(__uint_as_float(b.w) - __uint_as_float(b.w & 0xFFFFE000u));
+        dst[i] = l;
       }
       fence_proxy_async();
       __syncwarp();
       if (0 == lane) mbar_arrive(&b_split[s]);
-      // (2) epilogue of the PREVIOUS tile while this tile's MMAs run
-      if (it > 0) {
-        const long long tp = t - gridDim.x;
-        const int pb = (int)((it - 1) & 1);
-        mbar_wait(&acc_full[pb], (uint32_t)(((it - 1) >> 1) & 1));
-        tc_fence_after();
-        const long long col = tp * FT_BN + quarter * 32 + lane;
-        for (int m0 = 0; m0 < p.M; m0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pb * 256 + m0), v);
-          if (col < p.ncols) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (m0 + j < p.M) {
-                float* dst = p.C + (long long)(m0 + j) * p.ldc + col;
-                const float r = __uint_as_float(v[j]);
-                __stcs(dst, p.beta_one ? (r + __ldcs(dst)) : r);
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (0 == lane) mbar_arrive(&acc_free[pb]);
-      }
     }
-    // (3) epilogue of the last tile
-    if (it > 0) {
-      const long long tp = (long long)blockIdx.x + (it - 1) * gridDim.x;
-      const int pb = (int)((it - 1) & 1);
-      mbar_wait(&acc_full[pb], (uint32_t)(((it - 1) >> 1) & 1));
+  }
+  else {
+    // ---------------- epilogue: thread = panel column, registers = operator rows ----------------
+    // A worker's instruction stream is one dependent chain of memory instructions (each tens of cycles next to the
+    // UMMA operand traffic), so the 150 row stores of a tile are spread over sixteen warps: four per TMEM
+    // lane quarter, taking the 32-row chunks in turn.
+    const int quarter = warp & 3, part = (warp - 2 - FT_WORKERS) >> 2;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int ab = (int)(it & 1);
+      mbar_wait(&acc_full[ab], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const long long col = tp * FT_BN + quarter * 32 + lane;
-      for (int m0 = 0; m0 < p.M; m0 += 32) {
+      const long long col = t * FT_BN + quarter * 32 + lane;
+      for (int m0 = 32 * part; m0 < p.M; m0 += 32 * (FT_EPI / 4)) {
         uint32_t v[32];
-        tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pb * 256 + m0), v);
+        tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * 256 + m0), v);
         if (col < p.ncols) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -192,6 +177,8 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
         }
       }
       tc_fence_before();
+      __syncwarp();
+      if (0 == lane) mbar_arrive(&acc_free[ab]);
     }
   }
   __syncthreads();

@@ -7,7 +7,7 @@ import bench
 xs = importlib.import_module("libxsmm-1_b200")
 for tc in ("1", "0"):
     os.environ["LIBXSMM_B200_FSSPMDM_TC"] = tc
-    for dens in (1.0, 0.5):
+    for dens in ([float(x) for x in sys.argv[1:]] or [1.0, 0.5]):
         wl = dict(bench.WORKLOADS["c5"], density=dens, n_unique=None, N=1 << 22)
         gen = bench.run_fs_gpu(xs, wl, 10, 3, 1, want_e2e=False)
         assert next(gen) == "ready"
