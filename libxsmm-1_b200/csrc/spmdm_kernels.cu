@@ -448,6 +448,9 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
         const uint32_t pm = lt & mymask;
         uint32_t q = rowpos + __popc(b0 & pm) + 2 * __popc(b1 & pm) + 4 * __popc(b2 & pm) + 8 * __popc(b3 & pm);
         const uint32_t v[4] = { w[it].x, w[it].y, w[it].z, w[it].w };
+        // xb_tc16_pack(r, hl * 8 + e, value) = value | (base16 + e): everything but e is fixed for this lane and row
+        const uint32_t rowm = (uint32_t)r & 127u;
+        const uint32_t base16 = ((uint32_t)(hl >> 3) << 15) | ((rowm >> 3) * 512u + (rowm & 7u) * 64u + ((((uint32_t)hl ^ rowm) & 7u) << 3));
         // one trip per kept element of the fullest lane (1-2 in the sparse regime) instead of eight predicated slots
         for (uint32_t mm = m; mm; mm &= mm - 1u, ++q) {
           const int e = __ffs((int)mm) - 1;
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
           const uint32_t vb = (e & 1) ? (pr & 0xFFFF0000u) : (pr << 16);
           co[q] = (uint16_t)(hl * 8 + e);
           va[q] = __uint_as_float(vb);
-          if (aux) rk[q] = xb_tc16_pack(r, hl * 8 + e, vb);
+          if (aux) rk[q] = vb | (base16 + (uint32_t)e);
         }
       }
       pos += lo_tot + hi_tot;
