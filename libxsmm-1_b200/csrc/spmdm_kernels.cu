@@ -357,19 +357,23 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
 __device__ __forceinline__ uint32_t k1w_mask8(uint4 w)
 {
   // per 16-bit half h (sign dropped): kept iff 1 <= h <= 0x7F80, i.e. nonzero and not NaN (ordered compare of the
-  // reference's vector loops: src/libxsmm_spmdm_begin_avx2.h:54); denormals and Inf kept, -0.0 dropped
-  uint32_t m = 0;
+  // reference's vector loops: src/libxsmm_spmdm_begin_avx2.h:54); denormals and Inf kept, -0.0 dropped.
+  // Carry arithmetic leaves the verdict of the low / high half in bit 15 / 31 of k; the eight verdict bits are then
+  // collected in column order with two byte permutes and a multiply (bit 7 of four bytes -> one nibble).
   const uint32_t v[4] = { w.x, w.y, w.z, w.w };
+  uint32_t k[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t t = v[i] & 0x7FFF7FFFu;
     const uint32_t nz = t + 0x7FFF7FFFu;          // bit 15 / 31 set iff the half is nonzero
     const uint32_t nan = t + 0x007F007Fu;         // bit 15 / 31 set iff the half is > 0x7F80
-    const uint32_t k = nz & ~nan & 0x80008000u;
-    m |= ((k >> 15) & 1u) << (2 * i);
-    m |= (k >> 31) << (2 * i + 1);
+    k[i] = nz & ~nan;
   }
-  return m;
+  const uint32_t r01 = __byte_perm(k[0], k[1], 0x7531);   // bytes holding bit 15 and 31 of k0, k1: elements 0..3
+  const uint32_t r23 = __byte_perm(k[2], k[3], 0x7531);   // elements 4..7
+  const uint32_t lo = (((r01 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+  const uint32_t hi = (((r23 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+  return lo | (hi << 4);
 }
 
 template <int ROWS>
@@ -438,15 +442,24 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
       const uint32_t m = (masks[it / 4] >> (8 * (it % 4))) & 255u;
       const uint32_t nm = __popc(m);      // 0..8
       const uint32_t b0 = __ballot_sync(0xffffffffu, nm & 1u), b1 = __ballot_sync(0xffffffffu, nm & 2u);
-      const uint32_t b2 = __ballot_sync(0xffffffffu, nm & 4u), b3 = __ballot_sync(0xffffffffu, nm & 8u);
-      const uint32_t lo_tot = __popc(b0 & 0xFFFFu) + 2 * __popc(b1 & 0xFFFFu) + 4 * __popc(b2 & 0xFFFFu) + 8 * __popc(b3 & 0xFFFFu);
-      const uint32_t hi_tot = __popc(b0 >> 16) + 2 * __popc(b1 >> 16) + 4 * __popc(b2 >> 16) + 8 * __popc(b3 >> 16);
+      uint32_t lo_tot = __popc(b0 & 0xFFFFu) + 2 * __popc(b1 & 0xFFFFu);
+      uint32_t hi_tot = __popc(b0 >> 16) + 2 * __popc(b1 >> 16);
+      // a lane keeping four or more of its eight elements is rare below ~20 % density: the two upper count bits are
+      // voted on only then (warp-uniform branch)
+      const bool big = 0 != __any_sync(0xffffffffu, nm >= 4u);
+      uint32_t b2 = 0, b3 = 0;
+      if (big) {
+        b2 = __ballot_sync(0xffffffffu, nm & 4u); b3 = __ballot_sync(0xffffffffu, nm & 8u);
+        lo_tot += 4 * __popc(b2 & 0xFFFFu) + 8 * __popc(b3 & 0xFFFFu);
+        hi_tot += 4 * __popc(b2 >> 16) + 8 * __popc(b3 >> 16);
+      }
       const uint32_t rowpos = pos + (half ? lo_tot : 0u);
       const int r = row_lo + 2 * it + half;
       if (0 == hl && r < row_hi) ro[r] = (uint16_t)rowpos;
       if (m) {   // few lanes hold nonzeros in the sparse regime
         const uint32_t pm = lt & mymask;
-        uint32_t q = rowpos + __popc(b0 & pm) + 2 * __popc(b1 & pm) + 4 * __popc(b2 & pm) + 8 * __popc(b3 & pm);
+        uint32_t q = rowpos + __popc(b0 & pm) + 2 * __popc(b1 & pm);
+        if (big) q += 4 * __popc(b2 & pm) + 8 * __popc(b3 & pm);
         const uint32_t v[4] = { w[it].x, w[it].y, w[it].z, w[it].w };
         // xb_tc16_pack(r, hl * 8 + e, value) = value | (base16 + e): everything but e is fixed for this lane and row
         const uint32_t rowm = (uint32_t)r & 127u;
