@@ -479,6 +479,125 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
   }
 }
 
+// K1x: the same with NW 16-byte words (8 * NW elements) per lane: a row is 16 / NW lanes and one iteration of the
+// positioning phase covers 2 * NW rows, which divides the number of ballot rounds per slice by NW (the kernel is
+// instruction-issue bound).  Same outputs, bit for bit.  Measured on C2: NW = 1 (K1w) 25.1 us, NW = 2 23.2 us, NW = 4 23.1 us (not instantiated).
+template <int ROWS, int NW>
+__global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16x_kernel(const SliceArgs p)
+{
+  constexpr int LPR = 16 / NW;               // lanes per row
+  constexpr int RPI = 32 / LPR;              // rows per iteration
+  constexpr int ITS = (ROWS + RPI - 1) / RPI;
+  constexpr int MB = 8 * NW;                 // mask bits per lane and iteration
+  __shared__ uint32_t wtot[K1N_WARPS];
+  const Geom& g = p.g;
+  const int s = p.slice0 + (int)blockIdx.x * p.slice_step;
+  const int kb = s / g.mb, mbi = s - kb * g.mb;
+  const int nrows = min(g.bm, g.m - mbi * g.bm);
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qr = lane / LPR, hl = lane % LPR;       // row inside the group, segment of the row
+  const int rpw = (g.bm + K1N_WARPS - 1) / K1N_WARPS;
+  const int row_lo = warp * rpw, row_hi = min(nrows, row_lo + rpw);
+  const long long origin = p.origin_is_block ? 0ll : ((long long)mbi * g.bm * p.lda + (long long)kb * g.bk);
+  const uint16_t* A = (const uint16_t*)p.a + origin + hl * (8 * NW);
+
+  // ---- phase 1: load, test, count ---------------------------------------------------------------------
+  uint4 w[ITS][NW];
+  uint32_t masks[ITS];
+#pragma unroll
+  for (int it = 0; it < ITS; ++it) {
+    const int r = row_lo + RPI * it + qr;
+    const uint4* src = (const uint4*)(A + (long long)r * p.lda);
+#pragma unroll
+    for (int j = 0; j < NW; ++j) w[it][j] = (r < row_hi) ? __ldg(src + j) : make_uint4(0, 0, 0, 0);
+  }
+  uint32_t mine = 0;
+#pragma unroll
+  for (int it = 0; it < ITS; ++it) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) m |= k1w_mask8(w[it][j]) << (8 * j);
+    masks[it] = m;
+    mine += __popc(m);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  if (0 == lane) wtot[warp] = mine;
+  __syncthreads();
+  uint32_t pos;
+  {
+    const uint32_t t = wtot[lane];
+    uint32_t inc = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += u;
+    }
+    pos = __shfl_sync(0xffffffffu, inc - t, warp);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (0 == tid) {
+      p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
+      p.out.slice_nnz[s] = total;
+      xb_publish_nnz(p, total);
+    }
+  }
+
+  // ---- phase 2: positions and stores -----------------------------------------------------------------------
+  uint16_t* ro = p.out.rowidx + (size_t)s * (g.bm + 1);
+  uint16_t* co = p.out.colidx + (size_t)s * g.bm * g.bk;
+  float* va = p.out.values + (size_t)s * g.bm * g.bk;
+  uint32_t* rk = p.out.tcpk + (size_t)s * g.bm * g.bk;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t rowmask = ((1u << LPR) - 1u) << (LPR * qr);   // the lanes of this lane's row
+  const uint32_t before = (1u << (LPR * qr)) - 1u;             // the lanes of the rows above it in the group
+  const bool aux = (0 != p.write_aux);
+#pragma unroll
+  for (int it = 0; it < ITS; ++it) {
+    if (row_lo + RPI * it < row_hi) {      // warp-uniform
+      const uint32_t m = masks[it];
+      const uint32_t nm = __popc(m);       // 0 .. 8 * NW
+      const uint32_t b0 = __ballot_sync(0xffffffffu, nm & 1u), b1 = __ballot_sync(0xffffffffu, nm & 2u);
+      // a lane keeping four or more of its elements is rare in the sparse regime: the upper count bits are voted on
+      // only then (warp-uniform branch)
+      const bool big = 0 != __any_sync(0xffffffffu, nm >= 4u);
+      uint32_t b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+      if (big) {
+        b2 = __ballot_sync(0xffffffffu, nm & 4u); b3 = __ballot_sync(0xffffffffu, nm & 8u);
+        b4 = __ballot_sync(0xffffffffu, nm & 16u); b5 = __ballot_sync(0xffffffffu, nm & 32u);
+      }
+      auto kept = [&](uint32_t lanes) -> uint32_t {     // kept elements held by the given lanes
+        uint32_t c = __popc(b0 & lanes) + 2 * __popc(b1 & lanes);
+        if (big) c += 4 * __popc(b2 & lanes) + 8 * __popc(b3 & lanes) + 16 * __popc(b4 & lanes) + 32 * __popc(b5 & lanes);
+        return c;
+      };
+      const uint32_t rowpos = pos + kept(before);
+      const int r = row_lo + RPI * it + qr;
+      if (0 == hl && r < row_hi) ro[r] = (uint16_t)rowpos;
+      if (m) {   // few lanes hold nonzeros in the sparse regime
+        uint32_t q = rowpos + kept(lt & rowmask);
+        const uint32_t rowm = (uint32_t)r & 127u;
+        const uint32_t k0 = (uint32_t)hl * (8u * NW);                  // first column of this lane
+        const uint32_t rbase = ((k0 >> 6) << 15) | ((rowm >> 3) * 512u + (rowm & 7u) * 64u);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {             // the lane's 16-byte words: k = k0 + 8 * j + e
+          const uint32_t v[4] = { w[it][j].x, w[it][j].y, w[it][j].z, w[it][j].w };
+          // xb_tc16_pack(r, k, value) = value | (base16 + e): everything but e is fixed for this lane, row and word
+          const uint32_t base16 = rbase | (((((k0 >> 3) + (uint32_t)j) ^ rowm) & 7u) << 3);
+          for (uint32_t mm = (m >> (8 * j)) & 0xFFu; mm; mm &= mm - 1u, ++q) {
+            const int e = __ffs((int)mm) - 1;
+            const uint32_t pr = (e & 4) ? ((e & 2) ? v[3] : v[2]) : ((e & 2) ? v[1] : v[0]);
+            const uint32_t vb = (e & 1) ? (pr & 0xFFFF0000u) : (pr << 16);
+            co[q] = (uint16_t)(k0 + 8u * j + (uint32_t)e);
+            va[q] = __uint_as_float(vb);
+            if (aux) rk[q] = vb | (base16 + (uint32_t)e);
+          }
+        }
+      }
+      pos += kept(0xFFFFFFFFu);
+    }
+  }
+}
+
 template <bool BF16, int ROWS, bool KEEP>
 static void launch_slice_n(const SliceArgs& args, int nslices, bool full, cudaStream_t stream)
 {
@@ -497,7 +616,13 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
     const int rpw = (args.g.bm + K1N_WARPS - 1) / K1N_WARPS;
     if (args.is_bf16 && full && !args.origin_is_block && 0 == (args.lda & 7) && 0 == ((uintptr_t)args.a & 15) && 0 == (args.g.k & 7)) {
       // complete 128-column blocks, 16-byte aligned rows: the wide kernel (a lane holds 8 elements)
-      static const int wide = [] { const char* e = getenv("LIBXSMM_B200_K1_WIDE"); return (e && '0' == *e) ? 0 : 1; }();
+      static const int wide = [] { const char* e = getenv("LIBXSMM_B200_K1_WIDE"); return (e && *e >= '0' && *e <= '2') ? (*e - '0') : 2; }();
+      if (wide >= 2) {      // two 16-byte words per lane (default; LIBXSMM_B200_K1_WIDE=1: one word, =0: the generic kernel)
+        if (rpw <= 8) spmdm_slice_bf16x_kernel<8, 2><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+        else spmdm_slice_bf16x_kernel<16, 2><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+        XB_CUDA(cudaGetLastError());
+        return;
+      }
       if (wide) {
         if (rpw <= 8) spmdm_slice_bf16w_kernel<8><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
         else spmdm_slice_bf16w_kernel<16><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
