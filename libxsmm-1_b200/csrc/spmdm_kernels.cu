@@ -616,7 +616,8 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
     const int rpw = (args.g.bm + K1N_WARPS - 1) / K1N_WARPS;
     if (args.is_bf16 && full && !args.origin_is_block && 0 == (args.lda & 7) && 0 == ((uintptr_t)args.a & 15) && 0 == (args.g.k & 7)) {
       // complete 128-column blocks, 16-byte aligned rows: the wide kernel (a lane holds 8 elements)
-      static const int wide = [] { const char* e = getenv("LIBXSMM_B200_K1_WIDE"); return (e && *e >= '0' && *e <= '2') ? (*e - '0') : 2; }();
+      const char* wenv = getenv("LIBXSMM_B200_K1_WIDE");      // developer switch, read per call (tests flip it)
+      const int wide = (wenv && *wenv >= '0' && *wenv <= '2') ? (*wenv - '0') : 2;
       if (wide >= 2) {      // two 16-byte words per lane (default; LIBXSMM_B200_K1_WIDE=1: one word, =0: the generic kernel)
         if (rpw <= 8) spmdm_slice_bf16x_kernel<8, 2><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
         else spmdm_slice_bf16x_kernel<16, 2><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);

@@ -139,6 +139,37 @@ def test_special_values_in_a(gpu, oracle):
     np.testing.assert_array_equal(C[ok].view(np.uint32), OC[ok].view(np.uint32))
 
 
+@pytest.mark.parametrize("wide", ["2", "1", "0"])
+def test_special_values_bf16_wide_slicing(gpu, oracle, monkeypatch, wide):
+    """bf16 bit patterns through the slicing kernels for complete, aligned blocks (two / one 16-byte word per lane,
+    generic): +-0, NaN with either sign, +-Inf, denormals, the largest finite value, dense and empty lanes and rows --
+    kept iff ordered-nonzero like the reference's vector loops (quirk Q3).  Slices bit for bit against the oracle."""
+    monkeypatch.setenv("LIBXSMM_B200_K1_WIDE", wide)
+    M, N, K = 600, 48, 256           # two complete k-blocks, row pitch 512 B; two row blocks (512 + 88 rows)
+    rng = np.random.default_rng(11)
+    bits = np.where(rng.random((M, K)) < 0.05, rng.integers(1, 0x7F80, (M, K)), 0).astype(np.uint16)
+    bits[rng.random((M, K)) < 0.02] |= 0x8000                      # negative values and -0.0
+    special = np.array([0x0000, 0x8000, 0x7FC0, 0xFFC1, 0x7F81, 0x7F80, 0xFF80, 0x0001, 0x8001, 0x7F7F, 0xFF7F, 0x0080], np.uint16)
+    idx = rng.integers(0, M * K, 4000)
+    bits.reshape(-1)[idx] = special[rng.integers(0, len(special), len(idx))]
+    bits[3, :] = 0x3F80              # a completely dense row
+    bits[4, 16:32] = 0x4000          # one completely dense lane (two-word kernel) next to empty ones
+    bits[5, :] = 0                   # an empty row
+    bits[511, 120:128] = 0xC000      # last lane of the last row of the first block
+    A = np.ascontiguousarray(bits)
+    B = gpu.workloads.to_bf16_bits(rng.random((K, N)).astype(np.float32))
+    C0 = rng.random((M, N)).astype(np.float32)
+    g, sl, C = gpu_spmdm(gpu, A, B, C0, M, N, K, beta=0, bf16=True)
+    og, osl, OC = oracle_spmdm(oracle, g, A, B, C0, "N", "N", "N", 0.0)
+    nnz = valid_slices_equal(og, sl, osl)
+    keep = ((bits & 0x7FFF) >= 1) & ((bits & 0x7FFF) <= 0x7F80)
+    assert nnz == int(keep.sum())
+    ok = ~np.isnan(OC)
+    np.testing.assert_array_equal(np.isnan(C), np.isnan(OC))
+    np.testing.assert_array_equal(C[ok].view(np.uint32), OC[ok].view(np.uint32))
+    gpu.check()
+
+
 def test_all_zero_and_dense_wrap(gpu, oracle):
     """empty A; and a fully dense 512 x 128 slice whose u16 counter wraps to 0 like the reference's
     (quirk Q4, template :72): row pointers are compared modulo 2^16."""
