@@ -71,10 +71,10 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
 
   if (0 == tid) {
 #pragma unroll
-    for (int i = 0; i < TC_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_split[i], TC_WORKERS); mbar_init(&b_free[i], 1); }
+    for (int i = 0; i < TC_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_split[i], HIST ? TC_WORKERS / 2 : TC_WORKERS); mbar_init(&b_free[i], 1); }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_ready[i], TC_WORKERS); mbar_init(&a_free[i], 1);
+      mbar_init(&a_ready[i], HIST ? TC_WORKERS / 2 : TC_WORKERS); mbar_init(&a_free[i], 1);
       mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_WORKERS);
     }
     mbar_fence_init();
@@ -152,8 +152,14 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
   }
   else {
     // ---------------- workers: densify A, split B, drain accumulators, epilogue ----------------
-    const int w = warp - 2;                       // 0..7
-    const int wt = tid - 64;                      // 0..255
+    const int w = warp - 2;                       // 0..15
+    // HIST (sparse) variant: the sixteen worker warps split the per-step jobs -- warps 0-7 rebuild the A half, warps
+    // 8-15 write b_lo -- and all of them drain; a worker's instruction stream is one dependent chain of memory
+    // instructions, so two shorter chains side by side beat one long one.  The dense variant keeps all sixteen on
+    // every job (the rebuild of a dense half needs all the threads it can get).
+    constexpr int DW = HIST ? TC_WT / 2 : TC_WT;  // threads on the densify job / on the split job
+    const bool do_dens = !HIST || w < TC_WORKERS / 2, do_split = !HIST || w >= TC_WORKERS / 2;
+    const int wt = HIST ? ((tid - 64) & (DW - 1)) : (tid - 64);   // index within the job's threads
     const size_t cap = (size_t)g.bm * g.bk;
     // this thread's part of the output: row (quarter*32 + lane), 32 columns; warp w may touch TMEM lanes
     // 32*(w%4) .. +31, and the four warps that share a lane quarter take 32 columns each
@@ -190,16 +196,17 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
       if (last < first) last = (int)__ldg(ro + tile_rows - 1);   // wrapped u16 counter of a full slice: last row reads as empty
 #pragma unroll
       for (int i = 0; i < TC_NQ; ++i) {
-        const int q = first + wt + i * TC_WT;
+        const int q = first + wt + i * DW;
         pk[i] = 0; vv[i] = 0.f;
         if (q < last) { pk[i] = (uint32_t)__ldg(ri + q); vv[i] = __ldg(va + q); }
       }
     };
-    fetch(0);
+    if (do_dens) fetch(0);
     for (int t = 0; t < nsteps; ++t) {
       const int kb = t >> 1, h = t & 1;
       // (1) A half: wait until the MMAs that read this buffer (previous k-block) are done, zero, scatter.
       //     The other half is being multiplied meanwhile.
+      if (do_dens) {
       if (kb > 0) mbar_wait(&a_free[h], (kb - 1) & 1);
       unsigned char* abuf = smem + TC_SMEM_A + h * TC_A_HALF;
       // The half still holds the same half of the previous k-block.  If all of that k-block's nonzeros were in
@@ -207,12 +214,12 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
       // 64 KiB wipe that competes with the operand reads for shared memory); otherwise the half is wiped.
       bool wipe = true;
       if constexpr (HIST) {
-        if (kb > 0 && n_prev <= TC_NQ * TC_WT) {
+        if (kb > 0 && n_prev <= TC_NQ * DW) {
           wipe = false;
 #pragma unroll
           for (int i = 0; i < TC_NQ; ++i) {
-            if (i * TC_WT >= n_prev) break;                     // uniform
-            if (wt + i * TC_WT < n_prev && (int)((hk[i] >> 15) & 1u) == h) {
+            if (i * DW >= n_prev) break;                     // uniform
+            if (wt + i * DW < n_prev && (int)((hk[i] >> 15) & 1u) == h) {
               const uint32_t off = (hk[i] & 0x7FFFu) << 2;
               *(float*)(abuf + off) = 0.f;
               *(float*)(abuf + 2 * TC_A_CHUNK + off) = 0.f;
@@ -223,9 +230,9 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
       if (wipe) {
         uint4* z = (uint4*)abuf;
 #pragma unroll
-        for (int i = 0; i < TC_A_HALF / 16 / TC_WT; ++i) z[wt + i * TC_WT] = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < TC_A_HALF / 16 / DW; ++i) z[wt + i * DW] = make_uint4(0, 0, 0, 0);
       }
-      asm volatile("bar.sync 1, %0;\n" ::"n"(TC_WT) : "memory");   // clearing complete before the scatter (another thread may write there)
+      asm volatile("bar.sync 1, %0;\n" ::"n"(DW) : "memory");   // clearing complete before the scatter (another thread may write there)
       auto put = [&](uint32_t t, float v) {   // t = xb_tc_pack(row, k): half in bit 15, word offset below
         if ((int)((t >> 15) & 1u) == h) {
           const uint32_t off = (t & 0x7FFFu) << 2;
@@ -236,15 +243,15 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
       };
 #pragma unroll
       for (int i = 0; i < TC_NQ; ++i) {
-        const int q = first + wt + i * TC_WT;
+        const int q = first + wt + i * DW;
         if (q < last) put(pk[i], vv[i]);
       }
-      if (first + TC_NQ * TC_WT < last) {   // denser than TC_NQ*TC_WT nonzeros per tile: the rest straight from memory
+      if (first + TC_NQ * DW < last) {   // denser than TC_NQ*DW nonzeros per tile: the rest straight from memory
         const int sidx = kb * g.mb + mbi;
         const uint16_t* ri = p.sl.tcoff + sidx * cap;
         const float* va = p.sl.values + sidx * cap;
 #pragma unroll 2
-        for (int q = first + wt + TC_NQ * TC_WT; q < last; q += TC_WT) put((uint32_t)__ldg(ri + q), __ldg(va + q));
+        for (int q = first + wt + TC_NQ * DW; q < last; q += DW) put((uint32_t)__ldg(ri + q), __ldg(va + q));
       }
       fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
@@ -257,7 +264,9 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
         }
       }
       if (1 == h && kb + 1 < g.kb) fetch(kb + 1);   // registers are free again: next k-block's nonzeros, consumed a step later
+      }
       // (2) the two B chunks of this step: b_lo = b - trunc_tf32(b), same (swizzled) addresses
+      if (do_split) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int c = 2 * t + j, s = c % TC_NB;
@@ -265,18 +274,19 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
         const uint4* src = (const uint4*)(smem + TC_SMEM_B + s * 2 * TC_B_CHUNK);
         uint4* dst = (uint4*)(smem + TC_SMEM_B + s * 2 * TC_B_CHUNK + TC_B_CHUNK);
 #pragma unroll
-        for (int i = 0; i < TC_B_CHUNK / 16 / TC_WT; ++i) {
-          const uint4 b = src[wt + i * TC_WT];
+        for (int i = 0; i < TC_B_CHUNK / 16 / DW; ++i) {
+          const uint4 b = src[wt + i * DW];
           uint4 l;
           l.x = __float_as_uint(__uint_as_float(b.x) - __uint_as_float(b.x & 0xFFFFE000u));
           l.y = __float_as_uint(__uint_as_float(b.y) - __uint_as_float(b.y & 0xFFFFE000u));
           l.z = __float_as_uint(__uint_as_float(b.z) - __uint_as_float(b.z & 0xFFFFE000u));
           l.w = __float_as_uint(__uint_as_float(b.w) - __uint_as_float(b.w & 0xFFFFE000u));
-          dst[wt + i * TC_WT] = l;
+          dst[wt + i * DW] = l;
         }
         fence_proxy_async();
         __syncwarp();
         if (0 == lane) mbar_arrive(&b_split[s]);
+      }
       }
       // (3) drain the previous k-block's accumulator while this k-block's MMAs run
       if (0 == h && kb > 0) drain(kb - 1);
