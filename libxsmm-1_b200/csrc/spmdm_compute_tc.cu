@@ -350,7 +350,8 @@ bool launch_compute_tc(const ComputeArgs& a, cudaStream_t stream)
   }
   else if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 4, 32, TC_KC, true)) return false;
   // performance-only choice (both instantiations are complete): the host's estimate is one call old at most
-  const bool sparse_variant = a.density_hint >= 0.f && a.density_hint < 0.25f;
+  bool sparse_variant = a.density_hint >= 0.f && a.density_hint < 0.25f;
+  { const char* e = getenv("LIBXSMM_B200_K4_VARIANT"); if (e && 's' == *e) sparse_variant = true; else if (e && 'd' == *e) sparse_variant = false; }   // developer switch
   ensure_smem_optin(sparse_variant ? (const void*)spmdm_compute_tc_kernel<8, true> : (const void*)spmdm_compute_tc_kernel<16, false>, TC_SMEM_BYTES);
   const int tiles_per_mb = (a.g.bm + TC_BM - 1) / TC_BM;
   const dim3 grid((unsigned)((a.ncols + TC_BN - 1) / TC_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
