@@ -97,13 +97,27 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
       }
     }
   }
-  else {  // A stored k x m: consecutive rows of the slice are contiguous in memory
-    for (int idx = tid; idx < ncols * K1_R; idx += K1_THREADS) {
-      const int k = idx / K1_R, r = idx - k * K1_R;
-      if (r < rcount) {
-        const long long at = origin + (long long)k * p.lda + r0 + r;
-        tile[k * K1_TPITCH + r] = p.is_bf16 ? ((uint32_t)__ldg((const uint16_t*)p.a + at) << 16)
-                                            : __float_as_uint(__ldg((const float*)p.a + at));
+  else {  // A stored k x m: consecutive rows of the slice are contiguous in memory: four of them per load
+    const size_t esz = p.is_bf16 ? 2 : 4;
+    const bool vec = (0 == (p.lda & 3)) && (0 == (((uintptr_t)p.a + (size_t)(origin + r0) * esz) & (p.is_bf16 ? 7 : 15)));
+    for (int idx = tid; idx < ncols * (K1_R / 4); idx += K1_THREADS) {
+      const int k = idx / (K1_R / 4), r = (idx - k * (K1_R / 4)) * 4;
+      const long long at = origin + (long long)k * p.lda + r0 + r;
+      uint32_t* dst = &tile[k * K1_TPITCH + r];
+      if (vec && r + 3 < rcount) {
+        if (p.is_bf16) {
+          const uint2 raw = __ldg((const uint2*)((const uint16_t*)p.a + at));
+          dst[0] = raw.x << 16; dst[1] = raw.x & 0xFFFF0000u; dst[2] = raw.y << 16; dst[3] = raw.y & 0xFFFF0000u;
+        }
+        else {
+          const uint4 raw = __ldg((const uint4*)((const float*)p.a + at));
+          dst[0] = raw.x; dst[1] = raw.y; dst[2] = raw.z; dst[3] = raw.w;
+        }
+      }
+      else {
+        for (int e = 0; e < 4; ++e) {
+          if (r + e < rcount) dst[e] = p.is_bf16 ? ((uint32_t)__ldg((const uint16_t*)p.a + at + e) << 16) : __float_as_uint(__ldg((const float*)p.a + at + e));
+        }
       }
     }
   }
