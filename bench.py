@@ -66,6 +66,21 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_pipe_info(res):
+    """The tensor-core kernels multiply the DENSIFIED slices: their own pipe utilisation, for the reader -- the roofline
+    of the line stays the algorithmic (HBM) one of the sparse product.  bf16: one kind::f16 MMA per product; fp32: three
+    kind::tf32 MMAs (3xTF32) at half the bf16 rate."""
+    name = res.get("kernel_name", "")
+    if not name.startswith("spmdm_compute_tc") or not res.get("dense_flops"):
+        return None
+    tp, tsrc = tensor_peak()
+    bf16 = name.startswith("spmdm_compute_tc16")
+    ex = (1.0 if bf16 else 3.0) * res["dense_flops"] / (res["kernel_ms"] * 1e9)
+    peak = tp if bf16 else 0.5 * tp
+    return {"executed_dense_tflops": ex, "peak_tflops": peak, "frac": ex / peak, "peak_source": tsrc + ("" if bf16 else " x 0.5 (tf32)"),
+            "note": ("kind::f16 MMAs" if bf16 else "3 x kind::tf32 MMAs") + " over the densified A tile; executed, not algorithmic, flops"}
+
+
 def bind_to_gpu_numa_node(local_rank):
     """N > 1 ranks share one host: run this rank (and first-touch its page-locked buffers) on the CPUs NVML reports as
     local to its GPU, what `numactl` would do for a multi-GPU job.  Best effort; returns a note for the JSON line."""
@@ -518,13 +533,9 @@ def main():
                      "kernel_ms": res["kernel_ms"], "parts": res["parts"]},
         "clocks": clocks,
     }
-    if res["kernel_name"].startswith("spmdm_compute_tc16") and res.get("dense_flops"):
-        # the bf16 tensor-core kernels multiply the densified slices: their own pipe utilisation, for the reader --
-        # the roofline above stays the algorithmic (HBM) one of the sparse product
-        tp, tsrc = tensor_peak()
-        ex = res["dense_flops"] / (res["kernel_ms"] * 1e9)
-        line["roofline"]["tensor_pipe"] = {"executed_dense_tflops": ex, "peak_tflops": tp, "frac": ex / tp, "peak_source": tsrc,
-                                           "note": "kind::f16 MMAs over the densified A tile; executed, not algorithmic, flops"}
+    tpipe = tensor_pipe_info(res)
+    if tpipe:
+        line["roofline"]["tensor_pipe"] = tpipe
     if e2e is not None:
         e_ms = e2e["e2e_ms"] / args.steps
         line["e2e"] = {"value": e2e["flops_all"] / (e_ms * 1e6), "unit": "GFLOP/s", "ms_per_step": e_ms,
@@ -550,6 +561,9 @@ def main():
                 others[name] = {"workload": WORKLOADS[name.split("@")[0]]["desc"] + (" [LIBXSMM_B200_SPMDM_TC=0]" if forced else ""), "value": r2["flops"] / (ms2 * 1e6), "unit": "GFLOP/s", "ms_per_step": ms2,
                                 "hbm_gbs": r2["step_bytes"] / (ms2 * 1e6), "kernel": r2["kernel_name"], "kernel_ms": r2["kernel_ms"],
                                 "kernel_hbm_gbs": ach2, "kernel_hbm_frac": ach2 / peak, "parts": r2["parts"], "gpu_launches": r2["launches"]}
+                tp2 = tensor_pipe_info(r2)
+                if tp2:
+                    others[name]["tensor_pipe"] = tp2
             except Exception as ex:      # a secondary workload must never take the headline down
                 others[name] = {"error": repr(ex)[:200]}
                 xs.clear_error()
