@@ -94,6 +94,8 @@ struct SpmdmCtx {
   unsigned long long* d_nnz;      // device view of the same word
   unsigned long long* d_acc;      // device counters {sum, slices done}
   bool aux_written;               // the auxiliary per-nonzero words of the current slices are valid
+  bool dense_written;             // ... and so is their dense tile image
+  size_t dense_bytes;
 };
 
 // 0 unknown (first call), 1 sparse, 2 dense according to the last completed slicing pass and the thresholds of
@@ -106,6 +108,12 @@ static int density_hint(const SpmdmCtx* c, int is_bf16, bool transb, bool transc
   return ((double)n < thr) ? 1 : 2;   // either way the result is correct; a wrong guess only costs speed for one call
 }
 
+static float density_estimate(const SpmdmCtx* c)
+{
+  const unsigned long long n = c->h_nnz ? *(volatile unsigned long long*)c->h_nnz : ~0ull;
+  return (~0ull == n) ? -1.f : (float)((double)n / ((double)c->g.m * (double)c->g.k));
+}
+
 static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole)
 {
   a->acc = c->d_acc; a->host_total = c->d_nnz; a->total_slices = c->g.mb * c->g.kb;
@@ -115,12 +123,25 @@ static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole)
   a->write_aux = skip ? 0 : 1;
   if (whole) c->aux_written = (0 != a->write_aux);
   else c->aux_written = true;
-}
-
-static float density_estimate(const SpmdmCtx* c)
-{
-  const unsigned long long n = c->h_nnz ? *(volatile unsigned long long*)c->h_nnz : ~0ull;
-  return (~0ull == n) ? -1.f : (float)((double)n / ((double)c->g.m * (double)c->g.k));
+  // Dense tile image for the tensor-core kernel (fp32, A stored m x k, complete k-blocks, 16-byte aligned rows): written
+  // unless the last pass showed a matrix so sparse (< 1 %) that the CUDA-core kernels will multiply it whatever the
+  // orientation of B and C.  Costs ~4 us of extra stores per 2048^2 and takes 50-90 us off the multiply.  Allocated and
+  // zeroed on first use (rows and columns of partial tiles are never written and stay zero).
+  a->write_dense = 0;
+  if (whole && !is_bf16 && !a->transa && 0 == (c->g.k % 128) && c->simd_w > 1 && 0 == (a->lda & 3) && 0 == ((uintptr_t)a->a & 15)) {
+    const float d = density_estimate(c);
+    if (d < 0.f || d >= 0.01f) {
+      if (0 == c->arena.dense) {
+        const size_t tiles = (size_t)((c->g.bm + 127) / 128);
+        c->dense_bytes = (size_t)c->g.mb * c->g.kb * tiles * 131072;
+        if (cudaSuccess == cudaMalloc((void**)&c->arena.dense, c->dense_bytes)) { XB_CUDA(cudaMemset(c->arena.dense, 0, c->dense_bytes)); XB_CUDA(cudaDeviceSynchronize()); }   // once per handle
+        else { (void)cudaGetLastError(); c->arena.dense = 0; }
+        a->out.dense = c->arena.dense;
+      }
+      if (c->arena.dense) a->write_dense = 1;
+    }
+  }
+  c->dense_written = (0 != a->write_dense);
 }
 
 static int compute_policy(const SpmdmCtx* c, int is_bf16, bool transb, bool transc)
@@ -216,7 +237,7 @@ static void compute_whole(const libxsmm_spmdm_handle* handle, char transb, char 
   a.ldb = a.transb ? c->g.k : c->g.n;
   a.ldc = a.transc ? c->g.m : c->g.n;
   a.beta = beta; a.g = c->g; a.mb_first = 0; a.mb_count = c->g.mb;
-  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16, 0 != a.transb, 0 != a.transc); a.density_hint = density_estimate(c);
+  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16, 0 != a.transb, 0 != a.transc); a.density_hint = density_estimate(c); a.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0;
   launch_compute(a, stream);
 }
 
@@ -274,7 +295,7 @@ static void compute_block(const libxsmm_spmdm_handle* handle, char transb, char 
   const bool dev_b = is_device_ptr(b_in), dev_c = is_device_ptr(c_in);
   ComputeArgs a;
   a.sl = c->arena; a.transb = tb; a.transc = tc; a.is_bf16 = is_bf16; a.beta = beta; a.g = g;
-  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1; a.density_hint = -1.f;   // legacy block: no tensor-core twin
+  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1; a.density_hint = -1.f; a.dense_valid = 0;   // legacy block: no tensor-core twin
   char* slab = c->staging + (size_t)tid * c->staging_per_tid;
   const size_t slab_b_bytes = (((size_t)g.k * g.bn * 4) + 255) & ~(size_t)255;
   float* c_stage = (float*)(slab + slab_b_bytes);
@@ -368,7 +389,7 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena.tcpk = (uint32_t*)c->arena.tcoff;     // 4 bytes per entry: bf16 slices keep a 32-bit word per nonzero
   c->arena.slice_nnz = (uint32_t*)((char*)c->arena_base + row_bytes + col_bytes + val_bytes + val_bytes);
   XB_CUDA(cudaMemset(c->arena.slice_nnz, 0, nnz_bytes));
-  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false;
+  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->dense_bytes = 0; c->arena.dense = 0;
   if (cudaSuccess == cudaHostAlloc((void**)&c->h_nnz, sizeof(unsigned long long), cudaHostAllocMapped)) {
     *c->h_nnz = ~0ull;
     if (cudaSuccess != cudaHostGetDevicePointer((void**)&c->d_nnz, c->h_nnz, 0)) c->d_nnz = 0;
@@ -415,6 +436,7 @@ void libxsmm_spmdm_destroy(libxsmm_spmdm_handle* handle)
     if (c->d_b) cudaFree(c->d_b);
     if (c->d_c) cudaFree(c->d_c);
     cudaFree(c->arena_base);
+    if (c->arena.dense) cudaFree(c->arena.dense);
     cudaFree(c->staging);
     if (c->d_acc) cudaFree(c->d_acc);
     if (c->h_nnz) cudaFreeHost(c->h_nnz);
@@ -548,7 +570,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
   static const bool trace = [] { const char* e = getenv("LIBXSMM_B200_EXEC_TRACE"); return e && '1' == *e; }();
   std::vector<cudaEvent_t> tev;
   if (trace) { tev.resize((size_t)(3 * nd + 1)); for (size_t i = 0; i < tev.size(); ++i) XB_CUDA(cudaEventCreate(&tev[i])); XB_CUDA(cudaEventRecord(tev[3 * nd], c->xs[0])); }
-  int write_aux = 1; bool first_block = true;
+  int write_aux = 1, write_dense = 0; bool first_block = true;
   // a rectangle of C: row blocks [r0, r0 + rc) x columns [n0, n0 + w)
   auto rect = [&](int r0, int rc, int n0, int w, int* m0, int* rows) {
     *m0 = r0 * g.bm;
@@ -573,7 +595,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
     ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
     ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
     ca.beta = beta_f; ca.g = g; ca.mb_first = r0; ca.mb_count = rc;
-    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16, tb, tc); ca.density_hint = density_estimate(c);
+    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16, tb, tc); ca.density_hint = density_estimate(c); ca.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0;
     launch_compute(ca, c->xs[1]);
   };
   for (int d = 0; d < nd; ++d) {
@@ -607,9 +629,12 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
       sa.a = c->d_a; sa.transa = ta; sa.lda = ta ? g.m : g.k; sa.is_bf16 = is_bf16;
       sa.origin_is_block = 0; sa.slice0 = d; sa.slice_step = g.mb; sa.simd_w = c->simd_w; sa.g = g; sa.out = c->arena;
       slice_policy(c, &sa, is_bf16, true);
-      if (first_block) { write_aux = sa.write_aux; first_block = false; }
+      if (first_block) { write_aux = sa.write_aux; write_dense = sa.write_dense; first_block = false; }
       sa.write_aux = write_aux;                 // one decision for all row blocks of this multiply
+      sa.write_dense = (write_dense && c->arena.dense) ? 1 : 0;
+      sa.out = c->arena;
       c->aux_written = (0 != write_aux);
+      c->dense_written = (0 != sa.write_dense);
       launch_slices(sa, g.kb, c->xs[1]);
       compute_rect(d, 1, 0, row_cols);
     }

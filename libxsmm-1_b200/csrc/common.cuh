@@ -42,6 +42,10 @@ struct SliceArena {
   uint16_t* tcoff;   // auxiliary (not part of the reference's slice), same indexing as colidx: where the nonzero
                      // goes in the tensor-core branch's shared-memory A tile (fp32 slices: xb_tc_pack)
   uint32_t* tcpk;    // the same memory seen as 32-bit words (bf16 slices: xb_tc16_pack, value and position in one word)
+  float* dense;      // auxiliary, optional (fp32 slices of dense matrices): the slice once more as the tensor-core kernel's
+                     // shared-memory image -- per (slice, 128-row tile, 64-k half) 64 KiB: a_hi chunk 0, 1, a_lo chunk 0, 1,
+                     // each [128 rows x 32 k] fp32, K-major, SWIZZLE_128B -- so that K4 fetches a half with one bulk copy
+                     // instead of rebuilding it from (column, value) pairs.  0 until a dense matrix shows up.
 };
 
 // Tensor-core branch (spmdm_compute_tc.cu): A is rebuilt per k-block as two K-halves (k < 64, k >= 64), each
@@ -88,6 +92,7 @@ struct SliceArgs {
   unsigned long long* host_total;
   int total_slices;
   int write_aux;        // 0: skip the auxiliary per-nonzero words (tensor-core kernels will not be enqueued)
+  int write_dense;      // 1: also write the dense tile image (SliceArena::dense; fp32, transa = 'N', complete k-blocks)
 };
 
 #if defined(__CUDACC__)
@@ -138,6 +143,7 @@ struct ComputeArgs {
   // selected kernel does the work (dense <=> total nnz >= tc_min_nnz).  tc_twin = 0: no twin, always run.
   int tc_twin;
   unsigned long long tc_min_nnz;
+  int dense_valid;      // the slices' dense tile image (SliceArena::dense) was written by the slicing pass these slices come from
   float density_hint;   // host's lagging estimate of nnz / (M*K) from the last completed slicing pass, < 0: unknown (performance only)
   int tc_hint;      // host's lagging density hint: 0 unknown / borderline (enqueue both twins), 1 clearly sparse (CUDA cores only), 2 clearly dense (tensor cores only)
 };

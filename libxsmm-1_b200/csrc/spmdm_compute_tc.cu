@@ -41,7 +41,9 @@ constexpr int TC_SMEM_BYTES = TC_SMEM_BAR + 256;
 // k-block's and clears those instead of wiping the half.  <8, true> for slices up to ~25 % dense (measured on 2048^3 at
 // 10 %: 174 -> 139 us), <16, false> for denser ones (at 50 % the short register list sends half the nonzeros through
 // the memory loop: 183 -> 211 us); the register file (576 threads) does not hold 16 + 16 + 16.
-template <int TC_NQ, bool HIST>
+// DENSEA = the slicing kernel also left the dense tile image of the slices (SliceArena::dense): a half of A is then
+// one 64 KiB bulk copy issued by the producer thread and nobody rebuilds anything.
+template <int TC_NQ, bool HIST, bool DENSEA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeArgs p)
 {
@@ -74,7 +76,7 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
     for (int i = 0; i < TC_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_split[i], HIST ? TC_WORKERS / 2 : TC_WORKERS); mbar_init(&b_free[i], 1); }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_ready[i], HIST ? TC_WORKERS / 2 : TC_WORKERS); mbar_init(&a_free[i], 1);
+      mbar_init(&a_ready[i], DENSEA ? 1 : (HIST ? TC_WORKERS / 2 : TC_WORKERS)); mbar_init(&a_free[i], 1);
       mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_WORKERS);
     }
     mbar_fence_init();
@@ -92,7 +94,16 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
     // ---------------- TMA producer: B chunks through a 3-stage ring ----------------
     if (0 == lane) {
       tma_prefetch_desc(&tmB);
+      const int tiles_per_mb_img = (g.bm + 127) / 128;
       for (int c = 0; c < nsteps * 2; ++c) {
+        if (DENSEA && 0 == (c & 1)) {      // first chunk of a step: the step's A half straight from the dense image
+          const int t = c >> 1, kb = t >> 1, h = t & 1;
+          if (kb > 0) mbar_wait(&a_free[h], (kb - 1) & 1);
+          const float* src = p.sl.dense + ((size_t)(kb * g.mb + mbi) * tiles_per_mb_img + (size_t)(ml0 >> 7)) * 32768 + (size_t)h * 16384;
+          mbar_arrive_expect_tx(&a_ready[h], TC_A_HALF);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                       ::"r"(smem_u32(smem + TC_SMEM_A + h * TC_A_HALF)), "l"(src), "r"((uint32_t)TC_A_HALF), "r"(smem_u32(&a_ready[h])) : "memory");
+        }
         const int s = c % TC_NB, f = c / TC_NB;
         if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
         mbar_arrive_expect_tx(&b_full[s], TC_B_CHUNK);
@@ -158,7 +169,7 @@ spmdm_compute_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
     // instructions, so two shorter chains side by side beat one long one.  The dense variant keeps all sixteen on
     // every job (the rebuild of a dense half needs all the threads it can get).
     constexpr int DW = HIST ? TC_WT / 2 : TC_WT;  // threads on the densify job / on the split job
-    const bool do_dens = !HIST || w < TC_WORKERS / 2, do_split = !HIST || w >= TC_WORKERS / 2;
+    const bool do_dens = !DENSEA && (!HIST || w < TC_WORKERS / 2), do_split = !HIST || w >= TC_WORKERS / 2;
     const int wt = HIST ? ((tid - 64) & (DW - 1)) : (tid - 64);   // index within the job's threads
     const size_t cap = (size_t)g.bm * g.bk;
     // this thread's part of the output: row (quarter*32 + lane), 32 columns; warp w may touch TMEM lanes
@@ -349,16 +360,20 @@ bool launch_compute_tc(const ComputeArgs& a, cudaStream_t stream)
     if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.g.k, (unsigned long long)a.ncols, (unsigned long long)a.ldb * 4, 32, TC_BN, false)) return false;
   }
   else if (!make_tensor_map_2d_sw128(&map, a.b, 4, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 4, 32, TC_KC, true)) return false;
-  // performance-only choice (both instantiations are complete): the host's estimate is one call old at most
+  // performance-only choice (every instantiation is complete): the host's estimate is one call old at most
   bool sparse_variant = a.density_hint >= 0.f && a.density_hint < 0.25f;
   { const char* e = getenv("LIBXSMM_B200_K4_VARIANT"); if (e && 's' == *e) sparse_variant = true; else if (e && 'd' == *e) sparse_variant = false; }   // developer switch
-  ensure_smem_optin(sparse_variant ? (const void*)spmdm_compute_tc_kernel<8, true> : (const void*)spmdm_compute_tc_kernel<16, false>, TC_SMEM_BYTES);
+  const bool image = 0 != a.dense_valid && 0 != a.sl.dense && !(getenv("LIBXSMM_B200_K4_VARIANT"));   // the slicing pass left the A image: nothing to rebuild
+  const void* kern = image ? (const void*)spmdm_compute_tc_kernel<16, false, true>
+                   : (sparse_variant ? (const void*)spmdm_compute_tc_kernel<8, true, false> : (const void*)spmdm_compute_tc_kernel<16, false, false>);
+  ensure_smem_optin(kern, TC_SMEM_BYTES);
   const int tiles_per_mb = (a.g.bm + TC_BM - 1) / TC_BM;
   const dim3 grid((unsigned)((a.ncols + TC_BN - 1) / TC_BN), (unsigned)(a.mb_count * tiles_per_mb), 1);
   count_launch(1);
-  note_compute_kernel("spmdm_compute_tc_kernel");
-  if (sparse_variant) spmdm_compute_tc_kernel<8, true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
-  else spmdm_compute_tc_kernel<16, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
+  note_compute_kernel(image ? "spmdm_compute_tc_kernel (dense image)" : "spmdm_compute_tc_kernel");
+  if (image) spmdm_compute_tc_kernel<16, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
+  else if (sparse_variant) spmdm_compute_tc_kernel<8, true, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
+  else spmdm_compute_tc_kernel<16, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
   XB_CUDA(cudaGetLastError());
   return true;
 }

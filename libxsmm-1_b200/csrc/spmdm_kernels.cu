@@ -349,6 +349,21 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
       const uint32_t b0 = __ballot_sync(0xffffffffu, nm & 1u), b1 = __ballot_sync(0xffffffffu, nm & 2u), b2 = __ballot_sync(0xffffffffu, nm & 4u);
       uint32_t q = pos + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
       if (0 == lane) ro[row_lo + j] = (uint16_t)pos;
+      if (!BF16 && FULL && p.write_dense) {
+        // the row's piece of the tensor-core kernel's A image: this lane's four columns are one 16-byte swizzle
+        // unit of the [128 rows x 32 k] chunk (lane >> 3) & 1 of the 64-k half lane >> 4; a_hi, then a_lo 32 KiB on
+        const int rr = row_lo + j, trow = rr & 127;
+        float* img = p.out.dense + ((size_t)s * ((g.bm + 127) / 128) + (size_t)(rr >> 7)) * 32768
+                   + (size_t)(lane >> 4) * 16384 + (size_t)((lane >> 3) & 1) * 4096
+                   + (size_t)(trow >> 3) * 256 + (size_t)(trow & 7) * 32 + (size_t)(((lane & 7) ^ (trow & 7)) * 4);
+        uint4 hi, lo;
+        hi.x = (m & 1u) ? (v.x & 0xFFFFE000u) : 0u; lo.x = (m & 1u) ? __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x)) : 0u;
+        hi.y = (m & 2u) ? (v.y & 0xFFFFE000u) : 0u; lo.y = (m & 2u) ? __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y)) : 0u;
+        hi.z = (m & 4u) ? (v.z & 0xFFFFE000u) : 0u; lo.z = (m & 4u) ? __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z)) : 0u;
+        hi.w = (m & 8u) ? (v.w & 0xFFFFE000u) : 0u; lo.w = (m & 8u) ? __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w)) : 0u;
+        *(uint4*)img = hi;
+        *(uint4*)(img + 8192) = lo;
+      }
       if (m) {   // few lanes hold nonzeros in the sparse regime: one divergent region per row
         const int rr = row_lo + j;
         // auxiliary per-nonzero word: position in the tcgen05 branch's A tile (bf16 slices: value and position)
