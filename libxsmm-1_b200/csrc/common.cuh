@@ -170,7 +170,8 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tma(const ComputeArgs& args, bool partial, cudaStream_t stream);
 bool launch_compute_tc(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tc16(const ComputeArgs& args, cudaStream_t stream);   // tcgen05 branch for bf16 inputs
-bool launch_compute_tc16p(const ComputeArgs& args, cudaStream_t stream);  // CTA-pair (cta_group::2) persistent form of it
+bool launch_compute_tc16p(const ComputeArgs& args, cudaStream_t stream);
+bool launch_compute_tcq(const ComputeArgs& args, cudaStream_t stream);    // fp32 CTA-pair kernel (needs the slices' dense image)  // CTA-pair (cta_group::2) persistent form of it
 
 // ---- FSSPMDM --------------------------------------------------------------------------------
 struct FsOperator;   // fsspmdm.cu

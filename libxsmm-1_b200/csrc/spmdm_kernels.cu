@@ -1000,6 +1000,15 @@ static bool launch_tc_bf16(const ComputeArgs& a, cudaStream_t stream)
   return launch_compute_tc16(a, stream);
 }
 
+// fp32 tensor-core branch: the CTA-pair kernel when the slices carry their dense image (LIBXSMM_B200_TCQ=0: never),
+// else the single-CTA kernel
+static bool launch_tc_f32(const ComputeArgs& a, cudaStream_t stream)
+{
+  const char* e = getenv("LIBXSMM_B200_TCQ");
+  if (!(e && '0' == *e) && launch_compute_tcq(a, stream)) return true;
+  return launch_compute_tc(a, stream);
+}
+
 static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
 {
   if (launch_compute_tma(a, partial, stream)) return;   // TMA fast path (spmdm_compute_tma.cu)
@@ -1023,12 +1032,12 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
   if (2 == mode && 1 == args.tc_hint) mode = 0;      // clearly sparse last time: do not even enqueue the dense twin
   targs.tc_twin = 0;
   if (2 == mode && 2 == args.tc_hint) {              // clearly dense last time: the tensor-core kernel alone (correct for any density)
-    if (args.is_bf16 ? launch_tc_bf16(targs, stream) : launch_compute_tc(targs, stream)) return;
+    if (args.is_bf16 ? launch_tc_bf16(targs, stream) : launch_tc_f32(targs, stream)) return;
   }
   if (mode > 0) {
     targs.tc_twin = 1;
     targs.tc_min_nnz = (1 == mode) ? 0ull : (unsigned long long)(tc_density_threshold(0 != args.is_bf16, 0 != args.transb, 0 != args.transc) * (double)args.g.m * (double)args.g.k);
-    if (!(args.is_bf16 ? launch_tc_bf16(targs, stream) : launch_compute_tc(targs, stream))) targs.tc_twin = 0;
+    if (!(args.is_bf16 ? launch_tc_bf16(targs, stream) : launch_tc_f32(targs, stream))) targs.tc_twin = 0;
     else if (1 == mode) return;   // forced: nothing for the sparse kernels to do
   }
   const ComputeArgs& args2 = targs;
