@@ -123,12 +123,13 @@ static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole)
   a->write_aux = skip ? 0 : 1;
   if (whole) c->aux_written = (0 != a->write_aux);
   else c->aux_written = true;
-  // Dense tile image for the tensor-core kernel (fp32, A stored m x k, complete k-blocks, 16-byte aligned rows): written
+  // Dense tile image for the tensor-core kernel (fp32, complete k-blocks; A stored m x k: 16-byte aligned rows): written
   // unless the last pass showed a matrix so sparse (< 1 %) that the CUDA-core kernels will multiply it whatever the
   // orientation of B and C.  Costs ~4 us of extra stores per 2048^2 and takes 50-90 us off the multiply.  Allocated and
   // zeroed on first use (rows and columns of partial tiles are never written and stay zero).
   a->write_dense = 0;
-  if (whole && !is_bf16 && !a->transa && 0 == (c->g.k % 128) && c->simd_w > 1 && 0 == (a->lda & 3) && 0 == ((uintptr_t)a->a & 15)) {
+  // (A stored k x m goes through the strip kernel, which writes the image from its shared-memory tile: no alignment rule)
+  if (whole && !is_bf16 && 0 == (c->g.k % 128) && c->simd_w > 1 && (a->transa || (0 == (a->lda & 3) && 0 == ((uintptr_t)a->a & 15)))) {
     const float d = density_estimate(c);
     if (d < 0.f || d >= 0.01f) {
       if (0 == c->arena.dense) {

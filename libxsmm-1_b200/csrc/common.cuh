@@ -116,9 +116,10 @@ struct ColModes { int n_full_end; int tail_from; };
 // Density (nnz / (M*K)) from which the tensor-core twin takes over, measured on B200 (2048^3 and 4096^3):
 //   bf16: the CTA-pair kernel costs the same at any density and orientation (93 us for 4096^3, 28 us for 2048^3); the
 //         TMA CUDA-core kernel (N/N/N) is ahead of it below ~0.5 %, the generic one (transb / transc) never is.
-//   fp32: 3xTF32 costs ~78 us for 2048^3 when the slices carry their dense image (A stored m x k; the CTA-pair kernel)
+//   fp32: 3xTF32 costs 70-78 us for 2048^3 when the slices carry their dense image (the CTA-pair kernel; matrices the
+//         last slicing pass found below 1 % dense are sliced without it)
 //         and ~104 us / ~180 us without it (single-CTA kernel, patching / wiping variant); the TMA kernel (N/N/N) is
-//         ahead below ~2.8 %, the generic one below ~1 % (transc, where transa = 'T' has no image) and never (transb).
+//         ahead below ~2.8 %, the generic one below ~1 % (transc) and never (transb).
 inline double tc_density_threshold(bool is_bf16, bool transb, bool transc)
 {
   if (is_bf16) return (transb || transc) ? 0.0 : 0.005;

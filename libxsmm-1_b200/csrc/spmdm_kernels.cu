@@ -187,6 +187,17 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
           else ri[q] = xb_tc_pack(r0 + r, k);
         }
       }
+      if (p.write_dense && !p.is_bf16) {
+        // dense tile image (see SliceArena::dense): the 32 lanes cover one 128-byte image row of chunk j & 1 of half
+        // j >> 1 (16-byte units permuted by the swizzle, same line): a_hi, and a_lo 32 KiB further on
+        const int rr = r0 + r, trow = rr & 127;
+        float* img = p.out.dense + ((size_t)s * ((g.bm + 127) / 128) + (size_t)(rr >> 7)) * 32768
+                   + (size_t)(j >> 1) * 16384 + (size_t)(j & 1) * 4096
+                   + (size_t)(trow >> 3) * 256 + (size_t)(trow & 7) * 32 + (size_t)((((lane >> 2) ^ trow) & 7) * 4 + (lane & 3));
+        const float vh = keep ? __uint_as_float(__float_as_uint(v) & 0xFFFFE000u) : 0.f;
+        img[0] = vh;
+        img[8192] = keep ? (v - vh) : 0.f;
+      }
       pos += __popc(bal);
     }
   }
