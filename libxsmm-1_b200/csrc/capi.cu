@@ -114,7 +114,7 @@ static float density_estimate(const SpmdmCtx* c)
   return (~0ull == n) ? -1.f : (float)((double)n / ((double)c->g.m * (double)c->g.k));
 }
 
-static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole)
+static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole, cudaStream_t stream)
 {
   a->acc = c->d_acc; a->host_total = c->d_nnz; a->total_slices = c->g.mb * c->g.kb;
   // the orientation of the multiply that will consume the slices is not known here: the auxiliary words are
@@ -135,7 +135,7 @@ static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole)
       if (0 == c->arena.dense) {
         const size_t tiles = (size_t)((c->g.bm + 127) / 128);
         c->dense_bytes = (size_t)c->g.mb * c->g.kb * tiles * 131072;
-        if (cudaSuccess == cudaMalloc((void**)&c->arena.dense, c->dense_bytes)) { XB_CUDA(cudaMemset(c->arena.dense, 0, c->dense_bytes)); XB_CUDA(cudaDeviceSynchronize()); }   // once per handle
+        if (cudaSuccess == cudaMalloc((void**)&c->arena.dense, c->dense_bytes)) XB_CUDA(cudaMemsetAsync(c->arena.dense, 0, c->dense_bytes, stream));   // once per handle, ordered before the slicing kernel
         else { (void)cudaGetLastError(); c->arena.dense = 0; }
         a->out.dense = c->arena.dense;
       }
@@ -223,7 +223,7 @@ static void slices_whole(const libxsmm_spmdm_handle* handle, char transa, const 
   SliceArgs a;
   a.a = d_a; a.transa = is_t(transa); a.lda = a.transa ? c->g.m : c->g.k; a.is_bf16 = is_bf16;
   a.origin_is_block = 0; a.slice0 = 0; a.slice_step = 1; a.simd_w = c->simd_w; a.g = c->g; a.out = c->arena;
-  slice_policy(c, &a, is_bf16, true);
+  slice_policy(c, &a, is_bf16, true, stream);
   launch_slices(a, c->g.mb * c->g.kb, stream);
 }
 
@@ -273,7 +273,7 @@ static void slice_block(const libxsmm_spmdm_handle* handle, char transa, const v
     }
     a.a = slab; a.origin_is_block = 1;
   }
-  slice_policy(c, &a, is_bf16, false);
+  slice_policy(c, &a, is_bf16, false, (cudaStream_t)0);
   launch_slices(a, 1, st);
   XB_CUDA(cudaStreamSynchronize(st));
 }
@@ -629,7 +629,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
       SliceArgs sa;
       sa.a = c->d_a; sa.transa = ta; sa.lda = ta ? g.m : g.k; sa.is_bf16 = is_bf16;
       sa.origin_is_block = 0; sa.slice0 = d; sa.slice_step = g.mb; sa.simd_w = c->simd_w; sa.g = g; sa.out = c->arena;
-      slice_policy(c, &sa, is_bf16, true);
+      slice_policy(c, &sa, is_bf16, true, c->xs[1]);
       if (first_block) { write_aux = sa.write_aux; write_dense = sa.write_dense; first_block = false; }
       sa.write_aux = write_aux;                 // one decision for all row blocks of this multiply
       sa.write_dense = (write_dense && c->arena.dense) ? 1 : 0;
