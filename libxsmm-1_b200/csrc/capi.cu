@@ -143,11 +143,12 @@ static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole, cud
     }
   }
   c->dense_written = (0 != a->write_dense);
+  if (a->write_dense && whole) { a->write_aux = 0; c->aux_written = false; }   // the image replaces the per-nonzero words: every tensor-core kernel that could read them reads the image instead
 }
 
 static int compute_policy(const SpmdmCtx* c, int is_bf16, bool transb, bool transc)
 {
-  if (!c->aux_written) return 1;      // the slices carry no auxiliary words: CUDA cores only
+  if (!c->aux_written && !(c->dense_written && !is_bf16)) return 1;      // the slices carry neither auxiliary words nor the dense image: CUDA cores only
   return density_hint(c, is_bf16, transb, transc);
 }
 
