@@ -18,9 +18,13 @@ metric = effective GFLOP/s = 2.nnz.N / t  (SURVEY.md section 8d).
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, OpenMP over block ids like the sample) on this host.
 
 Multi-GPU (N > 1, launched by torchrun, one rank per GPU): the path shards by N-column panels with A
-replicated and NO collective on the data path.  Scaling is WEAK: every rank owns a
-4096-column panel, i.e. the global problem is M = K = 4096, N = 4096.N_gpus.  torch.distributed (NCCL) is
-used for the barriers and the max-over-ranks of the device time only.
+replicated and NO collective on the data path.  torch.distributed (NCCL) is used for
+the barriers and the max-over-ranks of the device time only.
+  * headline (C2): BASELINE.json names no sharding for it -- every rank multiplies its own 4096-column panel
+    (replicas, WEAK scaling: global problem M = K = 4096, N = 4096.N_gpus).
+  * `column_sharded` (C3: dfsspmdm N = 2^20, C5: sfsspmdm N = 2^24): the configs BASELINE.json names as column
+    sharded.  ONE global problem, rank r owns columns [r.N/g, (r+1).N/g) (libxsmm-1_b200/sharding.py), STRONG
+    scaling; reported device-resident and end to end at every N, so that the 1/2/4/8 curve can be read off.
 
 --impl reference times the reference CPU implementation on the same workload (rank 0 only).
 """
@@ -54,7 +58,16 @@ WORKLOADS = {
                    desc="spmdm fp32 2048^3 50%, transB (backprop)"),
     "c5": dict(kind="fsspmdm", M=150, K=64, density=0.30, n_unique=8, dtype="f32", N=1 << 24, beta=0.0,
                desc="sfsspmdm fp32 150x64 30% dense, N=2^24 columns, beta=0"),
+    "c3-b1": dict(kind="fsspmdm", M=150, K=64, density=0.30, n_unique=8, dtype="f64", N=1 << 20, beta=1.0,
+                  desc="dfsspmdm fp64 150x64 30% dense (8 distinct values), N=2^20 columns, beta=1"),
+    # real PyFR operators (reference samples/pyfr/mats/p4/hex/m0-sp.mtx, p4/tet/m6-sp.mtx; the matrices travel as the
+    # committed fixtures tests/golden/pyfr_*.npz and are handed to the library as MatrixMarket files: create_mtx)
+    "c3-hex": dict(kind="fsspmdm", fixture="pyfr_p4_hex_m0", M=150, K=125, dtype="f64", N=1 << 20, beta=0.0,
+                   desc="dfsspmdm fp64 PyFR p4/hex/m0-sp (150x125, 750 nnz, 5 distinct values), N=2^20 columns, beta=0"),
+    "c3-tet": dict(kind="fsspmdm", fixture="pyfr_p4_tet_m6", M=105, K=60, dtype="f64", N=1 << 20, beta=0.0,
+                   desc="dfsspmdm fp64 PyFR p4/tet/m6-sp (105x60, 50% dense, 202 distinct values: reference dense branch), N=2^20 columns, beta=0"),
 }
+FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: 148 SMs x 128 FMA lanes at the 1965 MHz the CUDA-core kernels run at (nominal; no measured figure in MEASURED_PEAKS.json)
 L2_BYTES = 126 << 20
 
 
@@ -191,6 +204,9 @@ def fs_bytes(wl, N):
 
 
 def fs_operator(xs, wl):
+    if wl.get("fixture"):
+        return np.ascontiguousarray(np.load(os.path.join(ROOT, "tests", "golden", wl["fixture"] + ".npz"))["a"],
+                                    np.float64 if wl["dtype"] == "f64" else np.float32)
     return xs.workloads.fsspmdm_operator(wl["M"], wl["K"], wl["density"], wl["n_unique"],
                                          np.float64 if wl["dtype"] == "f64" else np.float32, seed=1)
 
@@ -285,14 +301,31 @@ def run_spmdm_gpu(xs, wl, steps, warmup, want_e2e=True):
     p.destroy()
 
 
-def run_fs_gpu(xs, wl, steps, warmup, world, want_e2e=True):
-    """C3 / C5: total N columns split into contiguous panels of N / world per rank (A replicated)."""
+def run_fs_gpu(xs, wl, steps, warmup, world, want_e2e=True, rank=0):
+    """C3 / C5: the N columns of ONE global problem split into contiguous panels (sharding.column_panels: multiples of 16), one
+    per rank; every rank holds its own dense B / C panel (ld = panel width) and a replica of the operator."""
     dbl = wl["dtype"] == "f64"
     dtype = np.float64 if dbl else np.float32
     a = fs_operator(xs, wl)
     nnz = int(np.count_nonzero(a))
-    N = wl["N"] // world
-    op = xs.Fsspmdm(a, N, beta=wl["beta"])
+    sharding = importlib.import_module("libxsmm-1_b200.sharding")
+    n0, N = sharding.column_panels(wl["N"], world, 16)[rank]      # this rank's columns [n0, n0 + N) of the global B and C
+
+    def make_operator(ncols):
+        if not wl.get("fixture"):
+            return xs.Fsspmdm(a, ncols, beta=wl["beta"])
+        import tempfile                          # real operator: through the library's MatrixMarket entry (create_mtx)
+        with tempfile.NamedTemporaryFile("w", suffix=".mtx", delete=False) as f:
+            r, c = np.nonzero(a)
+            f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (a.shape[0], a.shape[1], len(r)))
+            for i, j in zip(r, c):
+                f.write("%d %d %r\n" % (i + 1, j + 1, float(a[i, j])))
+        try:
+            return xs.Fsspmdm.from_mtx(f.name, ncols, beta=wl["beta"], double=dbl)
+        finally:
+            os.unlink(f.name)
+
+    op = make_operator(N)
     esz = 8 if dbl else 4
     bB, bC = wl["K"] * N * esz, wl["M"] * N * esz
     nsets = max(1, int(np.ceil(2.5 * L2_BYTES / (bB + bC)))) if (bB + bC) < 3 * L2_BYTES else 1
@@ -317,12 +350,12 @@ def run_fs_gpu(xs, wl, steps, warmup, world, want_e2e=True):
     launches = xs.launch_count() - l0
     total_ms = t_first.elapsed_ms(t_last)
     xs.check()
-    yield dict(total_ms=total_ms, launches=launches, nnz=nnz, flops=2.0 * nnz * N, geo=dict(sparse=op.is_sparse, baked=op.is_baked),
+    yield dict(total_ms=total_ms, launches=launches, nnz=nnz, flops=2.0 * nnz * N, geo=dict(sparse=op.is_sparse, baked=op.is_baked, first_column=n0, columns_per_rank=N),
                kernel_ms=total_ms / steps, kernel_bytes=fs_bytes(wl, N), kernel_name=xs.last_compute_kernel(),
                parts={}, step_bytes=fs_bytes(wl, N), ring_sets=nsets, ring_bytes=nsets * (bB + bC))
     if want_e2e:
         Ne = min(N, 1 << 20)                      # host panel of at most 2^20 columns per step (537 MB + 1.26 GB for fp64)
-        ope = xs.Fsspmdm(a, Ne, beta=wl["beta"]) if Ne != N else op
+        ope = make_operator(Ne) if Ne != N else op
         hB = xs.HostBuffer((wl["K"], Ne), dtype); hB.array[...] = np.random.default_rng(5).random((wl["K"], Ne), np.float32)
         hC = xs.HostBuffer((wl["M"], Ne), dtype); hC.array[...] = 0
         ope.execute(hB, hC)
@@ -360,20 +393,34 @@ def cpu_reference(wl, budget_s, reps_min=1, reps_max=50):
             have_ref = pyoracle.Ref.available()
         except Exception:
             have_ref = False
+    # the reference has two SIMD instantiations of spmdm (src/libxsmm_spmdm.c:557-583): AVX2 (bn = 48, what a plain GCC
+    # build selects) and AVX-512 (bn = 96, `make AVX=3`).  Both are timed where the host can run them; the faster counts.
+    flavors = ["avx2"]
+    try:
+        if pyoracle.Ref.available("avx512") and "avx512f" in open("/proc/cpuinfo").read():
+            flavors.append("avx512")
+    except Exception:
+        pass
     if wl["kind"] == "spmdm":
         t = wl["trans"]
         A, B, C0 = w.spmdm_inputs(wl["M"], wl["N"], wl["K"], wl["density"], dtype=wl["dtype"], seed=1, transa=t[0], transb=t[1], transc=t[2])
         nnz = int(np.count_nonzero(A))
         flops = 2.0 * nnz * wl["N"]
         if have_ref:
-            ref = pyoracle.Ref()
-            C = C0.copy()
-            _, _, tm = ref.spmdm(A, B, C, wl["M"], wl["N"], wl["K"], t[0], t[1], t[2], wl["beta"], threads=cores, reps=1, dump=False)   # warm-up
-            reps = int(min(reps_max, max(reps_min, budget_s / max(tm[0, 2], 1e-4))))
-            _, _, tm = ref.spmdm(A, B, C, wl["M"], wl["N"], wl["K"], t[0], t[1], t[2], wl["beta"], threads=cores, reps=reps, dump=False)
-            ms = float(np.median(tm[:, 2])) * 1e3
-            return dict(value=flops / ms / 1e6, ms=ms, best_ms=float(tm[:, 2].min()) * 1e3, cores=cores, kind="reference",
-                        sample="full workload (%s), %d reps after 1 warm-up, median; OpenMP over block ids, AVX2 instantiation bn=48" % (wl["desc"], reps))
+            best, seen = None, []
+            for fl in flavors:
+                ref = pyoracle.Ref(fl)
+                C = C0.copy()
+                _, _, tm = ref.spmdm(A, B, C, wl["M"], wl["N"], wl["K"], t[0], t[1], t[2], wl["beta"], threads=cores, reps=1, dump=False)   # warm-up
+                reps = int(min(reps_max, max(reps_min, budget_s / len(flavors) / max(tm[0, 2], 1e-4))))
+                _, _, tm = ref.spmdm(A, B, C, wl["M"], wl["N"], wl["K"], t[0], t[1], t[2], wl["beta"], threads=cores, reps=reps, dump=False)
+                ms = float(np.median(tm[:, 2])) * 1e3
+                seen.append("%s (bn=%d) %.2f ms" % (fl, 96 if fl == "avx512" else 48, ms))
+                if best is None or ms < best[0]:
+                    best = (ms, float(tm[:, 2].min()) * 1e3, fl, reps)
+            ms, best_ms, fl, reps = best
+            return dict(value=flops / ms / 1e6, ms=ms, best_ms=best_ms, cores=cores, kind="reference", flavor=fl,
+                        sample="full workload (%s), %d reps after 1 warm-up, median; OpenMP over block ids; instantiations timed: %s; reported: %s" % (wl["desc"], reps, ", ".join(seen), fl))
         orc = pyoracle.Oracle()
         g = orc.geometry(wl["M"], wl["N"], wl["K"], 1, bn=48)
         t0 = time.perf_counter()
@@ -381,7 +428,7 @@ def cpu_reference(wl, budget_s, reps_min=1, reps_max=50):
         ms = (time.perf_counter() - t0) * 1e3
         return dict(value=flops / ms / 1e6, ms=ms, best_ms=ms, cores=1, kind="port", sample="full workload once, scalar oracle port")
     # fsspmdm: a bounded slab of columns, ld <= 2^20 (the reference's JIT addresses with 32-bit displacements)
-    a = w.fsspmdm_operator(wl["M"], wl["K"], wl["density"], wl["n_unique"], np.float64 if wl["dtype"] == "f64" else np.float32, seed=1)
+    a = fs_operator(importlib.import_module("libxsmm-1_b200"), wl)
     nnz = int(np.count_nonzero(a))
     Ns = 1 << 20 if wl["dtype"] == "f64" else 1 << 20
     rng = np.random.default_rng(3)
@@ -417,7 +464,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--others", default="c1,c3,c4,c4-tnt,c4-ntn,c5", help="extra workloads reported inside the line (N=1 only); '' = none")
+    ap.add_argument("--others", default="c1,c4,c4-tnt,c4-ntn,c3-b1,c3-hex,c3-tet", help="extra workloads reported inside the line (N=1 only); '' = none")
+    ap.add_argument("--sharded", default="c3,c5", help="column-sharded fsspmdm configs reported in `column_sharded` at every N (strong scaling); '' = none")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of reference CPU time for the headline cpu_baseline (a quarter of it per secondary workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -483,7 +532,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    def run(wl_, want_e2e, sample_clocks):
+    def run(wl_, want_e2e, sample_clocks, shard=1):
+        """one workload on this rank.  shard = 1: the whole problem on every rank (replicas).  shard = world: this rank's
+        N / world column panel of ONE global problem (fsspmdm)."""
         # the clock sampler (nvidia-smi every 200 ms) runs from before the warm-up until after the end-to-end
         # phase: the device-timed region alone lasts only milliseconds
         sampler = ClockSampler(local_rank) if sample_clocks else None
@@ -491,7 +542,7 @@ def main():
             sampler.start()
             time.sleep(0.3)
         gen = run_spmdm_gpu(xs, wl_, args.steps, args.warmup, want_e2e) if wl_["kind"] == "spmdm" else \
-            run_fs_gpu(xs, wl_, args.steps, args.warmup, 1, want_e2e)
+            run_fs_gpu(xs, wl_, args.steps, args.warmup, shard, want_e2e, rank if shard > 1 else 0)
         assert next(gen) == "ready"
         barrier()
         res = next(gen)
@@ -513,23 +564,53 @@ def main():
         clocks = sampler.finish() if sampler else None
         return res, e2e, clocks
 
-    res, e2e, clocks = run(wl, not args.no_e2e, rank == 0)
+    peak, peak_src = peaks()
+
+    def bound_of(wl_, r):
+        """which roofline bounds the dominant kernel of this workload, and the fraction of it achieved: HBM for the
+        sparse / streaming kernels (algorithmic bytes over the measured copy bandwidth); the tensor pipe for the tcgen05
+        kernels that multiply densified tiles; the fp32 FMA pipe for the CUDA-core spmdm kernels on C1 / C4, whose
+        arithmetic intensity (48-186 flop/B) is far above the FMA ridge."""
+        ach = r["kernel_bytes"] / (r["kernel_ms"] * 1e6)
+        out = {"kernel": r["kernel_name"], "kernel_ms": r["kernel_ms"], "hbm_achieved_gbs": ach, "hbm_frac": ach / peak}
+        tp = tensor_pipe_info(r)
+        if tp:
+            out.update(bound="tensor", frac=tp["frac"], tensor_pipe=tp)
+        elif wl_["kind"] == "spmdm" and 2.0 * r["nnz"] * wl_["N"] / r["kernel_bytes"] > 16.0:
+            tf = 2.0 * r["nnz"] * wl_["N"] / (r["kernel_ms"] * 1e9)
+            out.update(bound="fma", frac=tf / FP32_FMA_PEAK_TFLOPS, fma_pipe={"executed_tflops": tf, "peak_tflops": FP32_FMA_PEAK_TFLOPS, "peak_source": "nominal 148 x 128 lanes x 2 x 1.965 GHz"})
+        else:
+            out.update(bound="hbm", frac=ach / peak)
+        return out
+
+    def e2e_block(e, wl_):
+        e_ms = e["e2e_ms"] / args.steps
+        return {"value": e["flops_all"] / (e_ms * 1e6), "unit": "GFLOP/s", "ms_per_step": e_ms,
+                "h2d_bytes_per_step": int(e["h2d"]), "d2h_bytes_per_step": int(e["d2h"]),
+                "api": "libxsmm_spmdm_exec_host" if wl_["kind"] == "spmdm" else "libxsmm_[sd]fsspmdm_execute (host pointers)"}
+
+    res, e2e, clocks = run(wl, not args.no_e2e, rank == 0, shard=(world if wl["kind"] == "fsspmdm" else 1))
     ms_per_step = res["total_ms"] / args.steps
     value = res["flops_all"] / (ms_per_step * 1e6)
-    peak, peak_src = peaks()
     achieved = res["kernel_bytes"] / (res["kernel_ms"] * 1e6)
+    spm = wl["kind"] == "spmdm"
     line = {
         "metric": metric, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if spm else "strong", "vs_baseline": None,
         "dtype": "f32" if wl["dtype"] in ("f32", "bf16") else "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "per_gpu": "one N-column panel per rank, A replicated, no collective on the data path",
-                   "global_N": (wl["N"] * world), **({"numa": numa} if numa else {}), "inputs": "bf16" if wl["dtype"] == "bf16" else wl["dtype"],
-                   "l2_policy": "inputs larger than L2: ring of %d A/B/C sets = %.0f MB, a different set every step" % (res["ring_sets"], res["ring_bytes"] / 1e6),
-                   "geometry": res["geo"], "nnz": res["nnz"], "step": "createSparseSlice (all blocks) + compute (all blocks)" if wl["kind"] == "spmdm" else "execute"},
+        "config": {"workload": wl["desc"],
+                   "per_gpu": ("replicas: every rank multiplies its own 4096-column panel with its own copy of A (weak scaling; BASELINE.json names no sharding for this config); "
+                               "the column-SHARDED configs (C3, C5) are in `column_sharded`" if spm else
+                               "one N/%d-column panel of the global problem per rank, operator replicated, no collective on the data path (strong scaling)" % world),
+                   "global_N": (wl["N"] * world if spm else wl["N"]), **({"numa": numa} if numa else {}), "inputs": "bf16" if wl["dtype"] == "bf16" else wl["dtype"],
+                   "l2_policy": "inputs larger than L2: ring of %d input sets = %.0f MB, a different set every step" % (res["ring_sets"], res["ring_bytes"] / 1e6),
+                   "geometry": res["geo"], "nnz": res["nnz"], "step": "createSparseSlice (all blocks) + compute (all blocks)" if spm else "execute"},
         "hbm_gbs": res["step_bytes"] * world / (ms_per_step * 1e6),
         "gpu_launches": res["launches_all"],
         "roofline": {"bound": "hbm", "kernel": res["kernel_name"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": res["kernel_bytes"],
+                     "traffic": ncu_traffic(args.workload),
+                     "traffic_note": "ncu dram bytes of one launch are BELOW the algorithmic bytes because most of C (67 MB of fp32, written once) is still dirty in the 126 MB L2 when the kernel ends; the reads (A slices, B) are counted in full",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": res["kernel_bytes"],
                      "kernel_ms": res["kernel_ms"], "parts": res["parts"]},
         "clocks": clocks,
     }
@@ -537,40 +618,61 @@ def main():
     if tpipe:
         line["roofline"]["tensor_pipe"] = tpipe
     if e2e is not None:
-        e_ms = e2e["e2e_ms"] / args.steps
-        line["e2e"] = {"value": e2e["flops_all"] / (e_ms * 1e6), "unit": "GFLOP/s", "ms_per_step": e_ms,
-                       "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
-                       "api": "libxsmm_spmdm_exec_host" if wl["kind"] == "spmdm" else "libxsmm_[sd]fsspmdm_execute (host pointers)"}
+        line["e2e"] = e2e_block(e2e, wl)
+
+    # ---- the column-sharded configs of BASELINE.json (C3: dfsspmdm N = 2^20; C5: sfsspmdm N = 2^24) at this N: STRONG scaling,
+    #      rank r owns columns [r N/g, (r+1) N/g) of B and C (ld = N/g), the operator is replicated, nothing is exchanged ----
+    if args.sharded and spm:
+        sh = {}
+        for name in [n for n in args.sharded.split(",") if n]:
+            w_ = WORKLOADS[name]
+            try:
+                r2, e2, _ = run(w_, not args.no_e2e, False, shard=world)
+                ms2 = r2["total_ms"] / args.steps
+                ach2 = r2["kernel_bytes"] / (r2["kernel_ms"] * 1e6)
+                sh[name] = {"workload": w_["desc"], "scaling": "strong", "n_gpus": world, "columns_per_gpu": w_["N"] // world,
+                            "value": r2["flops_all"] / (ms2 * 1e6), "unit": "GFLOP/s", "ms_per_step": ms2,
+                            "hbm_gbs_all_gpus": fs_bytes(w_, w_["N"]) / (ms2 * 1e6), "kernel": r2["kernel_name"],
+                            "per_gpu_hbm_gbs": ach2, "per_gpu_hbm_frac": ach2 / peak, "gpu_launches": r2["launches_all"]}
+                if e2 is not None:
+                    sh[name]["e2e"] = e2e_block(e2, w_)
+                    sh[name]["e2e"]["note"] = "host panels of min(N/g, 2^20) columns per rank and step"
+            except Exception as ex:
+                sh[name] = {"error": repr(ex)[:200]}
+                xs.clear_error()
+        line["column_sharded"] = sh
+
     if world == 1 and rank == 0 and args.others:
         others = {}
         names = [n for n in args.others.split(",") if n and n != args.workload]
-        if wl["kind"] == "spmdm":
+        if spm:
             names.insert(0, args.workload + "@cuda-cores")     # same workload, LIBXSMM_B200_SPMDM_TC=0: the order-preserving (bit-exact) kernels only
         for name in names:
             try:
                 forced = name.endswith("@cuda-cores")
+                w_ = WORKLOADS[name.split("@")[0]]
                 if forced:
                     os.environ["LIBXSMM_B200_SPMDM_TC"] = "0"
                 try:
-                    r2, _, _ = run(WORKLOADS[name.split("@")[0]], False, False)
+                    r2, e2, _ = run(w_, (not args.no_e2e) and not forced, False)
                 finally:
                     if forced:
                         os.environ.pop("LIBXSMM_B200_SPMDM_TC", None)
                 ms2 = r2["total_ms"] / args.steps
-                ach2 = r2["kernel_bytes"] / (r2["kernel_ms"] * 1e6)
-                others[name] = {"workload": WORKLOADS[name.split("@")[0]]["desc"] + (" [LIBXSMM_B200_SPMDM_TC=0]" if forced else ""), "value": r2["flops"] / (ms2 * 1e6), "unit": "GFLOP/s", "ms_per_step": ms2,
-                                "hbm_gbs": r2["step_bytes"] / (ms2 * 1e6), "kernel": r2["kernel_name"], "kernel_ms": r2["kernel_ms"],
-                                "kernel_hbm_gbs": ach2, "kernel_hbm_frac": ach2 / peak, "parts": r2["parts"], "gpu_launches": r2["launches"]}
-                tp2 = tensor_pipe_info(r2)
-                if tp2:
-                    others[name]["tensor_pipe"] = tp2
+                others[name] = {"workload": w_["desc"] + (" [LIBXSMM_B200_SPMDM_TC=0]" if forced else ""), "value": r2["flops"] / (ms2 * 1e6), "unit": "GFLOP/s", "ms_per_step": ms2,
+                                "hbm_gbs": r2["step_bytes"] / (ms2 * 1e6), "roofline": bound_of(w_, r2), "parts": r2["parts"], "gpu_launches": r2["launches"]}
+                if e2 is not None:
+                    others[name]["e2e"] = e2e_block(e2, w_)
+                if not args.no_cpu and not forced:
+                    c = cpu_reference(w_, budget_s=args.cpu_budget / 4.0)
+                    others[name]["cpu_baseline"] = {"value": c["value"], "unit": "GFLOP/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"], "ms_per_step": c["ms"]}
             except Exception as ex:      # a secondary workload must never take the headline down
                 others[name] = {"error": repr(ex)[:200]}
                 xs.clear_error()
         line["other_workloads"] = others
     if world == 1 and rank == 0 and not args.no_cpu:
         try:
-            c = cpu_reference(wl, budget_s=12.0)
+            c = cpu_reference(wl, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": c["value"], "unit": "GFLOP/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"], "ms_per_step": c["ms"]}
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": host_cores(), "kind": "reference", "sample": "failed: %r" % (ex,)}

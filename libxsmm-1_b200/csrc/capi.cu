@@ -22,6 +22,7 @@ static std::mutex g_err_mtx;
 static int g_err_code = 0;
 static char g_err_msg[1024] = "";
 static std::atomic<unsigned long long> g_launches(0);
+static std::atomic<unsigned long long> g_err_seq(0);   // bumped by every set_error: lets a call tell its own failures from older, unrelated ones
 
 int verbosity()
 {
@@ -41,6 +42,7 @@ void set_error(int code, const char* fmt, ...)
   vsnprintf(g_err_msg, sizeof(g_err_msg), fmt, ap);
   va_end(ap);
   g_err_code = (0 != code) ? code : -1;
+  g_err_seq.fetch_add(1, std::memory_order_relaxed);
   if (0 != verbosity()) fprintf(stderr, "LIBXSMM_B200 ERROR: %s\n", g_err_msg);
 }
 
@@ -95,6 +97,7 @@ struct SpmdmCtx {
   unsigned long long* d_acc;      // device counters {sum, slices done}
   bool aux_written;               // the auxiliary per-nonzero words of the current slices are valid
   bool dense_written;             // ... and so is their dense tile image
+  bool captured;                  // the current slices were (are being) produced under stream capture
   size_t dense_bytes;
 };
 
@@ -114,25 +117,42 @@ static float density_estimate(const SpmdmCtx* c)
   return (~0ull == n) ? -1.f : (float)((double)n / ((double)c->g.m * (double)c->g.k));
 }
 
+static bool stream_is_capturing(cudaStream_t stream)
+{
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaSuccess != cudaStreamIsCapturing(stream, &st)) { (void)cudaGetLastError(); return false; }
+  return cudaStreamCaptureStatusNone != st;
+}
+
 static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole, cudaStream_t stream)
 {
   a->acc = c->d_acc; a->host_total = c->d_nnz; a->total_slices = c->g.mb * c->g.kb;
+  a->write_dense = 0;
+  if (!whole) {
+    // legacy per-block call: the block gets its auxiliary words, its part of a dense image (if any) is now stale.  Whether
+    // ALL slices carry auxiliary words is unchanged: they do only if the last whole pass wrote them.
+    a->write_aux = 1;
+    c->dense_written = false;
+    return;
+  }
+  // Under stream capture the decisions must not depend on the handle's history (the graph is replayed on other inputs) and
+  // nothing may be allocated: the slices get their auxiliary words, and the dense image too if the handle already owns one;
+  // the multiply then enqueues both kernel twins and the choice is made on the device from the slices' own counts.
+  const bool capturing = stream_is_capturing(stream);
+  c->captured = capturing;
   // the orientation of the multiply that will consume the slices is not known here: the auxiliary words are
   // skipped only when no orientation would take the tensor-core side (bf16: transposed panels always do)
-  const bool skip = whole && !is_bf16 && 1 == density_hint(c, is_bf16, true, false);
+  const bool skip = !capturing && !is_bf16 && 1 == density_hint(c, is_bf16, true, false);
   a->write_aux = skip ? 0 : 1;
-  if (whole) c->aux_written = (0 != a->write_aux);
-  else c->aux_written = true;
   // Dense tile image for the tensor-core kernel (fp32, complete k-blocks; A stored m x k: 16-byte aligned rows): written
   // unless the last pass showed a matrix so sparse (< 1 %) that the CUDA-core kernels will multiply it whatever the
   // orientation of B and C.  Costs ~4 us of extra stores per 2048^2 and takes 50-90 us off the multiply.  Allocated and
   // zeroed on first use (rows and columns of partial tiles are never written and stay zero).
-  a->write_dense = 0;
   // (A stored k x m goes through the strip kernel, which writes the image from its shared-memory tile: no alignment rule)
-  if (whole && !is_bf16 && 0 == (c->g.k % 128) && c->simd_w > 1 && (a->transa || (0 == (a->lda & 3) && 0 == ((uintptr_t)a->a & 15)))) {
+  if (!is_bf16 && 0 == (c->g.k % 128) && c->simd_w > 1 && (a->transa || (0 == (a->lda & 3) && 0 == ((uintptr_t)a->a & 15)))) {
     const float d = density_estimate(c);
-    if (d < 0.f || d >= 0.01f) {
-      if (0 == c->arena.dense) {
+    if (capturing || d < 0.f || d >= 0.01f) {
+      if (0 == c->arena.dense && !capturing) {
         const size_t tiles = (size_t)((c->g.bm + 127) / 128);
         c->dense_bytes = (size_t)c->g.mb * c->g.kb * tiles * 131072;
         if (cudaSuccess == cudaMalloc((void**)&c->arena.dense, c->dense_bytes)) XB_CUDA(cudaMemsetAsync(c->arena.dense, 0, c->dense_bytes, stream));   // once per handle, ordered before the slicing kernel
@@ -143,12 +163,14 @@ static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole, cud
     }
   }
   c->dense_written = (0 != a->write_dense);
-  if (a->write_dense && whole) { a->write_aux = 0; c->aux_written = false; }   // the image replaces the per-nonzero words: every tensor-core kernel that could read them reads the image instead
+  if (a->write_dense && !capturing) a->write_aux = 0;   // the image replaces the per-nonzero words: every tensor-core kernel that could read them reads the image instead
+  c->aux_written = (0 != a->write_aux);
 }
 
 static int compute_policy(const SpmdmCtx* c, int is_bf16, bool transb, bool transc)
 {
   if (!c->aux_written && !(c->dense_written && !is_bf16)) return 1;      // the slices carry neither auxiliary words nor the dense image: CUDA cores only
+  if (c->captured) return 0;                                             // recorded into a graph: both twins, selected on the device at every replay
   return density_hint(c, is_bf16, transb, transc);
 }
 
@@ -233,13 +255,13 @@ static void compute_whole(const libxsmm_spmdm_handle* handle, char transb, char 
 {
   SpmdmCtx* c = find_ctx(handle);
   if (0 == c) return;
-  ComputeArgs a;
+  ComputeArgs a = ComputeArgs();
   a.sl = c->arena; a.b = d_b; a.c = d_c;
   a.transb = is_t(transb); a.transc = is_t(transc); a.is_bf16 = is_bf16;
   a.ldb = a.transb ? c->g.k : c->g.n;
   a.ldc = a.transc ? c->g.m : c->g.n;
   a.beta = beta; a.g = c->g; a.mb_first = 0; a.mb_count = c->g.mb;
-  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16, 0 != a.transb, 0 != a.transc); a.density_hint = density_estimate(c); a.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0;
+  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16, 0 != a.transb, 0 != a.transc); a.density_hint = density_estimate(c); a.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0; a.aux_valid = c->aux_written ? 1 : 0;
   launch_compute(a, stream);
 }
 
@@ -295,9 +317,9 @@ static void compute_block(const libxsmm_spmdm_handle* handle, char transb, char 
   const int num_n = (g.bn < g.n - n0) ? g.bn : (g.n - n0);
   const bool tb = is_t(transb), tc = is_t(transc);
   const bool dev_b = is_device_ptr(b_in), dev_c = is_device_ptr(c_in);
-  ComputeArgs a;
+  ComputeArgs a = ComputeArgs();
   a.sl = c->arena; a.transb = tb; a.transc = tc; a.is_bf16 = is_bf16; a.beta = beta; a.g = g;
-  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1; a.density_hint = -1.f; a.dense_valid = 0;   // legacy block: no tensor-core twin
+  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1; a.density_hint = -1.f; a.dense_valid = 0; a.aux_valid = 0;   // legacy block: no tensor-core twin
   char* slab = c->staging + (size_t)tid * c->staging_per_tid;
   const size_t slab_b_bytes = (((size_t)g.k * g.bn * 4) + 255) & ~(size_t)255;
   float* c_stage = (float*)(slab + slab_b_bytes);
@@ -391,7 +413,7 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena.tcpk = (uint32_t*)c->arena.tcoff;     // 4 bytes per entry: bf16 slices keep a 32-bit word per nonzero
   c->arena.slice_nnz = (uint32_t*)((char*)c->arena_base + row_bytes + col_bytes + val_bytes + val_bytes);
   XB_CUDA(cudaMemset(c->arena.slice_nnz, 0, nnz_bytes));
-  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->dense_bytes = 0; c->arena.dense = 0;
+  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->captured = false; c->dense_bytes = 0; c->arena.dense = 0;
   if (cudaSuccess == cudaHostAlloc((void**)&c->h_nnz, sizeof(unsigned long long), cudaHostAllocMapped)) {
     *c->h_nnz = ~0ull;
     if (cudaSuccess != cudaHostGetDevicePointer((void**)&c->d_nnz, c->h_nnz, 0)) c->d_nnz = 0;
@@ -536,9 +558,16 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
   const size_t a_bytes = (size_t)g.m * g.k * esz, b_bytes = (size_t)g.k * g.n * esz, c_bytes = (size_t)g.m * g.n * 4;
   const float beta_f = is_bf16 ? (float)(*(const libxsmm_bfloat16*)beta) : *(const float*)beta;
   const bool tb = is_t(transb), tc = is_t(transc);
-  if (c->d_a_bytes < a_bytes) { if (c->d_a) cudaFree(c->d_a); c->d_a = 0; XB_CUDA(cudaMalloc(&c->d_a, a_bytes)); c->d_a_bytes = a_bytes; }
-  if (c->d_b_bytes < b_bytes) { if (c->d_b) cudaFree(c->d_b); c->d_b = 0; XB_CUDA(cudaMalloc(&c->d_b, b_bytes)); c->d_b_bytes = b_bytes; }
-  if (c->d_c_bytes < c_bytes) { if (c->d_c) cudaFree(c->d_c); c->d_c = 0; XB_CUDA(cudaMalloc((void**)&c->d_c, c_bytes)); c->d_c_bytes = c_bytes; }
+  auto grow = [](void** p, size_t* have, size_t need) {       // the recorded size changes only when the allocation succeeded: a later call retries
+    if (*have >= need && 0 != *p) return;
+    if (*p) cudaFree(*p);
+    *p = 0; *have = 0;
+    XB_CUDA(cudaMalloc(p, need));
+    if (*p) *have = need;
+  };
+  grow(&c->d_a, &c->d_a_bytes, a_bytes);
+  grow(&c->d_b, &c->d_b_bytes, b_bytes);
+  grow((void**)&c->d_c, &c->d_c_bytes, c_bytes);
   if (0 == c->xs[0]) {
     for (int i = 0; i < 3; ++i) XB_CUDA(cudaStreamCreateWithFlags(&c->xs[i], cudaStreamNonBlocking));
     for (int i = 0; i < kExecPanels + 1; ++i) XB_CUDA(cudaEventCreateWithFlags(&c->xev[i], cudaEventDisableTiming));
@@ -591,13 +620,13 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
   };
   auto compute_rect = [&](int r0, int rc, int n0, int w) {
     if (rc <= 0 || w <= 0) return;
-    ComputeArgs ca;
+    ComputeArgs ca = ComputeArgs();
     ca.sl = c->arena; ca.transb = tb; ca.transc = tc; ca.is_bf16 = is_bf16;
     ca.ldb = tb ? g.k : g.n; ca.ldc = tc ? g.m : g.n;
     ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
     ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
     ca.beta = beta_f; ca.g = g; ca.mb_first = r0; ca.mb_count = rc;
-    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16, tb, tc); ca.density_hint = density_estimate(c); ca.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0;
+    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16, tb, tc); ca.density_hint = density_estimate(c); ca.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0; ca.aux_valid = c->aux_written ? 1 : 0;
     launch_compute(ca, c->xs[1]);
   };
   for (int d = 0; d < nd; ++d) {
@@ -637,6 +666,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
       sa.out = c->arena;
       c->aux_written = (0 != write_aux);
       c->dense_written = (0 != sa.write_dense);
+      c->captured = false;
       launch_slices(sa, g.kb, c->xs[1]);
       compute_rect(d, 1, 0, row_cols);
     }
@@ -667,6 +697,42 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
 struct libxsmm_dfsspmdm;
 struct libxsmm_sfsspmdm;
 
+// staging contexts of the host-pointer execute path: one per concurrent caller and device, recycled through a free list
+struct FsStaging {
+  static const int kSlots = 3;
+  int device;
+  cudaStream_t st[kSlots];
+  char* dB[kSlots];
+  char* dC[kSlots];
+  size_t capB[kSlots], capC[kSlots];
+};
+static std::mutex g_fs_pool_mtx;
+static std::vector<FsStaging*> g_fs_pool;     // idle contexts (all devices)
+
+static FsStaging* fs_staging_acquire()
+{
+  int dev = 0;
+  if (cudaSuccess != cudaGetDevice(&dev)) { (void)cudaGetLastError(); set_error(-32, "fsspmdm_execute: no current device"); return 0; }
+  {
+    std::lock_guard<std::mutex> lock(g_fs_pool_mtx);
+    for (size_t i = 0; i < g_fs_pool.size(); ++i) if (g_fs_pool[i]->device == dev) {
+      FsStaging* sg = g_fs_pool[i];
+      g_fs_pool.erase(g_fs_pool.begin() + (long)i);
+      return sg;
+    }
+  }
+  FsStaging* sg = new FsStaging();
+  memset(sg, 0, sizeof(*sg));
+  sg->device = dev;
+  return sg;
+}
+
+static void fs_staging_release(FsStaging* sg)
+{
+  std::lock_guard<std::mutex> lock(g_fs_pool_mtx);
+  g_fs_pool.push_back(sg);
+}
+
 static void fs_execute_any(const FsOperator* op, const void* B, void* C)
 {
   if (0 == op) { set_error(-30, "fsspmdm_execute: NULL handle"); return; }
@@ -679,31 +745,36 @@ static void fs_execute_any(const FsOperator* op, const void* B, void* C)
     return;
   }
   // HOST panels: pipeline column chunks through compact device staging on three streams so that
-  // upload, kernel and download of neighbouring chunks overlap
-  static std::mutex mtx;
-  std::lock_guard<std::mutex> lock(mtx);
-  const int kSlots = 3;
-  static cudaStream_t st[kSlots] = { 0, 0, 0 };
-  static char* dB[kSlots] = { 0, 0, 0 };
-  static char* dC[kSlots] = { 0, 0, 0 };
-  static size_t capB = 0, capC = 0;
+  // upload, kernel and download of neighbouring chunks overlap.  The staging context (streams + buffers) comes from a
+  // pool keyed by device and is held for the duration of the call only: concurrent callers (the reference's driver runs
+  // execute from an OpenMP loop over column panels, samples/pyfr/pyfr_driver_asp_reg.c:297-302) each get their own, on
+  // the device that is current in THEIR thread, and nothing is serialised behind a global lock.
+  FsStaging* sg = fs_staging_acquire();
+  if (0 == sg) return;
   long long chunk = 1 << 16;
   if (chunk > N) chunk = N;
   const size_t needB = (size_t)K * chunk * esz, needC = (size_t)M * chunk * esz;
-  for (int s = 0; s < kSlots; ++s) if (0 == st[s]) XB_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
-  if (capB < needB) { for (int s = 0; s < kSlots; ++s) { if (dB[s]) cudaFree(dB[s]); dB[s] = 0; XB_CUDA(cudaMalloc((void**)&dB[s], needB)); } capB = needB; }
-  if (capC < needC) { for (int s = 0; s < kSlots; ++s) { if (dC[s]) cudaFree(dC[s]); dC[s] = 0; XB_CUDA(cudaMalloc((void**)&dC[s], needC)); } capC = needC; }
-  for (int s = 0; s < kSlots; ++s) if (0 == dB[s] || 0 == dC[s]) { capB = capC = 0; return; }
-  int slot = 0;
-  for (long long n0 = 0; n0 < N; n0 += chunk, slot = (slot + 1) % kSlots) {
-    const long long w = (N - n0 < chunk) ? (N - n0) : chunk;
-    XB_CUDA(cudaMemcpy2DAsync(dB[slot], w * esz, (const char*)B + n0 * esz, (size_t)ldb * esz, w * esz, K, cudaMemcpyHostToDevice, st[slot]));
-    if (fs_needs_c_input(op))   // beta == 1, or rows the sparse branch leaves untouched
-      XB_CUDA(cudaMemcpy2DAsync(dC[slot], w * esz, (char*)C + n0 * esz, (size_t)ldc * esz, w * esz, M, cudaMemcpyHostToDevice, st[slot]));
-    fs_execute(op, dB[slot], dC[slot], w, w, w, st[slot]);
-    XB_CUDA(cudaMemcpy2DAsync((char*)C + n0 * esz, (size_t)ldc * esz, dC[slot], w * esz, w * esz, M, cudaMemcpyDeviceToHost, st[slot]));
+  bool ok = true;
+  for (int s = 0; s < FsStaging::kSlots; ++s) {
+    if (0 == sg->st[s]) XB_CUDA(cudaStreamCreateWithFlags(&sg->st[s], cudaStreamNonBlocking));
+    if (sg->capB[s] < needB) { if (sg->dB[s]) cudaFree(sg->dB[s]); sg->dB[s] = 0; sg->capB[s] = 0; XB_CUDA(cudaMalloc((void**)&sg->dB[s], needB)); if (sg->dB[s]) sg->capB[s] = needB; }
+    if (sg->capC[s] < needC) { if (sg->dC[s]) cudaFree(sg->dC[s]); sg->dC[s] = 0; sg->capC[s] = 0; XB_CUDA(cudaMalloc((void**)&sg->dC[s], needC)); if (sg->dC[s]) sg->capC[s] = needC; }
+    ok = ok && 0 != sg->st[s] && 0 != sg->dB[s] && 0 != sg->dC[s];
   }
-  for (int s = 0; s < kSlots; ++s) XB_CUDA(cudaStreamSynchronize(st[s]));
+  if (ok) {
+    int slot = 0;
+    for (long long n0 = 0; n0 < N; n0 += chunk, slot = (slot + 1) % FsStaging::kSlots) {
+      const long long w = (N - n0 < chunk) ? (N - n0) : chunk;
+      cudaStream_t st = sg->st[slot];
+      XB_CUDA(cudaMemcpy2DAsync(sg->dB[slot], w * esz, (const char*)B + n0 * esz, (size_t)ldb * esz, w * esz, K, cudaMemcpyHostToDevice, st));
+      if (fs_needs_c_input(op))   // beta == 1, or rows the sparse branch leaves untouched
+        XB_CUDA(cudaMemcpy2DAsync(sg->dC[slot], w * esz, (char*)C + n0 * esz, (size_t)ldc * esz, w * esz, M, cudaMemcpyHostToDevice, st));
+      fs_execute(op, sg->dB[slot], sg->dC[slot], w, w, w, st);
+      XB_CUDA(cudaMemcpy2DAsync((char*)C + n0 * esz, (size_t)ldc * esz, sg->dC[slot], w * esz, w * esz, M, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < FsStaging::kSlots; ++s) XB_CUDA(cudaStreamSynchronize(sg->st[s]));
+  }
+  fs_staging_release(sg);
 }
 
 libxsmm_dfsspmdm* libxsmm_dfsspmdm_create(libxsmm_blasint M, libxsmm_blasint N, libxsmm_blasint K,
@@ -964,8 +1035,9 @@ int libxsmm_b200_sparse_matmul(libxsmm_spmdm_datatype datatype, char transa, cha
     else e = it->second;
     e->last_use = ++g_mm_clock;
   }
+  const unsigned long long seq = g_err_seq.load(std::memory_order_relaxed);
   libxsmm_spmdm_exec_stream(&e->handle, e->slices, datatype, transa, transb, transc, d_a, d_b, beta, d_c, stream);
-  return libxsmm_b200_last_error();
+  return (seq == g_err_seq.load(std::memory_order_relaxed)) ? 0 : libxsmm_b200_last_error();   // an older, unrelated sticky error is not this call's failure
 }
 
 int libxsmm_b200_sparse_matmul_cache_entries(void)

@@ -144,8 +144,10 @@ struct ComputeArgs {
   // selected kernel does the work (dense <=> total nnz >= tc_min_nnz).  tc_twin = 0: no twin, always run.
   int tc_twin;
   unsigned long long tc_min_nnz;
+  int aux_valid;        // the slices' per-nonzero auxiliary words (tcoff / tcpk) were written for ALL slices by the pass these slices come from
   int dense_valid;      // the slices' dense tile image (SliceArena::dense) was written by the slicing pass these slices come from
   float density_hint;   // host's lagging estimate of nnz / (M*K) from the last completed slicing pass, < 0: unknown (performance only)
+  int debug_flags;  // developer timing aid (LIBXSMM_B200_K2S_DEBUG; results are wrong when set): 1 = skip the multiply-adds, 2 = skip the B tile loads
   int tc_hint;      // host's lagging density hint: 0 unknown / borderline (enqueue both twins), 1 clearly sparse (CUDA cores only), 2 clearly dense (tensor cores only)
 };
 
@@ -169,6 +171,7 @@ __device__ __forceinline__ unsigned long long xb_total_nnz(const uint32_t* slice
 void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream);
 void launch_compute(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tma(const ComputeArgs& args, bool partial, cudaStream_t stream);
+bool launch_compute_sp(const ComputeArgs& args, cudaStream_t stream);    // K2s: cluster-multicast order-preserving kernel (spmdm_compute_sp.cu)
 bool launch_compute_tc(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tc16(const ComputeArgs& args, cudaStream_t stream);   // tcgen05 branch for bf16 inputs
 bool launch_compute_tc16p(const ComputeArgs& args, cudaStream_t stream);

@@ -363,7 +363,8 @@ bool launch_compute_tc(const ComputeArgs& a, cudaStream_t stream)
   // performance-only choice (every instantiation is complete): the host's estimate is one call old at most
   bool sparse_variant = a.density_hint >= 0.f && a.density_hint < 0.25f;
   { const char* e = getenv("LIBXSMM_B200_K4_VARIANT"); if (e && 's' == *e) sparse_variant = true; else if (e && 'd' == *e) sparse_variant = false; }   // developer switch
-  const bool image = 0 != a.dense_valid && 0 != a.sl.dense && !(getenv("LIBXSMM_B200_K4_VARIANT"));   // the slicing pass left the A image: nothing to rebuild
+  const bool image = 0 != a.dense_valid && 0 != a.sl.dense && !(getenv("LIBXSMM_B200_K4_VARIANT") && 0 != a.aux_valid);   // the slicing pass left the A image: nothing to rebuild
+  if (!image && 0 == a.aux_valid) return false;   // neither the image nor the per-nonzero words: the CUDA-core kernels multiply these slices
   const void* kern = image ? (const void*)spmdm_compute_tc_kernel<16, false, true>
                    : (sparse_variant ? (const void*)spmdm_compute_tc_kernel<8, true, false> : (const void*)spmdm_compute_tc_kernel<16, false, false>);
   ensure_smem_optin(kern, TC_SMEM_BYTES);

@@ -364,6 +364,7 @@ bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes
 // returns false when the panel does not qualify (caller falls back to K4h / the CUDA-core kernels)
 bool launch_compute_tc16p(const ComputeArgs& a, cudaStream_t stream)
 {
+  if (0 == a.aux_valid) return false;   // these kernels rebuild A from the packed per-nonzero words the slicing pass writes
   if (!a.is_bf16) return false;
   if (!a.transc && (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3))) return false;
   CUtensorMap map;

@@ -3,6 +3,7 @@
 //   K2  spmdm_compute_kernel  C = beta*C + slices * B (reference compute templates)
 // Hand-written CUDA; no library calls on the data path.
 #include "common.cuh"
+#include <map>
 #include <cooperative_groups.h>
 #include <mutex>
 #include <cstdlib>
@@ -159,8 +160,12 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
     for (int q = 0; q < nstrips; ++q) *cluster.map_shared_rank(&strip_tot[strip], q) = total;
   }
   cluster.sync();
-  uint32_t base = 0;
+  uint32_t base = 0, slice_total = 0;
   for (int q = 0; q < strip; ++q) base += strip_tot[q];
+  for (int q = 0; q < nstrips; ++q) slice_total += strip_tot[q];
+  // a completely full 512 x 128 slice wraps the reference's u16 counter (template :72): its last row pointer reads 0 and
+  // the reference's multiply sees row 511 as EMPTY.  The dense image mirrors that (the CSR arrays do by construction).
+  const bool wrapped = slice_total >= 65536u;
 
   // ---- pass 2: write row pointers, column indices, values ---------------------------------------
   uint16_t* ro = p.out.rowidx + (size_t)s * (g.bm + 1);
@@ -194,9 +199,10 @@ __global__ void __launch_bounds__(K1_THREADS) spmdm_slice_kernel(const SliceArgs
         float* img = p.out.dense + ((size_t)s * ((g.bm + 127) / 128) + (size_t)(rr >> 7)) * 32768
                    + (size_t)(j >> 1) * 16384 + (size_t)(j & 1) * 4096
                    + (size_t)(trow >> 3) * 256 + (size_t)(trow & 7) * 32 + (size_t)((((lane >> 2) ^ trow) & 7) * 4 + (lane & 3));
-        const float vh = keep ? __uint_as_float(__float_as_uint(v) & 0xFFFFE000u) : 0.f;
+        const bool in_image = keep && !(wrapped && rr == g.bm - 1);
+        const float vh = in_image ? __uint_as_float(__float_as_uint(v) & 0xFFFFE000u) : 0.f;
         img[0] = vh;
-        img[8192] = keep ? (v - vh) : 0.f;
+        img[8192] = in_image ? (v - vh) : 0.f;
       }
       pos += __popc(bal);
     }
@@ -323,6 +329,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
   if (0 == lane) wtot[warp] = mine;
   __syncthreads();
   uint32_t pos;   // first output position of this warp's rows
+  bool wrapped;   // completely full 512 x 128 slice: the reference's u16 counter wraps and its multiply sees the last row as empty
   {
     const uint32_t t = wtot[lane];
     uint32_t inc = t;
@@ -333,6 +340,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
     }
     pos = __shfl_sync(0xffffffffu, inc - t, warp);
     const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    wrapped = total >= 65536u;
     if (0 == tid) {
       p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
       p.out.slice_nnz[s] = total;
@@ -368,6 +376,8 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
                    + (size_t)(lane >> 4) * 16384 + (size_t)((lane >> 3) & 1) * 4096
                    + (size_t)(trow >> 3) * 256 + (size_t)(trow & 7) * 32 + (size_t)(((lane & 7) ^ (trow & 7)) * 4);
         uint4 hi, lo;
+        const uint32_t mraw = (masks[j / 8] >> (4 * (j % 8))) & 15u;
+        const uint32_t m = (wrapped && rr == g.bm - 1) ? 0u : mraw;   // the image mirrors the wrapped row pointer: row 511 of a full slice is empty
         hi.x = (m & 1u) ? (v.x & 0xFFFFE000u) : 0u; lo.x = (m & 1u) ? __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x)) : 0u;
         hi.y = (m & 2u) ? (v.y & 0xFFFFE000u) : 0u; lo.y = (m & 2u) ? __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y)) : 0u;
         hi.z = (m & 4u) ? (v.z & 0xFFFFE000u) : 0u; lo.z = (m & 4u) ? __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z)) : 0u;
@@ -986,12 +996,24 @@ static void launch_compute_variant(const ComputeArgs& a, cudaStream_t stream)
 //   [0, n_full_end)          full-width blocks: in-order fma chain
 //   [n_full_end, tail_from)  narrow block, vector part: per-kb partial sums
 //   [tail_from, N)           narrow block, scalar part: in-order fma chain (GCC contracts += b*v)
-static cudaStream_t side_stream()
+// The narrow last block forks onto a side stream.  The stream and the two events of the fork / join are created once per
+// (host thread, device): a process may drive several devices, callers may run concurrently, and nothing is created or
+// destroyed on the hot path (which also keeps the pattern legal under stream capture).
+struct SideCtx { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideCtx* side_ctx()
 {
-  static cudaStream_t s = 0;
-  static std::once_flag once;
-  std::call_once(once, [] { XB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); });
-  return s;
+  static thread_local std::map<int, SideCtx*> per_device;
+  int dev = 0;
+  if (cudaSuccess != cudaGetDevice(&dev)) { (void)cudaGetLastError(); return 0; }
+  SideCtx*& c = per_device[dev];
+  if (0 == c) {
+    c = new SideCtx();
+    c->stream = 0; c->fork = 0; c->join = 0;
+    XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    XB_CUDA(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+    XB_CUDA(cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming));
+  }
+  return (c->stream && c->fork && c->join) ? c : 0;
 }
 
 // LIBXSMM_B200_SPMDM_TC: "0" never use the tensor-core branch, "1" always (when the panel qualifies),
@@ -1022,7 +1044,8 @@ static bool launch_tc_f32(const ComputeArgs& a, cudaStream_t stream)
 
 static void launch_part(const ComputeArgs& a, bool partial, cudaStream_t stream)
 {
-  if (launch_compute_tma(a, partial, stream)) return;   // TMA fast path (spmdm_compute_tma.cu)
+  if (!partial && launch_compute_sp(a, stream)) return;  // K2s: cluster-multicast TMA kernel (spmdm_compute_sp.cu)
+  if (launch_compute_tma(a, partial, stream)) return;   // K2: narrow-block parts and LIBXSMM_B200_K2S=0 (spmdm_compute_tma.cu)
   if (a.is_bf16) {
     if (partial) launch_compute_variant<true, true, 4>(a, stream);
     else launch_compute_variant<true, false, 8>(a, stream);
@@ -1056,15 +1079,13 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
   const int cut[4] = { c_lo, min(max(args.modes.n_full_end, c_lo), c_hi), min(max(args.modes.tail_from, c_lo), c_hi), c_hi };
   // the narrow last block (at most bn - 1 columns, two small launches) runs on a side stream, forked from
   // and joined back into `stream`, so that it overlaps the main launch instead of serialising behind it
-  const bool narrow = (cut[3] > cut[1]) && (cut[1] > cut[0]);
-  cudaEvent_t fork = 0, join = 0;
+  SideCtx* sc = ((cut[3] > cut[1]) && (cut[1] > cut[0])) ? side_ctx() : 0;
+  const bool narrow = 0 != sc;
   cudaStream_t side = stream;
   if (narrow) {
-    side = side_stream();
-    XB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    XB_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-    XB_CUDA(cudaEventRecord(fork, stream));
-    XB_CUDA(cudaStreamWaitEvent(side, fork, 0));
+    side = sc->stream;
+    XB_CUDA(cudaEventRecord(sc->fork, stream));
+    XB_CUDA(cudaStreamWaitEvent(side, sc->fork, 0));
   }
   for (int part = 2; part >= 0; --part) {
     const int lo = cut[part], hi = cut[part + 1];
@@ -1081,10 +1102,8 @@ void launch_compute(const ComputeArgs& args, cudaStream_t stream)
   if (args2.tc_twin > 0) note_compute_kernel(args.is_bf16 ? "twin: spmdm_compute_tc16p_kernel | spmdm_compute_tma_kernel (selected on the device by nnz)"
                                                           : "twin: spmdm_compute_tc_kernel | spmdm_compute_tma_kernel (selected on the device by nnz)");
   if (narrow) {
-    XB_CUDA(cudaEventRecord(join, side));
-    XB_CUDA(cudaStreamWaitEvent(stream, join, 0));
-    XB_CUDA(cudaEventDestroy(fork));
-    XB_CUDA(cudaEventDestroy(join));
+    XB_CUDA(cudaEventRecord(sc->join, side));
+    XB_CUDA(cudaStreamWaitEvent(stream, sc->join, 0));
   }
 }
 

@@ -114,16 +114,18 @@ class Oracle:
         self.lib.orc_spmdm_slices(g.vec, dtype, transa.encode(), _ptr(a), simd_w, _ptr(ro), _ptr(co), _ptr(va))
         return ro, co, va
 
-    def compute(self, g, slices, b, c, transb="N", transc="N", beta=0.0, simd_w=None, tail_fma=1):
+    def compute(self, g, slices, b, c, transb="N", transc="N", beta=0.0, simd_w=None, tail_fma=1, fix_q17=False):
         """in-place on c (float32).  For bf16 pass beta as the float the reference derives
-        from the raw bits: float(int(bits))."""
+        from the raw bits: float(int(bits)).  fix_q17: scale ALL rows by beta in the AVX-512
+        instantiation's transc='T' staging (the reference leaves rows 8..15 of each 16 x 16
+        block unscaled, quirk Q17; mirrored by default because this is the restatement)."""
         b = np.ascontiguousarray(b)
         dtype = 0 if b.dtype == np.float32 else 1
         assert c.dtype == np.float32 and c.flags.c_contiguous
         simd_w = simd_width_for_bn(g.bn) if simd_w is None else simd_w
         ro, co, va = slices
         self.lib.orc_spmdm_compute(g.vec, dtype, transb.encode(), transc.encode(), float(beta),
-                                   _ptr(ro), _ptr(co), _ptr(va), _ptr(b), _ptr(c), simd_w, tail_fma)
+                                   _ptr(ro), _ptr(co), _ptr(va), _ptr(b), _ptr(c), simd_w, int(tail_fma) | (2 if fix_q17 else 0))
         return c
 
     # -- fsspmdm -------------------------------------------------------------------------

@@ -131,16 +131,24 @@ void orc_spmdm_slices(const int* g, int dtype, char transa, const void* a, int s
  * The bf16 variant widens B on staging (bf16 tpl.c:246-279); C stays fp32.
  * Row counts are taken as int differences of the u16 row pointers, so a wrapped slice
  * (end < start) contributes nothing, as in the reference (tpl.c:292-297).
+ * Quirk Q17 (AVX-512 instantiation only): staging beta*C for transc == 'T' and beta not in
+ * {0, 1} transposes SIMD_WIDTH x SIMD_WIDTH blocks and then scales EIGHT rows of each block,
+ * whatever the vector width (fp32 tpl.c:163-172, bf16 tpl.c:173-182: n_block_size*0 .. *7).
+ * With 16-wide vectors rows 8..15 of every complete 16 x 16 block therefore start from C
+ * instead of beta*C.  Mirrored here for simd_w == 16 unless flags bit 1 is set
+ * (flags = tail_fma | 2: the scaling every other path of the reference performs).
  */
 void orc_spmdm_compute(const int* g, int dtype, char transb, char transc, float beta,
                        const uint16_t* rowidx, const uint16_t* colidx, const float* values,
-                       const void* b, float* c, int simd_w, int tail_fma)
+                       const void* b, float* c, int simd_w, int flags)
 {
+  const int tail_fma = flags & 1, fix_q17 = flags & 2;
   const int M = g[G_M], N = g[G_N], K = g[G_K], bm = g[G_BM], bn = g[G_BN], bk = g[G_BK];
   const int mbc = g[G_MB], nbc = g[G_NB], kbc = g[G_KB];
   const size_t cap = (size_t)bm * bk;
   int mb, nb, ml, nl, kb, j;
   if (simd_w < 1) simd_w = 1;
+  const int fused = (simd_w > 1);
   for (mb = 0; mb < mbc; ++mb) for (nb = 0; nb < nbc; ++nb) {
     const int m0 = mb * bm, n0 = nb * bn;
     const int num_m = ((m0 + bm) > M ? M : (m0 + bm)) - m0;
@@ -152,7 +160,9 @@ void orc_spmdm_compute(const int* g, int dtype, char transb, char transc, float 
     for (ml = 0; ml < num_m; ++ml) for (nl = 0; nl < num_n; ++nl) {
       const size_t cat = is_t(transc) ? ((size_t)(n0 + nl) * M + m0 + ml) : ((size_t)(m0 + ml) * N + n0 + nl);
       const int mode = !narrow ? 0 : (nl < tail_from ? 1 : 2);
-      float run = (0.f == beta) ? 0.f : ((1.f == beta) ? c[cat] : beta * c[cat]);
+      const int q17 = is_t(transc) && 16 == simd_w && !fix_q17 && (ml % 16) >= 8
+                      && ml < (num_m / 16) * 16 && nl < (num_n / 16) * 16;   /* row 8..15 of a complete 16 x 16 block: not scaled */
+      float run = (0.f == beta) ? 0.f : ((1.f == beta || q17) ? c[cat] : beta * c[cat]);
       for (kb = 0; kb < kbc; ++kb) {
         const int s = kb * mbc + mb;
         const uint16_t* ro = rowidx + (size_t)s * (bm + 1);
@@ -164,7 +174,11 @@ void orc_spmdm_compute(const int* g, int dtype, char transb, char transc, float 
           const size_t kk = (size_t)kb * bk + co[j];
           const size_t bat = is_t(transb) ? ((size_t)(n0 + nl) * K + kk) : (kk * N + n0 + nl);
           const float bv = (0 == dtype) ? ((const float*)b)[bat] : bf16_widen(((const uint16_t*)b)[bat]);
-          if (0 == mode) run = fmaf(va[j], bv, run);
+          if (!fused) {   /* scalar instantiation: _MM_FMADD_FP32(x, y, z) is ((x)*(y))+(z) in a function without FMA target (libxsmm_spmdm_begin.h:51): two roundings */
+            volatile float p = va[j] * bv;
+            if (1 == mode) sum = p + sum; else run = p + run;
+          }
+          else if (0 == mode) run = fmaf(va[j], bv, run);
           else if (1 == mode) sum = fmaf(va[j], bv, sum);
           else if (tail_fma) run = fmaf(bv, va[j], run);
           else { volatile float p = bv * va[j]; run = run + p; }

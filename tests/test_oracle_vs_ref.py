@@ -95,3 +95,85 @@ def test_sfsspmdm(oracle, ref, xs, beta):
     OC = C0.copy()
     oracle.sfsspmdm_execute(a, B, OC, beta)
     np.testing.assert_array_equal(bits(OC), bits(C))
+
+
+# ---- the reference's other two instantiations (src/libxsmm_spmdm.c:557-583) -----------------------------------------------
+# AVX-512 (bn = 96, 16-wide vectors): `oracle/build_ref.sh avx512`.  Scalar (bn = 6): the AVX2 build run with
+# LIBXSMM_TARGET=sse -- fp32 only, the scalar bf16 path of the reference is wrong.  They pin the
+# restatement's mode boundaries (vector part / per-k-block partial sums / scalar tail) for simd_w = 16 and 1.
+@pytest.fixture(scope="session")
+def ref512():
+    import os
+    import pyoracle
+    if "avx512f" not in open("/proc/cpuinfo").read():
+        pytest.skip("host has no AVX-512")
+    if not pyoracle.Ref.available("avx512") and os.path.isdir("/root/reference/src"):
+        pyoracle.build_ref("avx512")
+    if not pyoracle.Ref.available("avx512"):
+        pytest.skip("oracle/_ref avx512 flavour not built (no /root/reference here)")
+    return pyoracle.Ref("avx512")
+
+
+@pytest.mark.parametrize("M,N,K,d,dt,ta,tb,tc,beta,T", SP + [(300, 330, 260, 0.2, "f32", "N", "N", "N", 0.5, 1), (512, 250, 256, 0.1, "bf16", "N", "N", "N", 0, 1)])
+def test_spmdm_avx512_instantiation(oracle, ref512, xs, M, N, K, d, dt, ta, tb, tc, beta, T):
+    import pyoracle
+    A, B, C0 = xs.workloads.spmdm_inputs(M, N, K, d, dtype=dt, seed=M ^ N, transa=ta, transb=tb, transc=tc)
+    C = C0.copy()
+    g, sl, _ = ref512.spmdm(A, B, C, M, N, K, ta, tb, tc, beta, threads=T)
+    assert g.bn == 96
+    og = oracle.geometry(M, N, K, T, bn=96)
+    assert dict(og) == dict(g)
+    assert xs.spmdm_geometry(M, N, K, T, 96) == {k: g[k] for k in ("m", "n", "k", "bm", "bn", "bk", "mb", "nb", "kb")}
+    osl = oracle.slices(og, A, ta)
+    cnt = pyoracle.slice_counts(g, sl[0])
+    for s in range(g.nslices):
+        nrows = min(g.bm, g.m - (s % g.mb) * g.bm)
+        np.testing.assert_array_equal(osl[0][s, :nrows + 1], sl[0][s, :nrows + 1])
+        np.testing.assert_array_equal(osl[1][s, :cnt[s]], sl[1][s, :cnt[s]])
+        np.testing.assert_array_equal(bits(osl[2][s, :cnt[s]]), bits(sl[2][s, :cnt[s]]))
+    OC = C0.copy()
+    oracle.compute(og, osl, B, OC, tb, tc, float(beta))
+    np.testing.assert_array_equal(bits(OC), bits(C))
+
+
+SSE_WORKER = r'''
+import os, sys
+os.environ["LIBXSMM_TARGET"] = "sse"          # read once by the reference's init (src/libxsmm_main.c:618)
+import numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "oracle"))
+import importlib, pyoracle
+w = importlib.import_module("libxsmm-1_b200.workloads")
+ref, orc = pyoracle.Ref(), pyoracle.Oracle()
+for (M, N, K, d, ta, tb, tc, beta, T) in [(300, 200, 260, 0.1, "N", "N", "N", 0.0, 1), (300, 203, 260, 0.1, "N", "N", "N", 0.5, 3),
+                                          (257, 190, 300, 0.5, "T", "N", "T", 1.0, 1), (257, 190, 300, 0.5, "N", "T", "N", 0.0, 2), (64, 7, 130, 0.3, "N", "N", "N", 0.25, 1)]:
+    A, B, C0 = w.spmdm_inputs(M, N, K, d, dtype="f32", seed=M ^ N, transa=ta, transb=tb, transc=tc)
+    A[0, 0] = np.nan                           # the scalar path KEEPS NaN (quirk Q3)
+    C = C0.copy()
+    g, sl, _ = ref.spmdm(A, B, C, M, N, K, ta, tb, tc, beta, threads=T)
+    assert g.bn == 6, g
+    og = orc.geometry(M, N, K, T, bn=6)
+    assert dict(og) == dict(g), (og, g)
+    osl = orc.slices(og, A, ta)
+    cnt = pyoracle.slice_counts(g, sl[0])
+    for s in range(g.nslices):
+        nrows = min(g.bm, g.m - (s %% g.mb) * g.bm)
+        assert np.array_equal(osl[0][s, :nrows + 1], sl[0][s, :nrows + 1])
+        assert np.array_equal(osl[1][s, :cnt[s]], sl[1][s, :cnt[s]])
+        assert np.array_equal(osl[2][s, :cnt[s]].view(np.uint32), sl[2][s, :cnt[s]].view(np.uint32))
+    OC = C0.copy()
+    orc.compute(og, osl, B, OC, tb, tc, float(beta))
+    same = (OC.view(np.uint32) == C.view(np.uint32)) | (np.isnan(OC) & np.isnan(C))
+    assert same.all(), "scalar instantiation: %%d elements differ" %% int((~same).sum())
+print("sse ok")
+'''
+
+
+def test_spmdm_scalar_instantiation(oracle, ref, tmp_path):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "sse_worker.py"
+    script.write_text(SSE_WORKER % {"root": root})
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "sse ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

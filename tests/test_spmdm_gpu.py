@@ -119,6 +119,38 @@ def test_spmdm_matches_oracle(gpu, oracle, M, N, K, density, dtype, ta, tb, tc, 
     gpu.check()
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("M,N,K,density", [(512, 768, 512, 0.02), (1024, 512, 384, 0.30), (256, 1100, 640, 0.004)])
+def test_mixed_sign_denormal_overflow(gpu, oracle, dtype, M, N, K, density):
+    """Inputs the uniform [0,1) workloads never produce: both signs (cancellation), denormal A and B entries, products
+    that underflow, sums that overflow to +-Inf.  The order-preserving kernels (K2s uses the mixed-precision
+    fma.rn.f32.bf16 for bf16 slices) must still reproduce the reference's fmaf chain bit for bit."""
+    w = gpu.workloads
+    rng = np.random.default_rng(M + N + K + (1 if dtype == "bf16" else 0))
+    A = np.where(rng.random((M, K)) < density, rng.uniform(-1.0, 1.0, (M, K)), 0.0).astype(np.float32)
+    B = rng.uniform(-1.0, 1.0, (K, N)).astype(np.float32)
+    C0 = rng.uniform(-1.0, 1.0, (M, N)).astype(np.float32)
+    nzr, nzc = np.nonzero(A)
+    assert len(nzr) > 64
+    pick = rng.permutation(len(nzr))
+    for j, v in zip(pick[:16], [1e-40, -3e-39, 9.2e-41, 1e-38] * 4):          # denormal (and near-denormal) operator entries
+        A[nzr[j], nzc[j]] = v
+    for j in pick[16:24]:                                                     # huge entries: partial sums overflow
+        A[nzr[j], nzc[j]] = 3e38
+    B[rng.integers(0, K, 64), rng.integers(0, N, 64)] = np.float32(1e-39)     # denormal B entries
+    B[nzc[pick[16]], :] = np.float32(2.5)                                      # 3e38 * 2.5 -> Inf in that output row
+    B[rng.integers(0, K, 64), rng.integers(0, N, 64)] = np.float32(1e-30)     # tiny x tiny products underflow to denormals / 0
+    if dtype == "bf16":
+        A = w.to_bf16_bits(A); B = w.to_bf16_bits(B)
+    g, sl, C = gpu_spmdm(gpu, A, B, C0, M, N, K, beta=1.0 if dtype == "f32" else 0, bf16=(dtype == "bf16"))
+    og, osl, OC = oracle_spmdm(oracle, g, A, B, C0, "N", "N", "N", 1.0 if dtype == "f32" else 0.0)
+    valid_slices_equal(og, sl, osl)
+    assert np.isinf(OC).any() and np.isfinite(OC).any()
+    same = (C.view(np.uint32) == OC.view(np.uint32)) | (np.isnan(C) & np.isnan(OC))
+    assert same.all(), "%d elements differ from the reference's rounding sequence" % int((~same).sum())
+    gpu.check()
+
+
 def test_special_values_in_a(gpu, oracle):
     """NaN / -0.0 / Inf / denormal handling of the slicing (reference quirk Q3): the vector part of the
     reference uses an ordered compare (drops NaN), the scalar remainder keeps NaN."""
