@@ -497,7 +497,7 @@ def main():
     if args.gpus > 1 and world == 1:      # convenience: re-launch under torchrun like the driver does
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
-        return subprocess.call(cmd)
+        return subprocess.call(cmd, stdout=out)      # the ranks write to the real stdout, not to the redirected descriptor 1
 
     xs = importlib.import_module("libxsmm-1_b200")
     xs.load()

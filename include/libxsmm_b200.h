@@ -124,8 +124,9 @@ LIBXSMM_API libxsmm_sfsspmdm* libxsmm_b200_sfsspmdm_create_mtx(const char* path,
  * geometry: the block geometry libxsmm_spmdm_init would choose (reference src/libxsmm_spmdm.c:552-608)
  *   for bn = 48 | 96 | 6; geom[9] = m n k bm bn bk mb nb kb.  Returns 0 on success.
  * plan: what create() decides for an operator (reference src/libxsmm_fsspmdm.c:88-143 and
- *   src/generator_spgemm_csr_asparse_reg.c:111-150): info[5] = nnz, unique values, 1 if the reference
- *   takes its sparse_reg branch, bytes of x86 code it would emit (0 if not evaluated), N_chunksize.
+ *   src/generator_spgemm_csr_asparse_reg.c:111-150): info[6] = nnz, unique values, 1 if the reference
+ *   takes its sparse_reg branch, bytes of x86 code it would emit (0 if not evaluated), N_chunksize, and the
+ *   form of the kernel create() bakes (0 none: generic kernel, 1 B rows in registers, 2 B strip in shared memory).
  * kernel_source: the CUDA source create() would bake for the operator (free with free_string). */
 LIBXSMM_API int libxsmm_b200_spmdm_geometry(int M, int N, int K, int max_threads, int bn, int* geom);
 LIBXSMM_API int libxsmm_b200_fsspmdm_plan(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta,

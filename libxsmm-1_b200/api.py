@@ -633,7 +633,7 @@ def fsspmdm_plan(a_dense, N=16, ldb=None, ldc=None, beta=0.0, lda=None):
     a = np.ascontiguousarray(a_dense)
     assert a.dtype in (np.float64, np.float32)
     M, K = a.shape
-    info = (ctypes.c_longlong * 5)()
+    info = (ctypes.c_longlong * 6)()
     rc = load().libxsmm_b200_fsspmdm_plan(int(a.dtype == np.float64), M, N, K, K if lda is None else lda,
                                           N if ldb is None else ldb, N if ldc is None else ldc, float(beta),
                                           a.ctypes.data, ctypes.cast(info, ctypes.c_void_p))
@@ -641,7 +641,8 @@ def fsspmdm_plan(a_dense, N=16, ldb=None, ldc=None, beta=0.0, lda=None):
         code, msg = last_error()
         clear_error()
         raise ValueError(msg)
-    return dict(nnz=int(info[0]), n_unique=int(info[1]), sparse=bool(info[2]), x86_code_size=int(info[3]), chunk=int(info[4]))
+    return dict(nnz=int(info[0]), n_unique=int(info[1]), sparse=bool(info[2]), x86_code_size=int(info[3]), chunk=int(info[4]),
+                form={0: "generic", 1: "baked-registers", 2: "baked-strip"}[int(info[5])])
 
 
 def fsspmdm_kernel_source(a_dense, N=16, ldb=None, ldc=None, beta=0.0):

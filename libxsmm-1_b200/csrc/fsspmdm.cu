@@ -284,6 +284,7 @@ int fs_is_double(const FsOperator* o) { return o ? o->is_double : 0; }
 void fs_plan_info(const FsOperator* o, long long* info)
 {
   info[0] = o->nnz; info[1] = o->n_unique; info[2] = o->sparse_branch; info[3] = o->x86_code_size; info[4] = o->N_chunksize;
+  info[5] = fs_jit_form(o->is_double, (0 == ((o->ldb | o->ldc) & 1)) ? 1 : 0, o->M, o->K, o->rowptr.data(), o->col.data());
 }
 char* fs_kernel_source(const FsOperator* o)
 {

@@ -4,6 +4,7 @@
 // create() falls back to the generic kernel and records the reason.
 #include "fsspmdm_jit.h"
 #include "common.cuh"
+#include <cuda.h>
 #include <nvrtc.h>
 #include <dlfcn.h>
 #include <cstdio>
@@ -13,6 +14,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <map>
 #include <mutex>
 
@@ -23,7 +25,14 @@ struct FsJit {
   cudaKernel_t kern;
   int cols_per_thread;  // 1, or 2 (float, even pitches: 8-byte accesses)
   int block;
+  // strip form (operators whose B rows do not fit the register file): a CTA stages K x 32 columns of B in shared memory by TMA
+  int strip;            // 0: register form
+  int esz, krows, box_rows, strip_w;
+  size_t smem;
 };
+
+bool make_tensor_map_2d(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
+                        unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows);
 
 namespace {
 
@@ -269,7 +278,132 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
   return s;
 }
 
-bool supported(int is_double, int M, int K, const int* rowptr, const int* col)
+// ---- strip form --------------------------------------------------------------------------------------------------------
+// For operators with more used B rows than the register file holds (> 100 double / 200 float: every p4..p6 hex / pri PyFR
+// operator, e.g. p4/hex/m0 150 x 125, up to p5/hex/m132 216 x 648) the B rows live in SHARED memory instead: a CTA owns 32
+// consecutive columns, one thread stages the K x 32 strip with TMA (cp.async.bulk.tensor over the caller's strided panel:
+// rows past K and columns past N are zero-filled by the hardware), and every output row is again a straight-line chain of
+// fused multiply-adds with literal operator values, its B operand read from shared memory at a literal offset (lane =
+// column: conflict-free).  The rows are dealt out to G warps (longest-processing-time first, four rows at a time so that
+// four independent chains interleave), each warp running its own section of the emitted code on the same strip; the order
+// of the multiply-adds inside a row is the reference's (ascending k).  Per nonzero: one LDS + one FMA.
+struct StripPlan { int G, W, box_rows, nboxes, krows; size_t smem; std::vector<std::vector<int> > blocks; };   // blocks[g] = first rows of the 4-row blocks of warp g
+
+const int kStripW = 32;
+
+StripPlan strip_plan(int is_double, int M, int K, const int* rowptr)
+{
+  StripPlan p;
+  const int esz = is_double ? 8 : 4;
+  p.nboxes = (K + 255) / 256;                       // a TMA box has at most 256 rows
+  p.box_rows = (K + p.nboxes - 1) / p.nboxes;
+  p.krows = p.nboxes * p.box_rows;
+  p.W = kStripW;                                    // 32 columns per CTA (lane = column); 16 when 32 do not fit shared memory (K > ~900 double)
+  p.smem = 128 + (size_t)p.krows * p.W * esz;
+  if (p.smem > 227u * 1024u) { p.W = 16; p.smem = 128 + (size_t)p.krows * p.W * esz; }
+  const int ctas = (int)((220u * 1024u) / p.smem) < 1 ? 1 : (int)((220u * 1024u) / p.smem);
+  int G = (24 + ctas - 1) / ctas;                      // ~24 warps per SM
+  const int nblocks = (M + 3) / 4;
+  if (G > 8) G = 8;
+  if (G > nblocks) G = nblocks;
+  if (G < 1) G = 1;
+  p.G = G;
+  p.blocks.assign((size_t)G, std::vector<int>());
+  std::vector<std::pair<int, int> > load;               // (nonzeros, first row) per block, heaviest first
+  for (int b = 0; b < nblocks; ++b) {
+    const int r0 = 4 * b, r1 = (r0 + 4 < M) ? r0 + 4 : M;
+    load.push_back(std::make_pair(rowptr[r1] - rowptr[r0] + 2 * (r1 - r0), r0));
+  }
+  std::sort(load.begin(), load.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+  std::vector<long long> tot((size_t)G, 0);
+  for (size_t i = 0; i < load.size(); ++i) {
+    int best = 0;
+    for (int g = 1; g < G; ++g) if (tot[g] < tot[best]) best = g;
+    tot[best] += load[i].first;
+    p.blocks[best].push_back(load[i].second);
+  }
+  for (int g = 0; g < G; ++g) std::sort(p.blocks[g].begin(), p.blocks[g].end());
+  return p;
+}
+
+std::string emit_ptx_strip(int is_double, int M, int K, int beta_one, int skip_empty, const int* rowptr, const int* col, const double* val, const StripPlan& pl)
+{
+  const int esz = is_double ? 8 : 4;
+  const char* ty = is_double ? "f64" : "f32";
+  const char* zero = is_double ? "0d0000000000000000" : "0f00000000";
+  std::string s;
+  s.reserve(80 * (size_t)rowptr[M] + 16384);
+  s += ".version 8.6\n.target sm_100a\n.address_size 64\n\n.extern .shared .align 128 .b8 fs_smem[];\n\n";
+  s += ".visible .entry fs_baked(.param .align 64 .b8 pMap[128], .param .u64 pC, .param .u64 pN, .param .u64 pLDC)\n";
+  append(s, ".maxntid %d, 1, 1\n{\n", pl.G * 32);
+  s += "  .reg .pred %p, %pv, %pw;\n  .reg .b32 %r<12>;\n  .reg .b64 %rd<10>;\n";
+  append(s, "  .reg .%s %%a<4>, %%b<4>;\n", ty);
+  s += "  mov.b64 %rd0, pMap;\n  cvta.param.u64 %rd0, %rd0;\n  ld.param.u64 %rd1, [pC];\n  ld.param.u64 %rd2, [pN];\n  ld.param.u64 %rd3, [pLDC];\n";
+  s += "  mov.u32 %r0, %tid.x;\n  mov.u32 %r1, %ctaid.x;\n  mov.u32 %r2, fs_smem;\n";       // %r2: mbarrier, strip at +128
+  append(s, "  mul.lo.u32 %%r3, %%r1, %d;\n", pl.W);                                         // first column of the strip
+  s += "  setp.ne.u32 %p, %r0, 0;\n  @%p bra INIT_DONE;\n";
+  s += "  mbarrier.init.shared::cta.b64 [%r2], 1;\n  fence.mbarrier_init.release.cluster;\n";
+  append(s, "  mbarrier.arrive.expect_tx.shared::cta.b64 _, [%%r2], %u;\n", (unsigned)((size_t)pl.krows * pl.W * esz));
+  for (int b = 0; b < pl.nboxes; ++b) {
+    append(s, "  add.u32 %%r4, %%r2, %u;\n  mov.u32 %%r5, %d;\n", (unsigned)(128 + (size_t)b * pl.box_rows * pl.W * esz), b * pl.box_rows);
+    s += "  cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%r4], [%rd0, {%r3, %r5}], [%r2];\n";
+  }
+  s += "INIT_DONE:\n  bar.sync 0;\n";
+  // this lane's column, its validity, its C pointer and its strip address
+  append(s, "  and.b32 %%r10, %%r0, 31;\n  and.b32 %%r6, %%r0, %d;\n  shr.u32 %%r7, %%r0, 5;\n  add.u32 %%r8, %%r3, %%r6;\n  cvt.u64.u32 %%rd4, %%r8;\n  setp.lt.s64 %%pv, %%rd4, %%rd2;\n", pl.W - 1);
+  if (pl.W < 32) append(s, "  setp.lt.u32 %%p, %%r10, %d;\n  and.pred %%pv, %%pv, %%p;\n", pl.W);      // a 16-column strip: the upper half warp idles
+  append(s, "  mad.lo.s64 %%rd1, %%rd4, %d, %%rd1;\n  mul.lo.s64 %%rd3, %%rd3, %d;\n", esz, esz);      // c = C + n; row pitch in bytes
+  append(s, "  mad.lo.u32 %%r9, %%r6, %d, %%r2;\n", esz);                                               // strip + lane * esz (the +128 goes into the literal offsets)
+  s += "WAIT:\n  mbarrier.try_wait.parity.shared::cta.b64 %pw, [%r2], 0;\n  @%pw bra READY;\n  bra WAIT;\nREADY:\n";
+  for (int g = 0; g < pl.G; ++g) {
+    if (g + 1 < pl.G) append(s, "  setp.ne.u32 %%p, %%r7, %d;\n  @%%p bra SEC%d;\n", g, g + 1);
+    for (size_t bi = 0; bi < pl.blocks[g].size(); ++bi) {
+      const int r0 = pl.blocks[g][bi], r1 = (r0 + 4 < M) ? r0 + 4 : M;
+      int maxlen = 0;
+      for (int m = r0; m < r1; ++m) {
+        const int len = rowptr[m + 1] - rowptr[m];
+        if (len > maxlen) maxlen = len;
+        if (0 == len) continue;
+        if (beta_one) {
+          append(s, "  mad.lo.s64 %%rd5, %%rd3, %d, %%rd1;\n  mov.%s %%a%d, %s;\n  @%%pv ld.global.cs.%s %%a%d, [%%rd5];\n", m, ty, m - r0, zero, ty, m - r0);
+        }
+        else append(s, "  mov.%s %%a%d, %s;\n", ty, m - r0, zero);
+      }
+      for (int j = 0; j < maxlen; ++j) {          // the four chains interleaved: independent accumulators, in-order inside a row
+        // a warp-level barrier every 8 steps (32 loads) is a scheduling fence: without it the assembler hoists hundreds of the
+        // independent shared-memory loads of a dense row ahead of their multiply-adds and spills them
+        if (j > 0 && 0 == (j % 8)) s += "  bar.warp.sync 0xffffffff;\n";
+        for (int m = r0; m < r1; ++m) if (rowptr[m] + j < rowptr[m + 1]) {
+          const int u = rowptr[m] + j;
+          char lit[32];
+          if (is_double) { unsigned long long bits; const double v = val[u]; memcpy(&bits, &v, 8); snprintf(lit, sizeof(lit), "0d%016llX", bits); }
+          else { unsigned int bits; const float v = (float)val[u]; memcpy(&bits, &v, 4); snprintf(lit, sizeof(lit), "0f%08X", bits); }
+          append(s, "  ld.shared.%s %%b%d, [%%r9+%u];\n  fma.rn.%s %%a%d, %s, %%b%d, %%a%d;\n", ty, m - r0, (unsigned)(128 + (size_t)col[u] * pl.W * esz), ty, m - r0, lit, m - r0, m - r0);
+        }
+      }
+      for (int m = r0; m < r1; ++m) {
+        const int len = rowptr[m + 1] - rowptr[m];
+        if (0 == len) {
+          if (!skip_empty && !beta_one) append(s, "  mad.lo.s64 %%rd5, %%rd3, %d, %%rd1;\n  mov.%s %%a0, %s;\n  @%%pv st.global.cs.%s [%%rd5], %%a0;\n", m, ty, zero, ty);
+          continue;
+        }
+        append(s, "  mad.lo.s64 %%rd5, %%rd3, %d, %%rd1;\n  @%%pv st.global.cs.%s [%%rd5], %%a%d;\n", m, ty, m - r0);
+      }
+    }
+    s += "  bra DONE;\n";
+    if (g + 1 < pl.G) append(s, "SEC%d:\n", g + 1);
+  }
+  s += "DONE:\n  ret;\n}\n";
+  return s;
+}
+
+bool strip_supported(int is_double, int M, int K, const int* rowptr)
+{
+  (void)is_double;
+  return rowptr[M] > 0 && rowptr[M] <= 200000 && strip_plan(is_double, M, K, rowptr).smem <= 227u * 1024u;
+}
+
+bool supported(int is_double, int vec2, int M, int K, const int* rowptr, const int* col)
 {
   std::vector<char> used(K, 0);
   int nused = 0;
@@ -277,7 +411,8 @@ bool supported(int is_double, int M, int K, const int* rowptr, const int* col)
   // B rows live in registers: 2 registers per double, 1 per float, out of 255
   // B rows live in registers (2 registers per double, 1 per float, out of 255); the NVRTC form is additionally
   // limited to ~6000 nonzeros in fs_jit_build (compile time grows faster than linearly)
-  return rowptr[M] > 0 && (is_double ? nused <= 100 : nused <= 200) && rowptr[M] <= 40000;
+  // (the float kernel that handles two columns per thread holds two registers per row as well)
+  return rowptr[M] > 0 && ((is_double || vec2) ? nused <= 100 : nused <= 200) && rowptr[M] <= 40000;
 }
 
 std::mutex g_cache_mtx;
@@ -285,12 +420,21 @@ std::map<std::string, std::vector<char> > g_cubin_cache;
 
 }  // namespace
 
+// which form fs_jit_build would emit for this operator: 0 none (generic kernel), 1 B rows in registers, 2 B strip in shared memory
+int fs_jit_form(int is_double, int vec2, int M, int K, const int* rowptr, const int* col)
+{
+  if (supported(is_double, vec2, M, K, rowptr, col)) return 1;
+  return strip_supported(is_double, M, K, rowptr) ? 2 : 0;
+}
+
 char* fs_jit_source(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
                     const int* rowptr, const int* col, const double* val)
 {
   const char* env = getenv("LIBXSMM_B200_FSSPMDM_JIT");
-  const std::string s = (env && 'n' == *env) ? emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val)
-                                             : emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
+  const bool strip = !supported(is_double, vec2, M, K, rowptr, col) && strip_supported(is_double, M, K, rowptr);
+  const std::string s = strip ? emit_ptx_strip(is_double, M, K, beta_one, skip_empty, rowptr, col, val, strip_plan(is_double, M, K, rowptr))
+                              : ((env && 'n' == *env) ? emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val)
+                                                      : emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val));
   char* out = (char*)malloc(s.size() + 1);
   if (out) memcpy(out, s.c_str(), s.size() + 1);
   return out;
@@ -301,11 +445,20 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
 {
   const char* env = getenv("LIBXSMM_B200_FSSPMDM_JIT");
   if (env && '0' == *env) return 0;
-  if (!supported(is_double, M, K, rowptr, col)) return 0;
+  const bool regs_ok = supported(is_double, vec2, M, K, rowptr, col);
+  const bool strip = !regs_ok && strip_supported(is_double, M, K, rowptr);   // B rows in shared memory instead of registers
+  if (!regs_ok && !strip) return 0;
   // default: PTX text assembled by the driver (fast); LIBXSMM_B200_FSSPMDM_JIT=nvrtc: CUDA C++ through NVRTC
-  const bool use_nvrtc = (env && 'n' == *env);
+  const bool use_nvrtc = (env && 'n' == *env) && !strip;
   std::vector<char> cubin;     // cubin (NVRTC) or NUL-terminated PTX text
-  if (!use_nvrtc) {
+  StripPlan plan;
+  if (strip) {
+    plan = strip_plan(is_double, M, K, rowptr);
+    const std::string ptx = emit_ptx_strip(is_double, M, K, beta_one, skip_empty, rowptr, col, val, plan);
+    cubin.assign(ptx.begin(), ptx.end());
+    cubin.push_back(0);
+  }
+  else if (!use_nvrtc) {
     const std::string ptx = emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
     cubin.assign(ptx.begin(), ptx.end());
     cubin.push_back(0);
@@ -343,10 +496,12 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
     }
   }
   FsJit* j = new FsJit();
-  j->block = kBlock;
-  j->cols_per_thread = (vec2 && !is_double) ? 2 : 1;
+  j->block = strip ? plan.G * 32 : kBlock;
+  j->cols_per_thread = (vec2 && !is_double && !strip) ? 2 : 1;
+  j->strip = strip ? 1 : 0; j->esz = is_double ? 8 : 4; j->krows = K; j->box_rows = strip ? plan.box_rows : 0; j->strip_w = strip ? plan.W : 0; j->smem = strip ? plan.smem : 0;
   cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), 0, 0, 0, 0, 0, 0);
   if (cudaSuccess == e) e = cudaLibraryGetKernel(&j->kern, j->lib, "fs_baked");
+  if (cudaSuccess == e && strip && j->smem > 48u * 1024u) e = cudaFuncSetAttribute((const void*)j->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)j->smem);
   if (cudaSuccess != e) {
     set_error((int)e, "fsspmdm: loading the baked kernel failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -358,6 +513,16 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
 
 bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream)
 {
+  if (j->strip) {
+    // the strip form reads B through a TMA tensor map built from the caller's panel: 16-byte aligned base and row pitch
+    CUtensorMap map;
+    if (!make_tensor_map_2d(&map, dB, j->esz, (unsigned long long)ncols, (unsigned long long)j->krows, (unsigned long long)ldb * j->esz, (unsigned)j->strip_w, (unsigned)j->box_rows)) return false;
+    const long long blocks = (ncols + j->strip_w - 1) / j->strip_w;
+    void* args[] = { (void*)&map, (void*)&dC, (void*)&ncols, (void*)&ldc };
+    const cudaError_t e = cudaLaunchKernel((const void*)j->kern, dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, j->smem, stream);
+    if (cudaSuccess != e) { set_error((int)e, "fsspmdm: baked strip kernel launch failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return false; }
+    return true;
+  }
   // the 2-column form needs 8-byte aligned rows: even pitches, even column count, aligned bases; a panel that does
   // not qualify goes to the generic kernel (return false)
   if (2 == j->cols_per_thread && !((0 == ((ldb | ldc | ncols) & 1)) && (0 == (((uintptr_t)dB | (uintptr_t)dC) & 7)))) return false;

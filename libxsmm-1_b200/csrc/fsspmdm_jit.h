@@ -12,6 +12,8 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
                     const int* rowptr, const int* col, const double* val);
 bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream);
 void fs_jit_destroy(FsJit* j);
+// 0: outside what can be baked (generic kernel), 1: B rows in registers, 2: B strip staged in shared memory by TMA
+int fs_jit_form(int is_double, int vec2, int M, int K, const int* rowptr, const int* col);
 // the CUDA source that would be compiled (for tests / inspection); caller frees with free()
 char* fs_jit_source(int is_double, int vec2, int M, int K, int beta_one, int skip_empty_rows,
                     const int* rowptr, const int* col, const double* val);
