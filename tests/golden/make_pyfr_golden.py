@@ -1,4 +1,4 @@
-"""Generates tests/golden/pyfr_all.npz by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref) on every operator shipped under
+"""Generates tests/golden/operators_pyfr.npz by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref) on every operator shipped under
 /root/reference/samples/pyfr/mats (150 coordinate-format files, p1..p6 x hex/pri/quad/tet/tri x m0/m3/m6/m132/m460).
 
     python tests/golden/make_pyfr_golden.py
@@ -54,10 +54,10 @@ def main():
             C = C0.copy()
             ref.fsspmdm(a, B, C, beta, panel=16)
             out["out%d_%d" % (int(beta), i)] = C
-    np.savez_compressed(os.path.join(HERE, "pyfr_all.npz"), names=np.array(names), shapes=np.array(shapes, np.int32), offsets=np.array(offs, np.int64),
+    np.savez_compressed(os.path.join(HERE, "operators_pyfr.npz"), names=np.array(names), shapes=np.array(shapes, np.int32), offsets=np.array(offs, np.int64),
                         rows=np.concatenate(rows), cols=np.concatenate(cols), vals=np.concatenate(vals), ref_sparse_branch=np.array(branch),
                         picked=np.array(picked, np.int32), **out)
-    print("wrote pyfr_all.npz: %d operators, %d nonzeros, %d with reference outputs; sparse branch taken for %d" % (len(ops), offs[-1], len(picked), sum(branch)))
+    print("wrote operators_pyfr.npz: %d operators, %d nonzeros, %d with reference outputs; sparse branch taken for %d" % (len(ops), offs[-1], len(picked), sum(branch)))
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 """All 150 operators the reference ships for its PyFR driver (samples/pyfr/mats/p1..p6/{hex,pri,quad,tet,tri}/m*-sp.mtx),
-from the committed fixture tests/golden/pyfr_all.npz (tests/golden/make_pyfr_golden.py wrote it by running the compiled
+from the committed fixture tests/golden/operators_pyfr.npz (tests/golden/make_pyfr_golden.py wrote it by running the compiled
 reference).  CPU part: the oracle reproduces the reference's outputs bit for bit; the product's host-side plan takes the
 branch the reference took and can BAKE every one of them (registers or shared-memory strip -- none falls back to the
 generic kernel).  GPU part: every operator is created, is baked, and its apply matches the reference / the oracle bit for bit."""
@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def pyfr():
-    d = np.load(os.path.join(ROOT, "tests", "golden", "pyfr_all.npz"))
+    d = np.load(os.path.join(ROOT, "tests", "golden", "operators_pyfr.npz"))
     ops = []
     for i, name in enumerate(d["names"]):
         M, K = (int(x) for x in d["shapes"][i])
