@@ -38,6 +38,8 @@ struct SliceArena {
   uint16_t* rowidx;
   uint16_t* colidx;
   float* values;
+  unsigned long long* lookback;   // auxiliary: per slice four words {launch epoch << 32 | nonzeros of that quarter of the slice} (k1_scan)
+  uint32_t* epoch;                // auxiliary: {launch epoch, CTAs finished} of the split slicing kernels
   uint32_t* slice_nnz;   // auxiliary: true nonzero count of every slice (the u16 row pointers wrap at 65536)
   uint16_t* tcoff;   // auxiliary (not part of the reference's slice), same indexing as colidx: where the nonzero
                      // goes in the tensor-core branch's shared-memory A tile (fp32 slices: xb_tc_pack)

@@ -266,6 +266,66 @@ template <> struct K1Raw<true> {
   static __device__ __forceinline__ uint4 widen(raw_t r) { return make_uint4(r.x << 16, r.x & 0xFFFF0000u, r.y << 16, r.y & 0xFFFF0000u); }
 };
 
+// A slice may be split over P = 32 / CW CTAs of CW warps (part q owns the "virtual warps" q*CW .. q*CW+CW-1 of the
+// one-CTA form, i.e. a contiguous quarter of the slice's rows): several small CTAs per SM overlap their load, scan and store
+// phases, where one 1024-thread CTA per SM runs them back to back.  The running position across the parts of a slice is a
+// decoupled look-back: a part publishes {epoch, its count} and adds up the counts of the parts before it (lower block
+// indices: already dispatched), spinning on the few that are not there yet.  The epoch (one per launch, advanced by the
+// last CTA to finish) makes stale words of earlier launches -- including replays of a captured graph -- unreadable.
+struct K1Scan { uint32_t pos; uint32_t slice_total; };   // first output position of this warp's rows; the slice's total (valid in the last part)
+
+template <int CW>
+__device__ __forceinline__ K1Scan k1_scan(const SliceArgs& p, int s, int part, uint32_t warp_total, uint32_t* wtot /* shared, CW + 1 words */, uint32_t epoch)
+{
+  constexpr int P = 32 / CW;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (0 == lane) wtot[warp] = warp_total;
+  __syncthreads();
+  const uint32_t t = (lane < CW) ? wtot[lane] : 0u;
+  uint32_t inc = t;
+#pragma unroll
+  for (int d = 1; d < CW; d <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += u;
+  }
+  const uint32_t cta_total = __shfl_sync(0xffffffffu, inc, CW - 1);
+  uint32_t base = 0;
+  if (P > 1) {
+    if (0 == tid) {
+      unsigned long long* lb = p.out.lookback + (size_t)s * P;
+      const unsigned long long mine = ((unsigned long long)epoch << 32) | cta_total;
+      asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(lb + part), "l"(mine) : "memory");
+      uint32_t b = 0;
+      for (int j = part - 1; j >= 0; --j) {
+        unsigned long long v;
+        do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(lb + j) : "memory"); } while ((uint32_t)(v >> 32) != epoch);
+        b += (uint32_t)v;
+      }
+      wtot[CW] = b;
+    }
+    __syncthreads();
+    base = wtot[CW];
+  }
+  K1Scan r;
+  r.pos = base + __shfl_sync(0xffffffffu, inc - t, warp);
+  r.slice_total = base + cta_total;
+  return r;
+}
+
+__device__ __forceinline__ uint32_t k1_epoch(const SliceArgs& p) { return p.out.epoch ? (*(volatile uint32_t*)p.out.epoch + 1u) : 1u; }
+
+// last CTA of the launch to get here advances the epoch (all CTAs have read it long before)
+__device__ __forceinline__ void k1_finish(const SliceArgs& p, uint32_t epoch)
+{
+  if (0 == p.out.epoch) return;
+  __syncthreads();
+  if (0 == threadIdx.x) {
+    __threadfence();
+    const uint32_t done = atomicAdd(p.out.epoch + 1, 1u);
+    if (done + 1u == gridDim.x) { p.out.epoch[1] = 0u; __threadfence(); *(volatile uint32_t*)p.out.epoch = epoch; }
+  }
+}
+
 // keep-mask of the lane's four elements.  FULL = complete 128-column block whose columns are all inside the
 // reference's vector loops: kept iff ordered-nonzero, i.e. |v| > 0 (NaN and -0.0 dropped, denormals kept).
 template <bool FULL>
@@ -286,14 +346,17 @@ __device__ __forceinline__ uint32_t k1n_mask(uint4 w, int lane, int ncols, int v
 
 // ROWS = rows a warp handles (>= rows per warp); KEEP = rows stay in registers between the two phases,
 // otherwise phase 2 re-reads them (fp32 slices of 512 rows do not fit the register file).
-template <bool BF16, bool FULL, int ROWS, bool KEEP>
-__global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const SliceArgs p)
+template <bool BF16, bool FULL, int ROWS, bool KEEP, int CW>
+__global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_n_kernel(const SliceArgs p)
 {
   typedef K1Raw<BF16> Raw;
   typedef typename Raw::raw_t raw_t;
-  __shared__ uint32_t wtot[K1N_WARPS];
+  constexpr int P = 32 / CW;
+  __shared__ uint32_t wtot[CW + 1];
   const Geom& g = p.g;
-  const int s = p.slice0 + (int)blockIdx.x * p.slice_step;
+  const uint32_t epoch = (P > 1) ? k1_epoch(p) : 0u;
+  const int part = (int)blockIdx.x % P;
+  const int s = p.slice0 + ((int)blockIdx.x / P) * p.slice_step;
   const int kb = s / g.mb, mbi = s - kb * g.mb;
   const int nrows = min(g.bm, g.m - mbi * g.bm);
   const int ncols = min(g.bk, g.k - kb * g.bk);
@@ -301,7 +364,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
   if (p.simd_w <= 1) vec_end = 0;
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rpw = (g.bm + K1N_WARPS - 1) / K1N_WARPS;      // rows per warp (<= 16 because bm <= 512)
-  const int row_lo = warp * rpw, row_hi = min(nrows, row_lo + rpw);
+  const int row_lo = (part * CW + warp) * rpw, row_hi = min(nrows, row_lo + rpw);
   const size_t esz = BF16 ? 2 : 4;
   const long long origin = p.origin_is_block ? 0ll : ((long long)mbi * g.bm * p.lda + (long long)kb * g.bk);
   const char* A = (const char*)p.a + origin * (long long)esz;
@@ -326,26 +389,15 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
   for (int j = 0; j < (ROWS + 7) / 8; ++j) mine += __popc(masks[j]);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
-  if (0 == lane) wtot[warp] = mine;
-  __syncthreads();
-  uint32_t pos;   // first output position of this warp's rows
-  bool wrapped;   // completely full 512 x 128 slice: the reference's u16 counter wraps and its multiply sees the last row as empty
-  {
-    const uint32_t t = wtot[lane];
-    uint32_t inc = t;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += u;
-    }
-    pos = __shfl_sync(0xffffffffu, inc - t, warp);
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    wrapped = total >= 65536u;
-    if (0 == tid) {
-      p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
-      p.out.slice_nnz[s] = total;
-      xb_publish_nnz(p, total);
-    }
+  const K1Scan sc = k1_scan<CW>(p, s, part, mine, wtot, epoch);
+  uint32_t pos = sc.pos;   // first output position of this warp's rows
+  // completely full 512 x 128 slice: the reference's u16 counter wraps and its multiply sees the last row as empty.  Known
+  // here only to the last part -- which is the one that owns row 511
+  const bool wrapped = (P - 1 == part) && sc.slice_total >= 65536u;
+  if (P - 1 == part && 0 == tid) {
+    p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)sc.slice_total;   // u16 like the reference's counter
+    p.out.slice_nnz[s] = sc.slice_total;
+    xb_publish_nnz(p, sc.slice_total);
   }
 
   // ---- phase 2: positions and stores -----------------------------------------------------------------------
@@ -396,6 +448,7 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_n_kernel(const Sli
       pos += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     }
   }
+  if (P > 1) k1_finish(p, epoch);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -532,22 +585,25 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
 // K1x: the same with NW 16-byte words (8 * NW elements) per lane: a row is 16 / NW lanes and one iteration of the
 // positioning phase covers 2 * NW rows, which divides the number of ballot rounds per slice by NW (the kernel is
 // instruction-issue bound).  Same outputs, bit for bit.  Measured on C2: NW = 1 (K1w) 25.1 us, NW = 2 23.2 us, NW = 4 23.1 us (not instantiated).
-template <int ROWS, int NW>
-__global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16x_kernel(const SliceArgs p)
+template <int ROWS, int NW, int CW>
+__global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x_kernel(const SliceArgs p)
 {
   constexpr int LPR = 16 / NW;               // lanes per row
   constexpr int RPI = 32 / LPR;              // rows per iteration
   constexpr int ITS = (ROWS + RPI - 1) / RPI;
   constexpr int MB = 8 * NW;                 // mask bits per lane and iteration
-  __shared__ uint32_t wtot[K1N_WARPS];
+  constexpr int P = 32 / CW;                 // CTAs per slice (k1_scan)
+  __shared__ uint32_t wtot[CW + 1];
   const Geom& g = p.g;
-  const int s = p.slice0 + (int)blockIdx.x * p.slice_step;
+  const uint32_t epoch = (P > 1) ? k1_epoch(p) : 0u;
+  const int part = (int)blockIdx.x % P;
+  const int s = p.slice0 + ((int)blockIdx.x / P) * p.slice_step;
   const int kb = s / g.mb, mbi = s - kb * g.mb;
   const int nrows = min(g.bm, g.m - mbi * g.bm);
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qr = lane / LPR, hl = lane % LPR;       // row inside the group, segment of the row
   const int rpw = (g.bm + K1N_WARPS - 1) / K1N_WARPS;
-  const int row_lo = warp * rpw, row_hi = min(nrows, row_lo + rpw);
+  const int row_lo = (part * CW + warp) * rpw, row_hi = min(nrows, row_lo + rpw);
   const long long origin = p.origin_is_block ? 0ll : ((long long)mbi * g.bm * p.lda + (long long)kb * g.bk);
   const uint16_t* A = (const uint16_t*)p.a + origin + hl * (8 * NW);
 
@@ -572,24 +628,12 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16x_kernel(const
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
-  if (0 == lane) wtot[warp] = mine;
-  __syncthreads();
-  uint32_t pos;
-  {
-    const uint32_t t = wtot[lane];
-    uint32_t inc = t;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += u;
-    }
-    pos = __shfl_sync(0xffffffffu, inc - t, warp);
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    if (0 == tid) {
-      p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)total;   // u16 like the reference's counter
-      p.out.slice_nnz[s] = total;
-      xb_publish_nnz(p, total);
-    }
+  const K1Scan sc = k1_scan<CW>(p, s, part, mine, wtot, epoch);
+  uint32_t pos = sc.pos;
+  if (P - 1 == part && 0 == tid) {
+    p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)sc.slice_total;   // u16 like the reference's counter
+    p.out.slice_nnz[s] = sc.slice_total;
+    xb_publish_nnz(p, sc.slice_total);
   }
 
   // ---- phase 2: positions and stores -----------------------------------------------------------------------
@@ -646,13 +690,20 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16x_kernel(const
       pos += kept(0xFFFFFFFFu);
     }
   }
+  if (P > 1) k1_finish(p, epoch);
 }
 
+// split: the slices of a whole pass are cut into four 8-warp CTAs each (k1_scan); a lone slice (legacy per-block calls, which
+// may run concurrently on several streams of one handle) keeps the one-CTA form, which shares no state between launches
 template <bool BF16, int ROWS, bool KEEP>
-static void launch_slice_n(const SliceArgs& args, int nslices, bool full, cudaStream_t stream)
+static void launch_slice_n(const SliceArgs& args, int nslices, bool full, bool split, cudaStream_t stream)
 {
-  if (full) spmdm_slice_n_kernel<BF16, true, ROWS, KEEP><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
-  else spmdm_slice_n_kernel<BF16, false, ROWS, KEEP><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+  if (split) {
+    if (full) spmdm_slice_n_kernel<BF16, true, ROWS, KEEP, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
+    else spmdm_slice_n_kernel<BF16, false, ROWS, KEEP, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
+  }
+  else if (full) spmdm_slice_n_kernel<BF16, true, ROWS, KEEP, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+  else spmdm_slice_n_kernel<BF16, false, ROWS, KEEP, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
 }
 
 void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
@@ -664,13 +715,22 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
     // makes the NaN rule of the scalar remainder unreachable)
     const bool full = (0 == (args.g.k % 128)) && (args.simd_w > 1);
     const int rpw = (args.g.bm + K1N_WARPS - 1) / K1N_WARPS;
+    // LIBXSMM_B200_K1_SPLIT=1: four 8-warp CTAs per slice chained by a decoupled look-back (k1_scan).  Measured on B200 it is
+    // SLOWER than one 32-warp CTA per slice (4096^2 bf16: 32.7 vs 23.3 us; 2048^2 fp32: 29.2 vs 19.0 us): the three hops
+    // of the look-back cost more than the overlap of the parts' phases gains.  Kept as an experiment, off by default.
+    static const bool split_env = [] { const char* e = getenv("LIBXSMM_B200_K1_SPLIT"); return e && '1' == *e; }();
+    const bool split = split_env && nslices > 1 && !args.origin_is_block && 0 != args.out.lookback && 0 != args.out.epoch;
     if (args.is_bf16 && full && !args.origin_is_block && 0 == (args.lda & 7) && 0 == ((uintptr_t)args.a & 15) && 0 == (args.g.k & 7)) {
       // complete 128-column blocks, 16-byte aligned rows: the wide kernel (a lane holds 8 elements)
       const char* wenv = getenv("LIBXSMM_B200_K1_WIDE");      // developer switch, read per call (tests flip it)
       const int wide = (wenv && *wenv >= '0' && *wenv <= '2') ? (*wenv - '0') : 2;
       if (wide >= 2) {      // two 16-byte words per lane (default; LIBXSMM_B200_K1_WIDE=1: one word, =0: the generic kernel)
-        if (rpw <= 8) spmdm_slice_bf16x_kernel<8, 2><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
-        else spmdm_slice_bf16x_kernel<16, 2><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+        if (split) {
+          if (rpw <= 8) spmdm_slice_bf16x_kernel<8, 2, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
+          else spmdm_slice_bf16x_kernel<16, 2, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
+        }
+        else if (rpw <= 8) spmdm_slice_bf16x_kernel<8, 2, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+        else spmdm_slice_bf16x_kernel<16, 2, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
         XB_CUDA(cudaGetLastError());
         return;
       }
@@ -683,13 +743,13 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
     }
     if (args.is_bf16) {
       static const int keep16 = [] { const char* e = getenv("LIBXSMM_B200_K1_KEEP"); return (e && '1' == *e) ? 1 : 0; }();
-      if (rpw <= 8) launch_slice_n<true, 8, true>(args, nslices, full, stream);
-      else if (keep16) launch_slice_n<true, 16, true>(args, nslices, full, stream);
-      else launch_slice_n<true, 16, false>(args, nslices, full, stream);
+      if (rpw <= 8) launch_slice_n<true, 8, true>(args, nslices, full, split, stream);
+      else if (keep16) launch_slice_n<true, 16, true>(args, nslices, full, split, stream);
+      else launch_slice_n<true, 16, false>(args, nslices, full, split, stream);
     }
     else {
-      if (rpw <= 8) launch_slice_n<false, 8, true>(args, nslices, full, stream);
-      else launch_slice_n<false, 16, false>(args, nslices, full, stream);
+      if (rpw <= 8) launch_slice_n<false, 8, true>(args, nslices, full, split, stream);
+      else launch_slice_n<false, 16, false>(args, nslices, full, split, stream);
     }
     XB_CUDA(cudaGetLastError());
     return;
