@@ -120,6 +120,28 @@ LIBXSMM_API void libxsmm_b200_csr_free(unsigned int* row_ptr, unsigned int* col_
 LIBXSMM_API libxsmm_dfsspmdm* libxsmm_b200_dfsspmdm_create_mtx(const char* path, int N, int ldb, int ldc, double beta, int* M, int* K);
 LIBXSMM_API libxsmm_sfsspmdm* libxsmm_b200_sfsspmdm_create_mtx(const char* path, int N, int ldb, int ldc, float beta, int* M, int* K);
 
+/* CSR "A sparse" x dense SoA kernels: the GPU counterpart of
+ *     kernel = libxsmm_create_xcsr_soa(descriptor(m, n, k, lda = 0, ldb, ldc, alpha = 1, beta), row_ptr, column_idx, values)
+ *     kernel(values, B, C)                                   once per mesh element
+ * (reference src/template/libxsmm.h:283-293, src/libxsmm_main.c:2423-2447, src/generator_spgemm_csr_asparse_soa.c; caller
+ * samples/edge/asparse_srsoa.c:148-160).  B is [k][ldb][soa_width], C is [m][ldc][soa_width] per element;
+ *     C[m][n][s] = (beta == 0 ? 0 : C[m][n][s]) + sum over row m's nonzeros z, in CSR order, of values[z] * B[column_idx[z]][n][s]
+ * with one fused multiply-add per nonzero (beta is 0 or 1, as for the reference's descriptor); rows WITHOUT nonzeros are
+ * left untouched, like the reference's emitted code.
+ * soa_width is a property of the caller's tensors (the reference's generator fixes it per host: 8 doubles / 16 floats with
+ * AVX-512, 4 / 8 otherwise).  One element is far too small for a launch, so execute is BATCHED: n_elements elements, element
+ * e at d_B + e * stride_b and d_C + e * stride_c (strides in scalars), asynchronous on `stream`.  The operator's values are
+ * fixed at create (the reference's kernel re-reads them at every call from its first argument; callers pass the same array). */
+typedef struct libxsmm_b200_csr_soa libxsmm_b200_csr_soa;
+LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_dcsr_soa_create(int M, int N, int K, int ldb, int ldc, int soa_width, double beta,
+  const unsigned int* row_ptr, const unsigned int* column_idx, const double* values);
+LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_scsr_soa_create(int M, int N, int K, int ldb, int ldc, int soa_width, float beta,
+  const unsigned int* row_ptr, const unsigned int* column_idx, const float* values);
+LIBXSMM_API void libxsmm_b200_csr_soa_execute(const libxsmm_b200_csr_soa* handle, const void* d_B, void* d_C, long long n_elements,
+  long long stride_b, long long stride_c, void* stream);
+LIBXSMM_API int libxsmm_b200_csr_soa_is_baked(const libxsmm_b200_csr_soa* handle);
+LIBXSMM_API void libxsmm_b200_csr_soa_destroy(libxsmm_b200_csr_soa* handle);
+
 /* Host-only planning entries (no CUDA call is made; they work on a machine without a GPU).
  * geometry: the block geometry libxsmm_spmdm_init would choose (reference src/libxsmm_spmdm.c:552-608)
  *   for bn = 48 | 96 | 6; geom[9] = m n k bm bn bk mb nb kb.  Returns 0 on success.

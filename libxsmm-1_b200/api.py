@@ -51,6 +51,8 @@ ADDED_SYMBOLS = [
     "libxsmm_b200_graph_begin", "libxsmm_b200_graph_end", "libxsmm_b200_graph_launch", "libxsmm_b200_graph_destroy",
     "libxsmm_b200_sparse_matmul", "libxsmm_b200_sparse_matmul_cache_entries", "libxsmm_b200_sparse_matmul_cache_clear",
     "libxsmm_b200_csr_read_mtx", "libxsmm_b200_csr_free", "libxsmm_b200_dfsspmdm_create_mtx", "libxsmm_b200_sfsspmdm_create_mtx",
+    "libxsmm_b200_dcsr_soa_create", "libxsmm_b200_scsr_soa_create", "libxsmm_b200_csr_soa_execute", "libxsmm_b200_csr_soa_is_baked",
+    "libxsmm_b200_csr_soa_destroy",
 ]
 
 
@@ -618,6 +620,50 @@ class Fsspmdm:
     def destroy(self):
         if self.handle:
             (libxsmm_dfsspmdm_destroy if self.double else libxsmm_sfsspmdm_destroy)(self.handle)
+            self.handle = None
+
+
+class CsrSoa:
+    """CSR operator applied to [element][row][column][soa] tensors (libxsmm_b200_[sd]csr_soa_*; the batched GPU counterpart of
+    libxsmm_create_xcsr_soa, reference samples/edge/asparse_srsoa.c:148-160)."""
+
+    def __init__(self, M, N, K, rowptr, colidx, values, soa_width, ldb=None, ldc=None, beta=0.0):
+        require_gpu()
+        L = load()
+        values = np.ascontiguousarray(values)
+        assert values.dtype in (np.float64, np.float32)
+        self.double = values.dtype == np.float64
+        rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
+        f = L.libxsmm_b200_dcsr_soa_create if self.double else L.libxsmm_b200_scsr_soa_create
+        f.restype = ctypes.c_void_p
+        f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double if self.double else ctypes.c_float] + [ctypes.c_void_p] * 3
+        self.M, self.N, self.K, self.soa = M, N, K, soa_width
+        self.ldb = N if ldb is None else ldb
+        self.ldc = N if ldc is None else ldc
+        self.handle = f(M, N, K, self.ldb, self.ldc, soa_width, float(beta), rowptr.ctypes.data, colidx.ctypes.data, values.ctypes.data)
+        if not self.handle:
+            code, msg = last_error()
+            clear_error()
+            raise ValueError("csr_soa_create failed: %s" % msg)
+        clear_error()
+
+    @property
+    def is_baked(self):
+        return bool(load().libxsmm_b200_csr_soa_is_baked(ctypes.c_void_p(self.handle)))
+
+    def execute(self, d_B, d_C, n_elements, stride_b=None, stride_c=None, stream=None):
+        L = load()
+        L.libxsmm_b200_csr_soa_execute.restype = None
+        L.libxsmm_b200_csr_soa_execute.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]
+        sb = self.K * self.ldb * self.soa if stride_b is None else stride_b
+        sc = self.M * self.ldc * self.soa if stride_c is None else stride_c
+        L.libxsmm_b200_csr_soa_execute(self.handle, _addr(d_B), _addr(d_C), n_elements, sb, sc, _sptr(stream))
+
+    def destroy(self):
+        if self.handle:
+            L = load()
+            L.libxsmm_b200_csr_soa_destroy.argtypes = [ctypes.c_void_p]
+            L.libxsmm_b200_csr_soa_destroy(self.handle)
             self.handle = None
 
 

@@ -72,6 +72,7 @@ static long long fs_x86_code_size(const FsOperator& o)
 struct FsDev {
   int M, beta_one, skip_empty;
   long long ldb, ldc;
+  long long J, sb, sc;   // batched form (CSR x SoA): columns per element and element strides; J = 0: plain column panel
   const int* rowptr;
   const int* col;
   const void* val;
@@ -83,11 +84,13 @@ __global__ void __launch_bounds__(256) fs_generic_kernel(const FsDev p, const T*
   const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (n >= ncols) return;
   const T* __restrict__ val = (const T*)p.val;
-  const T* Bn = B + n;
+  long long nb = n, nc = n;
+  if (p.J > 0) { const long long e = n / p.J, j = n - e * p.J; nb = e * p.sb + j; nc = e * p.sc + j; }   // (element, column) form: VEC == 1
+  const T* Bn = B + nb;
   for (int m = 0; m < p.M; ++m) {
     const int lo = __ldg(p.rowptr + m), hi = __ldg(p.rowptr + m + 1);
     if (hi == lo && p.skip_empty) continue;
-    T* crow = C + (long long)m * p.ldc + n;
+    T* crow = C + (long long)m * p.ldc + nc;
     T acc[VEC];
     if (p.beta_one) {
 #pragma unroll
@@ -232,6 +235,7 @@ void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, 
   FsDev d;
   d.M = o->M; d.beta_one = o->beta_one; d.skip_empty = o->sparse_branch;
   d.ldb = ldb; d.ldc = ldc; d.rowptr = o->d_rowptr; d.col = o->d_col; d.val = o->d_val;
+  d.J = 0; d.sb = 0; d.sc = 0;
   const int threads = 256;
   if (o->is_double) {
     const bool v2 = (0 == (ldb & 1)) && (0 == (ldc & 1)) && (0 == (((uintptr_t)dB | (uintptr_t)dC) & 15));
@@ -255,6 +259,71 @@ void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, 
       fs_generic_kernel<float, 1><<<(unsigned)blocks, threads, 0, stream>>>(d, (const float*)dB, (float*)dC, ncols);
     }
   }
+  XB_CUDA(cudaGetLastError());
+}
+
+// ---- CSR x dense SoA ----------------------------------------------------------------------------
+// The operator arrives as CSR (reference libxsmm_create_xcsr_soa, src/libxsmm_main.c:2423-2447) and is applied to
+// [row][column][soa] tensors.  Arithmetic of the reference's emitted kernel (src/generator_spgemm_csr_asparse_soa.c:
+// 213-420): per row with nonzeros an in-order chain of fused multiply-adds from C (beta != 0) or from zero; rows without
+// nonzeros are skipped.  With the SoA lanes as innermost columns this IS the fixed-operator apply over N * soa columns
+// with row pitches ldb * soa / ldc * soa, so it reuses the baked kernel (batched over mesh elements).
+FsOperator* fs_create_csr(int is_double, int M, int N, int K, int ldb, int ldc, int soa, double beta,
+                          const unsigned int* rowptr, const unsigned int* colidx, const void* values)
+{
+  if (M <= 0 || N <= 0 || K <= 0 || soa <= 0 || ldb < N || ldc < N || 0 == rowptr || 0 == colidx || 0 == values
+      || !(0.0 == beta || 1.0 == beta)) {   // the reference's descriptor (libxsmm_gemm_descriptor_dinit) exists for beta 0 and 1 only
+    set_error(-60, "csr_soa_create: bad argument (M=%d N=%d K=%d ldb=%d ldc=%d soa=%d)", M, N, K, ldb, ldc, soa);
+    return 0;
+  }
+  for (int m = 0; m < M; ++m) if (rowptr[m + 1] < rowptr[m]) { set_error(-61, "csr_soa_create: row pointers not monotone"); return 0; }
+  for (unsigned int z = rowptr[0]; z < rowptr[M]; ++z) if (colidx[z] >= (unsigned int)K) { set_error(-62, "csr_soa_create: column index out of range"); return 0; }
+  FsOperator* o = new FsOperator();
+  o->M = M; o->N = N * soa; o->K = K; o->ldb = ldb * soa; o->ldc = ldc * soa;
+  o->a_dense = 0; o->kernel = 0; o->jit = 0; o->tc = 0;
+  o->is_double = is_double; o->beta_one = (0.0 != beta);
+  o->d_rowptr = 0; o->d_col = 0; o->d_val = 0;
+  o->sparse_branch = 1;                                          // rows without nonzeros are skipped
+  o->n_unique = 0; o->x86_code_size = 0; o->N_chunksize = soa;
+  o->rowptr.assign(M + 1, 0);
+  for (int m = 0; m <= M; ++m) o->rowptr[m] = (int)(rowptr[m] - rowptr[0]);
+  o->nnz = o->rowptr[M];
+  o->col.resize((size_t)o->nnz); o->val.resize((size_t)o->nnz);
+  for (int z = 0; z < o->nnz; ++z) {
+    o->col[z] = (int)colidx[rowptr[0] + z];
+    o->val[z] = is_double ? ((const double*)values)[rowptr[0] + z] : (double)((const float*)values)[rowptr[0] + z];
+  }
+  const size_t nalloc = (size_t)(o->nnz > 0 ? o->nnz : 1);
+  XB_CUDA(cudaMalloc(&o->d_rowptr, sizeof(int) * (M + 1)));
+  XB_CUDA(cudaMalloc(&o->d_col, sizeof(int) * nalloc));
+  XB_CUDA(cudaMalloc(&o->d_val, 8 * nalloc));
+  if (0 == o->d_rowptr || 0 == o->d_col || 0 == o->d_val) { fs_destroy(o); return 0; }
+  XB_CUDA(cudaMemcpy(o->d_rowptr, o->rowptr.data(), sizeof(int) * (M + 1), cudaMemcpyHostToDevice));
+  if (o->nnz > 0) {
+    XB_CUDA(cudaMemcpy(o->d_col, o->col.data(), sizeof(int) * (size_t)o->nnz, cudaMemcpyHostToDevice));
+    if (is_double) XB_CUDA(cudaMemcpy(o->d_val, o->val.data(), 8 * (size_t)o->nnz, cudaMemcpyHostToDevice));
+    else { std::vector<float> vf(o->val.begin(), o->val.end()); XB_CUDA(cudaMemcpy(o->d_val, vf.data(), 4 * (size_t)o->nnz, cudaMemcpyHostToDevice)); }
+  }
+  o->jit = fs_jit_build(is_double, 0, M, K, o->beta_one, 1, o->rowptr.data(), o->col.data(), o->val.data(), 1 /*batched*/);
+  o->kernel = o->jit;
+  return o;
+}
+
+void fs_execute_batched(const FsOperator* o, const void* dB, void* dC, long long n_elem, long long stride_b, long long stride_c, cudaStream_t stream)
+{
+  if (0 == o || n_elem <= 0) return;
+  count_launch(1);
+  const long long J = o->N;
+  if (o->jit && fs_jit_launch_batched(o->jit, dB, dC, n_elem, J, o->ldb, o->ldc, stride_b, stride_c, stream)) { note_compute_kernel("fs_baked (batched)"); return; }
+  note_compute_kernel("fs_generic_kernel (batched)");
+  FsDev d;
+  d.M = o->M; d.beta_one = o->beta_one; d.skip_empty = 1;
+  d.ldb = o->ldb; d.ldc = o->ldc; d.rowptr = o->d_rowptr; d.col = o->d_col; d.val = o->d_val;
+  d.J = J; d.sb = stride_b; d.sc = stride_c;
+  const int threads = 256;
+  const long long total = n_elem * J, blocks = (total + threads - 1) / threads;
+  if (o->is_double) fs_generic_kernel<double, 1><<<(unsigned)blocks, threads, 0, stream>>>(d, (const double*)dB, (double*)dC, total);
+  else fs_generic_kernel<float, 1><<<(unsigned)blocks, threads, 0, stream>>>(d, (const float*)dB, (float*)dC, total);
   XB_CUDA(cudaGetLastError());
 }
 

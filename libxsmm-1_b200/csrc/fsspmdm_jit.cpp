@@ -26,6 +26,7 @@ struct FsJit {
   int cols_per_thread;  // 1, or 2 (float, even pitches: 8-byte accesses)
   int block;
   // strip form (operators whose B rows do not fit the register file): a CTA stages K x 32 columns of B in shared memory by TMA
+  int batched;          // 1: (element, column) form with strides (fs_jit_launch_batched)
   int strip;            // 0: register form
   int esz, krows, box_rows, strip_w;
   size_t smem;
@@ -175,10 +176,12 @@ static int fs_prefetch_groups()
   return (e && *e) ? atoi(e) : 2;
 }
 
+// batched: the columns are (element, column-in-element) pairs -- thread n works on element n / J, column n % J, whose B / C
+// rows start at element * stride (the [element][row][column][soa] tensors of the CSR x SoA kernels)
 std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
-                     const int* rowptr, const int* col, const double* val)
+                     const int* rowptr, const int* col, const double* val, int batched = 0)
 {
-  const int cpt = (vec2 && !is_double) ? 2 : 1;
+  const int cpt = (vec2 && !is_double && !batched) ? 2 : 1;
   const int esz = is_double ? 8 : 4;
   const char* ty = is_double ? "f64" : "f32";
   std::vector<char> used(K, 0);
@@ -186,16 +189,24 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
   std::string s;
   s.reserve(96 * (size_t)rowptr[M] * cpt + 8192);
   s += ".version 8.6\n.target sm_100a\n.address_size 64\n\n";
-  s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC)\n";
+  if (batched) s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC, .param .u64 pJ, .param .u64 pSB, .param .u64 pSC)\n";
+  else s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC)\n";
   append(s, ".maxntid %d, 1, 1\n", kBlock);
   s += "{\n";
-  s += "  .reg .pred %p, %pf;\n  .reg .b32 %r<4>;\n  .reg .b64 %rd<12>;\n";
+  s += "  .reg .pred %p, %pf;\n  .reg .b32 %r<4>;\n  .reg .b64 %rd<20>;\n";
   append(s, "  .reg .%s %%bx<%d>, %%by<%d>, %%cx<%d>, %%cy<%d>, %%ax, %%ay;\n", ty, K, K, M, M);
   s += "  ld.param.u64 %rd0, [pB];\n  ld.param.u64 %rd1, [pC];\n  ld.param.u64 %rd2, [pN];\n  ld.param.u64 %rd3, [pLDB];\n  ld.param.u64 %rd4, [pLDC];\n";
   s += "  mov.u32 %r0, %ctaid.x;\n  mov.u32 %r1, %tid.x;\n";
   append(s, "  mul.wide.u32 %%rd5, %%r0, %d;\n  cvt.u64.u32 %%rd6, %%r1;\n  add.s64 %%rd5, %%rd5, %%rd6;\n", kBlock);
   if (2 == cpt) s += "  shl.b64 %rd5, %rd5, 1;\n";
   s += "  setp.ge.s64 %p, %rd5, %rd2;\n  @%p bra DONE;\n";
+  if (batched) {   // element e = n / J, column j = n % J: b = B + e * SB + j, c = C + e * SC + j
+    s += "  ld.param.u64 %rd12, [pJ];\n  ld.param.u64 %rd13, [pSB];\n  ld.param.u64 %rd14, [pSC];\n";
+    s += "  div.u64 %rd15, %rd5, %rd12;\n  mul.lo.s64 %rd16, %rd15, %rd12;\n  sub.s64 %rd16, %rd5, %rd16;\n";
+    s += "  mad.lo.s64 %rd17, %rd15, %rd13, %rd16;\n  mad.lo.s64 %rd18, %rd15, %rd14, %rd16;\n";
+    append(s, "  mad.lo.s64 %%rd0, %%rd17, %d, %%rd0;\n  mad.lo.s64 %%rd1, %%rd18, %d, %%rd1;\n", esz, esz);
+  }
+  else
   append(s, "  mad.lo.s64 %%rd0, %%rd5, %d, %%rd0;\n  mad.lo.s64 %%rd1, %%rd5, %d, %%rd1;\n", esz, esz);   // b = B + n, c = C + n
   append(s, "  mul.lo.s64 %%rd3, %%rd3, %d;\n  mul.lo.s64 %%rd4, %%rd4, %d;\n", esz, esz);                 // row pitches in bytes
   s += "  and.b32 %r2, %r1, 15;\n  setp.eq.u32 %pf, %r2, 0;\n";                                          // one lane per 128-byte line issues prefetches
@@ -209,7 +220,7 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
   // latency instead of DRAM latency.  Measured on B200 (fraction of the 6554 GB/s copy peak): 150 x 64 float operator,
   // N = 2^24: 0.854 -> 0.989; double, N = 2^20: 0.960 -> 0.984.  Twice as far ahead is worth nothing (0.88), further
   // is harmful; with beta = 1 the C-row prefetches below already fill the queues and this one costs 1-4 %.
-  if (!beta_one && fs_prefetch_b() > 0) {      // (measured: helps beta = 0, costs 2-4 % with beta = 1, where the C prefetches below already fill the queues)
+  if (!beta_one && !batched && fs_prefetch_b() > 0) {      // (measured: helps beta = 0, costs 2-4 % with beta = 1, where the C prefetches below already fill the queues)
     s += "  mov.u32 %r3, %nsmid;\n";
     append(s, "  mul.wide.u32 %%rd10, %%r3, %d;\n", fs_prefetch_b() * kBlock * cpt / 2);                                          // columns ahead
     s += "  add.s64 %rd11, %rd5, %rd10;\n  setp.lt.s64 %p, %rd11, %rd2;\n  and.pred %p, %p, %pf;\n";
@@ -441,12 +452,13 @@ char* fs_jit_source(int is_double, int vec2, int M, int K, int beta_one, int ski
 }
 
 FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
-                    const int* rowptr, const int* col, const double* val)
+                    const int* rowptr, const int* col, const double* val, int batched)
 {
+  if (batched) vec2 = 0;
   const char* env = getenv("LIBXSMM_B200_FSSPMDM_JIT");
   if (env && '0' == *env) return 0;
   const bool regs_ok = supported(is_double, vec2, M, K, rowptr, col);
-  const bool strip = !regs_ok && strip_supported(is_double, M, K, rowptr);   // B rows in shared memory instead of registers
+  const bool strip = !regs_ok && !batched && strip_supported(is_double, M, K, rowptr);   // B rows in shared memory instead of registers
   if (!regs_ok && !strip) return 0;
   // default: PTX text assembled by the driver (fast); LIBXSMM_B200_FSSPMDM_JIT=nvrtc: CUDA C++ through NVRTC
   const bool use_nvrtc = (env && 'n' == *env) && !strip;
@@ -459,12 +471,12 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
     cubin.push_back(0);
   }
   else if (!use_nvrtc) {
-    const std::string ptx = emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
+    const std::string ptx = emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val, batched);
     cubin.assign(ptx.begin(), ptx.end());
     cubin.push_back(0);
   }
   else {
-    if (rowptr[M] > 6000) return 0;
+    if (rowptr[M] > 6000 || batched) return 0;
     Nvrtc* rt = nvrtc();
     if (0 == rt) { set_error(-2, "fsspmdm: NVRTC (libnvrtc.so.12) not found; using the generic kernel"); return 0; }
     const std::string src = emit(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val);
@@ -498,6 +510,7 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
   FsJit* j = new FsJit();
   j->block = strip ? plan.G * 32 : kBlock;
   j->cols_per_thread = (vec2 && !is_double && !strip) ? 2 : 1;
+  j->batched = batched ? 1 : 0;
   j->strip = strip ? 1 : 0; j->esz = is_double ? 8 : 4; j->krows = K; j->box_rows = strip ? plan.box_rows : 0; j->strip_w = strip ? plan.W : 0; j->smem = strip ? plan.smem : 0;
   cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), 0, 0, 0, 0, 0, 0);
   if (cudaSuccess == e) e = cudaLibraryGetKernel(&j->kern, j->lib, "fs_baked");
@@ -513,6 +526,7 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
 
 bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream)
 {
+  if (j->batched) return false;
   if (j->strip) {
     // the strip form reads B through a TMA tensor map built from the caller's panel: 16-byte aligned base and row pitch
     CUtensorMap map;
@@ -531,6 +545,18 @@ bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, lo
   void* args[] = { (void*)&dB, (void*)&dC, (void*)&ncols, (void*)&ldb, (void*)&ldc };
   const cudaError_t e = cudaLaunchKernel((const void*)j->kern, dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, 0, stream);
   if (cudaSuccess != e) { set_error((int)e, "fsspmdm: baked kernel launch failed: %s", cudaGetErrorString(e)); return false; }
+  return true;
+}
+
+bool fs_jit_launch_batched(const FsJit* j, const void* dB, void* dC, long long n_elem, long long cols_per_elem, long long ldb, long long ldc,
+                           long long stride_b, long long stride_c, cudaStream_t stream)
+{
+  if (!j->batched) return false;
+  long long total = n_elem * cols_per_elem;
+  const long long blocks = (total + j->block - 1) / j->block;
+  void* args[] = { (void*)&dB, (void*)&dC, (void*)&total, (void*)&ldb, (void*)&ldc, (void*)&cols_per_elem, (void*)&stride_b, (void*)&stride_c };
+  const cudaError_t e = cudaLaunchKernel((const void*)j->kern, dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, 0, stream);
+  if (cudaSuccess != e) { set_error((int)e, "csr_soa: baked kernel launch failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return false; }
   return true;
 }
 

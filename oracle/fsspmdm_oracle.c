@@ -164,3 +164,39 @@ int orc_dfsspmdm_branch(int M, int K, int lda, const double* a, int ldb, int ldc
   free(rowptr); free(colidx); free(val);
   return branch;
 }
+
+/*
+ * CSR "A sparse" x dense SoA kernel: what the code emitted by
+ * src/generator_spgemm_csr_asparse_soa.c:213-420 computes for ONE element:
+ *     C[m][n][s] = (beta == 0 ? 0 : C[m][n][s]) + sum_z a[z] * B[col[z]][n][s],   z over row m's nonzeros in CSR order,
+ * B laid out [k][ldb][soa], C [m][ldc][soa].  One fused multiply-add per nonzero, in order, starting from the loaded C
+ * (any beta != 0 loads C: the generator only tests the BETA_0 flag, :253-267) or from zero.  A row without nonzeros is
+ * skipped entirely (:249: "if (l_row_elements > 0)"): its C entries are left untouched even for beta = 0.  The operator
+ * VALUES are read at run time from the kernel's first argument (:277-285); the N chunking (:176-180) does not change
+ * the arithmetic.  dbl: 1 = double, 0 = float.  n_elem elements, strides in scalars.
+ */
+void orc_csr_soa_execute(int dbl, int M, int N, int K, int ldb, int ldc, int soa, double beta,
+                         const uint32_t* rowptr, const uint32_t* colidx, const void* values,
+                         const void* B, void* C, long n_elem, long stride_b, long stride_c)
+{
+  long e; int m, n, s; uint32_t z;
+  (void)K;
+  for (e = 0; e < n_elem; ++e) for (m = 0; m < M; ++m) {
+    if (rowptr[m + 1] == rowptr[m]) continue;
+    for (n = 0; n < N; ++n) for (s = 0; s < soa; ++s) {
+      const size_t cat = (size_t)e * stride_c + ((size_t)m * ldc + n) * soa + s;
+      if (dbl) {
+        double acc = (0.0 == beta) ? 0.0 : ((double*)C)[cat];
+        for (z = rowptr[m]; z < rowptr[m + 1]; ++z)
+          acc = fma(((const double*)values)[z], ((const double*)B)[(size_t)e * stride_b + ((size_t)colidx[z] * ldb + n) * soa + s], acc);
+        ((double*)C)[cat] = acc;
+      }
+      else {
+        float acc = (0.0 == beta) ? 0.f : ((float*)C)[cat];
+        for (z = rowptr[m]; z < rowptr[m + 1]; ++z)
+          acc = fmaf(((const float*)values)[z], ((const float*)B)[(size_t)e * stride_b + ((size_t)colidx[z] * ldb + n) * soa + s], acc);
+        ((float*)C)[cat] = acc;
+      }
+    }
+  }
+}

@@ -170,6 +170,25 @@ class Oracle:
         return C
 
 
+    # -- CSR x dense SoA (section 8f-1) ------------------------------------------------
+    def csr_soa_execute(self, rowptr, colidx, values, B, C, N, ldb=None, ldc=None, soa=None, beta=0.0):
+        """in place on C.  B: [E][K][ldb][soa], C: [E][M][ldc][soa] (E may be absent)."""
+        values = np.ascontiguousarray(values)
+        dbl = 1 if values.dtype == np.float64 else 0
+        assert B.dtype == values.dtype and C.dtype == values.dtype and B.flags.c_contiguous and C.flags.c_contiguous
+        if B.ndim == 3:
+            B = B[None]; C = C[None]
+        E, K, ldb_, soa_ = B.shape
+        M = C.shape[1]
+        rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
+        f = self.lib.orc_csr_soa_execute
+        f.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double] + [ctypes.c_void_p] * 5 + [ctypes.c_long] * 3
+        f.restype = None
+        f(dbl, M, N, K, ldb_ if ldb is None else ldb, C.shape[2] if ldc is None else ldc, soa_ if soa is None else soa, float(beta),
+          _ptr(rowptr), _ptr(colidx), _ptr(values), _ptr(B), _ptr(C), E, K * ldb_ * soa_, M * C.shape[2] * soa_)
+        return C
+
+
 class Ref:
     """The compiled reference.  ``Ref.available()`` is False where oracle/_ref is absent."""
 
@@ -194,6 +213,35 @@ class Ref:
 
     def max_threads(self):
         return self.lib.refdrv_max_threads()
+
+    def csr_soa(self, rowptr, colidx, values, B, C, N, beta=0.0):
+        """libxsmm_create_xcsr_soa + one kernel call per element, in place on C.  B: [E][K][ldb][soa], C: [E][M][ldc][soa].
+        Returns the SoA width the reference's generator uses on this host (the arrays' last dimension must equal it)."""
+        values = np.ascontiguousarray(values)
+        dbl = 1 if values.dtype == np.float64 else 0
+        assert B.dtype == values.dtype and C.dtype == values.dtype and B.flags.c_contiguous and C.flags.c_contiguous
+        if B.ndim == 3:
+            B = B[None]; C = C[None]
+        E, K, ldb, soa = B.shape
+        M, ldc = C.shape[1], C.shape[2]
+        rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
+        used = ctypes.c_int(0)
+        f = self.lib.refdrv_csr_soa_run
+        f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double] + [ctypes.c_void_p] * 5 + [ctypes.c_long] * 3 + [ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        rc = f(dbl, M, N, K, ldb, ldc, float(beta), _ptr(rowptr), _ptr(colidx), _ptr(values), _ptr(B), _ptr(C), E, K * ldb * soa, M * ldc * soa,
+               ctypes.cast(ctypes.byref(used), ctypes.c_void_p))
+        if rc != 0:
+            raise RuntimeError("reference csr_soa kernel could not be generated (rc=%d)" % rc)
+        if used.value != soa:
+            raise ValueError("SoA width of the arrays is %d, the reference's generator uses %d on this host" % (soa, used.value))
+        return used.value
+
+    @staticmethod
+    def soa_width(dtype):
+        """SoA width of the reference's generator on this host (generator_spgemm_csr_asparse_soa.c:126-156)."""
+        avx512 = "avx512f" in open("/proc/cpuinfo").read()
+        return (8 if avx512 else 4) if np.dtype(dtype) == np.float64 else (16 if avx512 else 8)
 
     def geometry(self, M, N, K, max_threads=1):
         vec = (ctypes.c_int * 9)()

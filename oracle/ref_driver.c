@@ -137,3 +137,4 @@ int refdrv_fsspmdm_run(int dbl, int M, int N, int K, int lda, int ld, double bet
 }
 
 int refdrv_max_threads(void) { return omp_get_max_threads(); }
+

@@ -1,0 +1,41 @@
+/*
+ * TEST INFRASTRUCTURE ONLY (never linked into the product).  Second part of the driver around the UNMODIFIED reference
+ * (oracle/_ref/libxsmm_ref.so), compiled against the reference's OWN headers (the first part, ref_driver.c, is compiled
+ * against this repository's drop-in headers on purpose).
+ */
+/*
+ * CSR "A sparse" x dense SoA kernels: libxsmm_create_xcsr_soa, called the way
+ * samples/edge/asparse_srsoa.c:148-160 does -- descriptor (m, n, k, lda = 0, ldb, ldc, alpha = 1, beta, 'N','N', no prefetch),
+ * then kernel(values, B, C) once per element.  B is [k][ldb][soa], C is [m][ldc][soa] (soa = 8 doubles / 16 floats on an
+ * AVX-512 host, 4 / 8 otherwise: returned in *soa_width_used by probing the target the way the generator selects it).
+ * n_elem elements, strides in scalars.  Returns 0, or -1 if the kernel could not be generated.
+ */
+#include "libxsmm.h"
+int refdrv_csr_soa_run(int dbl, int M, int N, int K, int ldb, int ldc, double beta,
+                       const unsigned int* rowptr, const unsigned int* colidx, const void* values,
+                       const void* B, void* C, long n_elem, long stride_b, long stride_c, int* soa_width_used)
+{
+  libxsmm_descriptor_blob blob;
+  const int flags = LIBXSMM_GEMM_FLAGS('N', 'N');
+  long e;
+  libxsmm_init();
+  if (soa_width_used) {
+    const int avx512 = (libxsmm_get_target_archid() >= LIBXSMM_X86_AVX512);
+    *soa_width_used = dbl ? (avx512 ? 8 : 4) : (avx512 ? 16 : 8);
+  }
+  if (dbl) {
+    const libxsmm_gemm_descriptor* d = libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F64, M, N, K, 0, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
+    libxsmm_dmmfunction kern = (0 != d) ? libxsmm_create_xcsr_soa(d, rowptr, colidx, values).dmm : 0;
+    if (0 == kern) return -1;
+    for (e = 0; e < n_elem; ++e) kern((const double*)values, (const double*)B + e * stride_b, (double*)C + e * stride_c);
+    libxsmm_release_kernel((const void*)kern);
+  }
+  else {
+    const libxsmm_gemm_descriptor* d = libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F32, M, N, K, 0, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
+    libxsmm_smmfunction kern = (0 != d) ? libxsmm_create_xcsr_soa(d, rowptr, colidx, values).smm : 0;
+    if (0 == kern) return -1;
+    for (e = 0; e < n_elem; ++e) kern((const float*)values, (const float*)B + e * stride_b, (float*)C + e * stride_c);
+    libxsmm_release_kernel((const void*)kern);
+  }
+  return 0;
+}

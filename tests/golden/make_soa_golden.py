@@ -1,0 +1,69 @@
+"""Generates tests/golden/csr_soa.npz by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref): libxsmm_create_xcsr_soa kernels
+(src/generator_spgemm_csr_asparse_soa.c) on real EDGE operators shipped under /root/reference/samples/edge/mats
+(tet4_<order>_stiffV / stiffT / fluxN, CSR files) and two synthetic ones (a dense operator, one with empty rows), for
+double (SoA width 8) and float (16), beta = 0 and 1, two mesh elements each -- driven like samples/edge/asparse_srsoa.c.
+
+    python tests/golden/make_soa_golden.py
+
+(The largest stiffness operators, e.g. tet4_6_stiffV_2 with 1680 nonzeros and beta = 1, make the reference's generator run
+past its 128 KiB code buffer -- "stack smashing detected" -- so the order-6 case here is the smaller stiffT_0.)
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pyoracle  # noqa: E402
+
+w = importlib.import_module("libxsmm-1_b200.workloads")
+MATS = "/root/reference/samples/edge/mats"
+
+
+def csr_of(a):
+    rp, ci, va = [0], [], []
+    for i in range(a.shape[0]):
+        nz = np.nonzero(a[i])[0]
+        ci += list(nz); va += list(a[i, nz]); rp.append(len(ci))
+    return np.array(rp, np.uint32), np.array(ci, np.uint32), np.array(va, a.dtype)
+
+
+def main():
+    pyoracle.build_ref("avx2")
+    ref = pyoracle.Ref()
+    assert ref.soa_width(np.float64) == 8, "generate on an AVX-512 host (SoA width 8 / 16)"
+    rng = np.random.default_rng(31)
+    ops = []
+    for f in ("tet4_4_stiffV_0_csr.mtx", "tet4_5_stiffT_1_csr.mtx", "tet4_3_fluxN_5_csr.mtx", "tet4_6_stiffT_0_csr.mtx"):
+        ops.append((f[:-8], w.read_mtx(os.path.join(MATS, f))))
+    ops.append(("dense_12x12", rng.uniform(-1, 1, (12, 12))))
+    sp = np.where(rng.random((20, 28)) < 0.15, rng.uniform(-1, 1, (20, 28)), 0.0); sp[4, :] = 0; sp[19, :] = 0
+    ops.append(("synthetic_empty_rows", sp))
+    out, names = {}, []
+    for name, a64 in ops:
+        for dt in (np.float64, np.float32):
+            a = a64.astype(dt)
+            rp, ci, va = csr_of(a)
+            M, K = a.shape
+            N, E = 9, 2
+            soa = ref.soa_width(dt)
+            B = rng.uniform(-1, 1, (E, K, N, soa)).astype(dt); C0 = rng.uniform(-1, 1, (E, M, N, soa)).astype(dt)
+            key = "%s_%s" % (name, "d" if dt == np.float64 else "s")
+            names.append(key)
+            out[key + "_shape"] = np.array([M, K, N, soa, E], np.int32)
+            out[key + "_rowptr"], out[key + "_colidx"], out[key + "_values"] = rp, ci, va
+            out[key + "_B"], out[key + "_C0"] = B, C0
+            for beta in (0.0, 1.0):
+                C = C0.copy()
+                ref.csr_soa(rp, ci, va, B, C, N, beta)
+                out[key + "_out%d" % int(beta)] = C
+    np.savez_compressed(os.path.join(HERE, "csr_soa.npz"), names=np.array(names), **out)
+    print("wrote csr_soa.npz:", len(names), "cases")
+
+
+if __name__ == "__main__":
+    main()
