@@ -142,6 +142,25 @@ LIBXSMM_API void libxsmm_b200_csr_soa_execute(const libxsmm_b200_csr_soa* handle
 LIBXSMM_API int libxsmm_b200_csr_soa_is_baked(const libxsmm_b200_csr_soa* handle);
 LIBXSMM_API void libxsmm_b200_csr_soa_destroy(libxsmm_b200_csr_soa* handle);
 
+/* Dense SMM dispatch for row-major operators with very many columns: the GPU counterpart of
+ *     kernel = libxsmm_dmmdispatch(nblock, M_op, K_op, &ldb_panel, &lda_op, &ldc_panel, alpha, beta, flags, prefetch)
+ *     for (i = 0; i < N; i += nblock) kernel(B_panel + i, A_op, C_panel + i)
+ * (reference src/libxsmm_main.c:2166-2195; caller samples/pyfr/pyfr_gemm_rm.c:98-122).  Same argument meaning as
+ * libxsmm_[sd]mmdispatch: column-major C(m x n) = A(m x k) B(k x n) + beta C with NULL lda / ldb / ldc = m / k / m and
+ * NULL alpha / beta = 1; like the reference's JIT it exists for alpha = 1 and beta in {0, 1} only (NULL otherwise).
+ * execute covers m_total rows of A and C -- all the chunks of the caller's loop -- in one asynchronous call: d_a, d_c
+ * are DEVICE pointers, b (the small k x n operand = the row-major operator, pitch ldb) may be a host or a device
+ * pointer and is read at every call; the handle keeps the kernel baked for the operand's current content and re-bakes when
+ * it changes.  Per output element: an in-order chain of fused multiply-adds over k starting from C (beta = 1) or 0. */
+typedef struct libxsmm_b200_mm libxsmm_b200_mm;
+LIBXSMM_API libxsmm_b200_mm* libxsmm_b200_dmmdispatch(int m, int n, int k, const int* lda, const int* ldb, const int* ldc,
+  const double* alpha, const double* beta);
+LIBXSMM_API libxsmm_b200_mm* libxsmm_b200_smmdispatch(int m, int n, int k, const int* lda, const int* ldb, const int* ldc,
+  const float* alpha, const float* beta);
+LIBXSMM_API void libxsmm_b200_mm_execute(libxsmm_b200_mm* handle, const void* d_a, const void* b, void* d_c, long long m_total, void* stream);
+LIBXSMM_API const char* libxsmm_b200_mm_kernel(const libxsmm_b200_mm* handle);   /* which kernel the handle currently holds */
+LIBXSMM_API void libxsmm_b200_mm_release(libxsmm_b200_mm* handle);
+
 /* Host-only planning entries (no CUDA call is made; they work on a machine without a GPU).
  * geometry: the block geometry libxsmm_spmdm_init would choose (reference src/libxsmm_spmdm.c:552-608)
  *   for bn = 48 | 96 | 6; geom[9] = m n k bm bn bk mb nb kb.  Returns 0 on success.

@@ -53,6 +53,7 @@ ADDED_SYMBOLS = [
     "libxsmm_b200_csr_read_mtx", "libxsmm_b200_csr_free", "libxsmm_b200_dfsspmdm_create_mtx", "libxsmm_b200_sfsspmdm_create_mtx",
     "libxsmm_b200_dcsr_soa_create", "libxsmm_b200_scsr_soa_create", "libxsmm_b200_csr_soa_execute", "libxsmm_b200_csr_soa_is_baked",
     "libxsmm_b200_csr_soa_destroy",
+    "libxsmm_b200_dmmdispatch", "libxsmm_b200_smmdispatch", "libxsmm_b200_mm_execute", "libxsmm_b200_mm_kernel", "libxsmm_b200_mm_release",
 ]
 
 
@@ -620,6 +621,46 @@ class Fsspmdm:
     def destroy(self):
         if self.handle:
             (libxsmm_dfsspmdm_destroy if self.double else libxsmm_sfsspmdm_destroy)(self.handle)
+            self.handle = None
+
+
+class MmDispatch:
+    """libxsmm_b200_[sd]mmdispatch: column-major SMM handle used the way samples/pyfr/pyfr_gemm_rm.c:98-122 uses
+    libxsmm_dmmdispatch (row-major operator applied to a panel with very many columns)."""
+
+    def __init__(self, m, n, k, lda=None, ldb=None, ldc=None, alpha=None, beta=None, dtype=np.float64):
+        require_gpu()
+        L = load()
+        self.double = np.dtype(dtype) == np.float64
+        f = L.libxsmm_b200_dmmdispatch if self.double else L.libxsmm_b200_smmdispatch
+        f.restype = ctypes.c_void_p
+        f.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5
+        sc = ctypes.c_double if self.double else ctypes.c_float
+        box = lambda v, t: None if v is None else ctypes.cast(ctypes.pointer(t(v)), ctypes.c_void_p)   # noqa: E731
+        self.handle = f(m, n, k, box(lda, ctypes.c_int), box(ldb, ctypes.c_int), box(ldc, ctypes.c_int), box(alpha, sc), box(beta, sc))
+        if not self.handle:
+            code, msg = last_error()
+            clear_error()
+            raise ValueError("mmdispatch failed: %s" % msg)
+
+    def execute(self, d_a, b, d_c, m_total, stream=None):
+        L = load()
+        L.libxsmm_b200_mm_execute.restype = None
+        L.libxsmm_b200_mm_execute.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
+        L.libxsmm_b200_mm_execute(self.handle, _addr(d_a), _addr(b), _addr(d_c), m_total, _sptr(stream))
+
+    @property
+    def kernel(self):
+        L = load()
+        L.libxsmm_b200_mm_kernel.restype = ctypes.c_char_p
+        L.libxsmm_b200_mm_kernel.argtypes = [ctypes.c_void_p]
+        return L.libxsmm_b200_mm_kernel(self.handle).decode()
+
+    def release(self):
+        if self.handle:
+            L = load()
+            L.libxsmm_b200_mm_release.argtypes = [ctypes.c_void_p]
+            L.libxsmm_b200_mm_release(self.handle)
             self.handle = None
 
 

@@ -845,6 +845,87 @@ void libxsmm_b200_csr_soa_execute(const libxsmm_b200_csr_soa* handle, const void
 int libxsmm_b200_csr_soa_is_baked(const libxsmm_b200_csr_soa* handle) { return fs_is_baked((const FsOperator*)handle); }
 void libxsmm_b200_csr_soa_destroy(libxsmm_b200_csr_soa* handle) { fs_destroy((FsOperator*)handle); }
 
+// ---- dense SMM dispatch for row-major operators with very many columns ---------------------------
+// The reference's callers apply a DENSE fixed operator to a row-major panel with the column-major SMM kernel
+//     kernel = libxsmm_dmmdispatch(nblock, M_op, K_op, &ldb_panel, &lda_op, &ldc_panel, alpha, beta, ...)
+//     kernel(B_panel + i, A_op, C_panel + i)          for i = 0, nblock, 2 nblock, ...
+// (samples/pyfr/pyfr_gemm_rm.c:98-122; libxsmm_[sd]mmdispatch, src/libxsmm_main.c:2166-2195; it is also what
+// libxsmm_[sd]fsspmdm_create falls back to, src/libxsmm_fsspmdm.c:134-142).  Column-major C(m x n) = A(m x k) B(k x n) + beta C
+// with m = panel columns, n = operator rows, k = operator columns: A[i + l lda] is panel element (row l, column i) and
+// B[l + j ldb] is operator element (row j, column l), so the small operand b IS the row-major operator with pitch ldb.
+// Here one execute call covers m_total panel columns (all the chunks of the caller's loop).  The small operand is read at
+// execute (host or device pointer); the handle keeps the kernel baked for its current CONTENT (fused multiply-add chains
+// with literal values, or the tcgen05 kernel for dense float operators) and re-bakes only when the content changes --
+// the callers' operators are constant.  Rounding sequence of the reference's SMM kernel: in-order fma over k from C / 0.
+struct libxsmm_b200_mm;
+struct MmHandle {
+  int is_double, m, n, k, lda, ldb, ldc;
+  double beta;
+  std::mutex mtx;
+  unsigned long long hash;
+  FsOperator* op;
+};
+
+static MmHandle* mm_dispatch(int is_double, int m, int n, int k, const int* lda, const int* ldb, const int* ldc, double alpha, double beta)
+{
+  const int la = lda ? *lda : m, lb = ldb ? *ldb : k, lc = ldc ? *ldc : m;
+  if (m <= 0 || n <= 0 || k <= 0 || la < m || lb < k || lc < m || !(1.0 == alpha) || !(0.0 == beta || 1.0 == beta)) {
+    set_error(-70, "mmdispatch: unsupported descriptor (m=%d n=%d k=%d lda=%d ldb=%d ldc=%d alpha=%g beta=%g; alpha must be 1, beta 0 or 1 like the reference's JIT)", m, n, k, la, lb, lc, alpha, beta);
+    return 0;
+  }
+  MmHandle* h = new MmHandle();
+  h->is_double = is_double; h->m = m; h->n = n; h->k = k; h->lda = la; h->ldb = lb; h->ldc = lc; h->beta = beta; h->hash = 0; h->op = 0;
+  return h;
+}
+
+libxsmm_b200_mm* libxsmm_b200_dmmdispatch(int m, int n, int k, const int* lda, const int* ldb, const int* ldc, const double* alpha, const double* beta)
+{ return (libxsmm_b200_mm*)mm_dispatch(1, m, n, k, lda, ldb, ldc, alpha ? *alpha : 1.0, beta ? *beta : 1.0); }   // LIBXSMM_ALPHA = LIBXSMM_BETA = 1
+libxsmm_b200_mm* libxsmm_b200_smmdispatch(int m, int n, int k, const int* lda, const int* ldb, const int* ldc, const float* alpha, const float* beta)
+{ return (libxsmm_b200_mm*)mm_dispatch(0, m, n, k, lda, ldb, ldc, alpha ? (double)*alpha : 1.0, beta ? (double)*beta : 1.0); }
+
+void libxsmm_b200_mm_execute(libxsmm_b200_mm* handle, const void* d_a, const void* b, void* d_c, long long m_total, void* stream)
+{
+  MmHandle* h = (MmHandle*)handle;
+  if (0 == h || 0 == d_a || 0 == b || 0 == d_c) { set_error(-71, "mm_execute: NULL argument"); return; }
+  if (m_total <= 0) return;
+  const size_t esz = h->is_double ? 8 : 4;
+  const size_t nb = ((size_t)(h->n - 1) * h->ldb + h->k) * esz;      // the operator as it lies in memory: n rows of pitch ldb
+  std::vector<unsigned char> host(nb);
+  if (is_device_ptr(b)) {
+    XB_CUDA(cudaMemcpyAsync(host.data(), b, nb, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    XB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  else memcpy(host.data(), b, nb);
+  unsigned long long hash = 1469598103934665603ull;                      // FNV-1a over the operator's elements (not the pitch padding)
+  for (int j = 0; j < h->n; ++j) {
+    const unsigned char* row = host.data() + (size_t)j * h->ldb * esz;
+    for (size_t z = 0; z < (size_t)h->k * esz; ++z) { hash ^= row[z]; hash *= 1099511628211ull; }
+  }
+  std::lock_guard<std::mutex> lock(h->mtx);
+  if (0 == h->op || hash != h->hash) {
+    if (h->op) { XB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); fs_destroy(h->op); h->op = 0; }
+    h->op = fs_create(h->is_double, h->n, -1 /* any column count */, h->k, h->ldb, h->lda, h->ldc, h->beta, host.data());
+    h->hash = hash;
+    if (0 == h->op) return;
+  }
+  fs_execute(h->op, d_a, d_c, m_total, h->lda, h->ldc, (cudaStream_t)stream);
+}
+
+const char* libxsmm_b200_mm_kernel(const libxsmm_b200_mm* handle)
+{
+  const MmHandle* h = (const MmHandle*)handle;
+  if (0 == h || 0 == h->op) return "none";
+  return fs_is_tensor_core(h->op) ? "fs_tc_kernel" : (fs_is_baked(h->op) ? "fs_baked" : "fs_generic_kernel");
+}
+
+void libxsmm_b200_mm_release(libxsmm_b200_mm* handle)
+{
+  MmHandle* h = (MmHandle*)handle;
+  if (0 == h) return;
+  if (h->op) fs_destroy(h->op);
+  delete h;
+}
+
 // =====================================================================================================
 // service
 // =====================================================================================================

@@ -136,7 +136,9 @@ FsOperator* fs_plan(int is_double, int M, int N, int K, int lda, int ldb, int ld
 {
   // the reference asserts this contract (src/libxsmm_fsspmdm.c:65-71) and calls a NULL kernel when it
   // is violated in a release build; here a violation is an error and create returns NULL.
-  if (M <= 0 || K <= 0 || N < 16 || 0 != (N % 16) || K > lda || N > ldb || N > ldc || 0 == a_dense
+  // N < 0: no contract on the column count (the dense dispatch entry, capi.cu: the caller's panels may have any width)
+  const bool free_n = (N < 0);
+  if (M <= 0 || K <= 0 || (!free_n && (N < 16 || 0 != (N % 16) || N > ldb || N > ldc)) || K > lda || 0 == a_dense
       || !(beta == 0.0 || beta == 1.0)) {
     set_error(-1, "fsspmdm_create: contract violated (M=%d N=%d K=%d lda=%d ldb=%d ldc=%d beta=%g)", M, N, K, lda, ldb, ldc, beta);
     return 0;
@@ -153,7 +155,7 @@ FsOperator* fs_plan(int is_double, int M, int N, int K, int lda, int ldb, int ld
   o->n_unique = 0;
   o->sparse_branch = 0;
   o->x86_code_size = 0;
-  if (is_double && o->nnz > 0) {
+  if (is_double && o->nnz > 0 && !free_n) {   // (the dense dispatch entry is the dense SMM kernel by definition: no sparse_reg branch)
     std::vector<double> table;
     std::vector<double> exec_val(o->val);
     table.push_back(o->val[0]);

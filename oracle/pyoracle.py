@@ -237,6 +237,20 @@ class Ref:
             raise ValueError("SoA width of the arrays is %d, the reference's generator uses %d on this host" % (soa, used.value))
         return used.value
 
+    def mm_rm(self, a, B, C, beta=1.0, nblock=16, lda=None):
+        """libxsmm_[sd]mmdispatch applied to a row-major panel like samples/pyfr/pyfr_gemm_rm.c:98-122; in place on C."""
+        a = np.ascontiguousarray(a)
+        dbl = 1 if a.dtype == np.float64 else 0
+        assert B.dtype == a.dtype and C.dtype == a.dtype and B.flags.c_contiguous and C.flags.c_contiguous and B.shape[1] == C.shape[1]
+        M, K = a.shape
+        f = self.lib.refdrv_mm_rm_run
+        f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_int] + [ctypes.c_void_p] * 3
+        f.restype = ctypes.c_int
+        rc = f(dbl, M, B.shape[1], K, K if lda is None else lda, B.shape[1], float(beta), nblock, _ptr(a), _ptr(B), _ptr(C))
+        if rc != 0:
+            raise RuntimeError("reference mmdispatch failed rc=%d" % rc)
+        return C
+
     @staticmethod
     def soa_width(dtype):
         """SoA width of the reference's generator on this host (generator_spgemm_csr_asparse_soa.c:126-156)."""

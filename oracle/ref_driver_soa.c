@@ -39,3 +39,30 @@ int refdrv_csr_soa_run(int dbl, int M, int N, int K, int ldb, int ldc, double be
   }
   return 0;
 }
+
+/*
+ * Dense SMM dispatch used on a row-major panel, exactly as samples/pyfr/pyfr_gemm_rm.c:98-122:
+ *     kernel = libxsmm_dmmdispatch(nblock, M, K, &ld_panel, &lda_op, &ld_panel, &alpha, &beta, NULL, &prefetch_none)
+ *     for (i = 0; i < N; i += nblock) kernel(B + i, A, C + i)
+ * A: M x K row-major operator (pitch lda_op); B: K x N panel, C: M x N panel (pitch ld).  N % nblock == 0.
+ */
+int refdrv_mm_rm_run(int dbl, int M, int N, int K, int lda_op, int ld, double beta, int nblock, const void* A, const void* B, void* C)
+{
+  const int prefetch = LIBXSMM_GEMM_PREFETCH_NONE;
+  int i;
+  if (nblock <= 0 || 0 != (N % nblock)) return -2;
+  libxsmm_init();
+  if (dbl) {
+    const double alpha = 1.0;
+    libxsmm_dmmfunction kern = libxsmm_dmmdispatch(nblock, M, K, &ld, &lda_op, &ld, &alpha, &beta, NULL, &prefetch);
+    if (0 == kern) return -1;
+    for (i = 0; i < N; i += nblock) kern((const double*)B + i, (const double*)A, (double*)C + i);
+  }
+  else {
+    const float alpha = 1.f, fbeta = (float)beta;
+    libxsmm_smmfunction kern = libxsmm_smmdispatch(nblock, M, K, &ld, &lda_op, &ld, &alpha, &fbeta, NULL, &prefetch);
+    if (0 == kern) return -1;
+    for (i = 0; i < N; i += nblock) kern((const float*)B + i, (const float*)A, (float*)C + i);
+  }
+  return 0;
+}

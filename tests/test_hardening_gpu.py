@@ -236,3 +236,71 @@ def test_concurrent_execute_on_host_panels(gpu, oracle):
     oracle.dfsspmdm_execute(a, B, want, 1.0, oracle.dfsspmdm_branch(a, Ntot, Ntot, 1.0))
     np.testing.assert_array_equal(C.view(np.uint64), want.view(np.uint64))
     xs.check()
+
+
+@pytest.mark.parametrize("kind", ["spmdm-f32", "spmdm-bf16", "fsspmdm-regs", "fsspmdm-strip", "csr-soa"])
+def test_guard_bands_stay_intact(gpu, oracle, monkeypatch, kind):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_compute_sanitizer_closed.log), so out-of-bounds WRITES are
+    hunted the plain way: every output (and every input, which must not be written at all) sits between two 64 KiB guard
+    bands of a known pattern inside a larger allocation, shapes are ragged on purpose, and the bands -- and the inputs --
+    must be bit-identical afterwards, for the CUDA-core and the tensor-core dispatch."""
+    xs = gpu
+    G = 1 << 16
+
+    def guarded(arr):
+        raw = np.full(2 * G + arr.nbytes, 0xA5, np.uint8)
+        raw[G:G + arr.nbytes] = arr.view(np.uint8).ravel()
+        d = xs.DeviceBuffer.from_numpy(raw)
+        return d, raw
+
+    def check(d, raw, nbytes, changed_ok):
+        got = d.to_numpy(np.uint8, raw.shape)
+        assert np.array_equal(got[:G], raw[:G]) and np.array_equal(got[G + nbytes:], raw[G + nbytes:]), "guard band overwritten"
+        if not changed_ok:
+            assert np.array_equal(got, raw), "input buffer was written"
+        d.free()
+
+    rng = np.random.default_rng(12)
+    if kind.startswith("spmdm"):
+        bf16 = kind.endswith("bf16")
+        for tc in ("0", "1"):
+            monkeypatch.setenv("LIBXSMM_B200_SPMDM_TC", tc)
+            for (M, N, K, ta, tb, tcc) in ((300, 203, 260, "N", "N", "N"), (513, 97, 384, "N", "N", "N"), (260, 200, 300, "T", "N", "T"), (129, 333, 128, "N", "T", "N")):
+                A, B, C0 = xs.workloads.spmdm_inputs(M, N, K, 0.2, dtype="bf16" if bf16 else "f32", seed=M, transa=ta, transb=tb, transc=tcc)
+                (dA, rA), (dB, rB), (dC, rC) = guarded(A), guarded(B), guarded(C0)
+                p = xs.Spmdm(M, N, K, 2)
+                p.create_slices(dA.ptr + G, ta, bf16)
+                p.compute(dB.ptr + G, dC.ptr + G, tb, tcc, 0 if bf16 else 0.5, bf16)
+                xs.synchronize()
+                p.destroy()
+                check(dA, rA, A.nbytes, False); check(dB, rB, B.nbytes, False); check(dC, rC, C0.nbytes, True)
+    elif kind.startswith("fsspmdm"):
+        for dt in (np.float64, np.float32):
+            M, K = (150, 125) if kind.endswith("strip") else (47, 33)
+            a = np.where(rng.random((M, K)) < 0.1, rng.uniform(-1, 1, (M, K)), 0).astype(dt)
+            for (N, ld) in ((16, 16), (80, 80), (48, 112), (1040, 1040)):
+                B = rng.uniform(-1, 1, (K, ld)).astype(dt); C0 = rng.uniform(-1, 1, (M, ld)).astype(dt)
+                (dB, rB), (dC, rC) = guarded(B), guarded(C0)
+                op = xs.Fsspmdm(a, N, ldb=ld, ldc=ld, beta=1.0)
+                assert xs.fsspmdm_plan(a, N=N, ldb=ld, ldc=ld)["form"] == ("baked-strip" if kind.endswith("strip") else "baked-registers")
+                op.execute_stream(dB.ptr + G, dC.ptr + G)
+                xs.synchronize()
+                got = dC.to_numpy(np.uint8, rC.shape)[G:G + C0.nbytes].view(dt).reshape(C0.shape)
+                assert np.array_equal(got[:, N:], C0[:, N:]), "columns past N were written"
+                op.destroy()
+                check(dB, rB, B.nbytes, False); check(dC, rC, C0.nbytes, True)
+    else:
+        M, K, N, soa, E = 35, 35, 9, 8, 7
+        a = np.where(rng.random((M, K)) < 0.1, rng.uniform(-1, 1, (M, K)), 0)
+        rp, ci, va = [0], [], []
+        for i in range(M):
+            nz = np.nonzero(a[i])[0]
+            ci += list(nz); va += list(a[i, nz]); rp.append(len(ci))
+        B = rng.uniform(-1, 1, (E, K, N, soa)); C0 = rng.uniform(-1, 1, (E, M, N, soa))
+        (dB, rB), (dC, rC) = guarded(B), guarded(C0)
+        op = xs.CsrSoa(M, N, K, np.array(rp, np.uint32), np.array(ci, np.uint32), np.array(va), soa, beta=1.0)
+        op.execute(dB.ptr + G, dC.ptr + G, E)
+        xs.synchronize()
+        op.destroy()
+        check(dB, rB, B.nbytes, False); check(dC, rC, C0.nbytes, True)
+    xs.check()
