@@ -67,6 +67,11 @@ WORKLOADS = {
     "c3-tet": dict(kind="fsspmdm", fixture="pyfr_p4_tet_m6", M=105, K=60, dtype="f64", N=1 << 20, beta=0.0,
                    desc="dfsspmdm fp64 PyFR p4/tet/m6-sp (105x60, 50% dense, 202 distinct values: reference dense branch), N=2^20 columns, beta=0"),
 }
+# CSR x dense SoA at EDGE sizes: the order-4 tetrahedral stiffness operator of the reference's EDGE proxy
+# (samples/edge/mats/tet4_4_stiffV_0: 35 x 35, 108 nonzeros; fixture tests/golden/csr_soa.npz), 9 quantities x 8 fused runs per
+# element ([35][9][8] doubles = 20 KB per tensor), 2^16 mesh elements per step
+WORKLOADS["soa"] = dict(kind="soa", case="tet4_4_stiffV_0_d", dtype="f64", elements=1 << 16, beta=1.0,
+                        desc="dcsr_soa EDGE tet4 order 4 stiffV_0 (35x35, 108 nnz) x [35][9][8] tensors, 65536 elements, beta=1")
 FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: 148 SMs x 128 FMA lanes at the 1965 MHz the CUDA-core kernels run at (nominal; no measured figure in MEASURED_PEAKS.json)
 L2_BYTES = 126 << 20
 
@@ -209,6 +214,48 @@ def fs_operator(xs, wl):
                                     np.float64 if wl["dtype"] == "f64" else np.float32)
     return xs.workloads.fsspmdm_operator(wl["M"], wl["K"], wl["density"], wl["n_unique"],
                                          np.float64 if wl["dtype"] == "f64" else np.float32, seed=1)
+
+
+def run_soa_gpu(xs, wl, steps, warmup):
+    d = np.load(os.path.join(ROOT, "tests", "golden", "csr_soa.npz"))
+    key = wl["case"]
+    M, K, N, soa, _ = (int(x) for x in d[key + "_shape"])
+    rp, ci, va = d[key + "_rowptr"], d[key + "_colidx"], d[key + "_values"]
+    E = wl["elements"]
+    esz = va.dtype.itemsize
+    bB, bC = E * K * N * soa * esz, E * M * N * soa * esz
+    op = xs.CsrSoa(M, N, K, rp, ci, va, soa, beta=wl["beta"])
+    nsets = max(1, int(np.ceil(2.5 * L2_BYTES / (bB + bC))))
+    ring = []
+    for s_ in range(nsets):
+        dB, dC = xs.DeviceBuffer(bB), xs.DeviceBuffer(bC)
+        fill_device_random(xs, dB, bB, va.dtype, 21 + s_)
+        dC.fill(0)
+        ring.append((dB, dC))
+    st = xs.Stream()
+    t0, t1 = xs.Event(), xs.Event()
+    for i in range(warmup):
+        op.execute(*ring[i % nsets], E, stream=st)
+    st.synchronize(); xs.check()
+    yield "ready"
+    l0 = xs.launch_count()
+    t0.record(st)
+    for i in range(steps):
+        op.execute(*ring[(warmup + i) % nsets], E, stream=st)
+    t1.record(st)
+    st.synchronize()
+    total_ms = t0.elapsed_ms(t1)
+    xs.check()
+    nnz = len(va)
+    rows_touched = int(np.count_nonzero(np.diff(rp)))       # rows without nonzeros are neither read nor written,
+    cols_used = int(len(np.unique(ci)))                      # B rows no nonzero refers to are never read
+    bytes_ = esz * E * N * soa * (cols_used + rows_touched * (2 if float(wl["beta"]) != 0.0 else 1))
+    yield dict(total_ms=total_ms, launches=xs.launch_count() - l0, nnz=nnz, flops=2.0 * nnz * N * soa * E, geo=dict(baked=op.is_baked, M=M, K=K, N=N, soa=soa, elements=E),
+               kernel_ms=total_ms / steps, kernel_bytes=bytes_, kernel_name=xs.last_compute_kernel(), parts={}, step_bytes=bytes_, ring_sets=nsets, ring_bytes=nsets * (bB + bC))
+    for bufs in ring:
+        for b in bufs:
+            b.free()
+    op.destroy()
 
 
 def fill_device_random(xs, dbuf, nbytes, dtype, seed):
@@ -401,6 +448,25 @@ def cpu_reference(wl, budget_s, reps_min=1, reps_max=50):
             flavors.append("avx512")
     except Exception:
         pass
+    if wl["kind"] == "soa":
+        if not have_ref:
+            raise RuntimeError("no compiled reference for the SoA kernel")
+        d = np.load(os.path.join(ROOT, "tests", "golden", "csr_soa.npz"))
+        key = wl["case"]
+        M, K, N, soa, _ = (int(x) for x in d[key + "_shape"])
+        rp, ci, va = d[key + "_rowptr"], d[key + "_colidx"], d[key + "_values"]
+        ref = pyoracle.Ref()
+        if ref.soa_width(va.dtype) != soa:
+            raise RuntimeError("host without AVX-512: the reference's SoA width differs from the workload's")
+        E = min(wl["elements"], 1 << 14)                      # bounded sample: 2^14 elements (~0.65 GB of tensors)
+        rng = np.random.default_rng(3)
+        B = rng.random((E, K, N, soa)).astype(va.dtype); C = np.zeros((E, M, N, soa), va.dtype)
+        tm = ref.csr_soa_bench(rp, ci, va, B, C, N, wl["beta"], threads=cores, reps=1)
+        reps = int(min(reps_max, max(reps_min, budget_s / max(tm[0], 1e-4))))
+        tm = ref.csr_soa_bench(rp, ci, va, B, C, N, wl["beta"], threads=cores, reps=reps)
+        ms = float(np.median(tm)) * 1e3
+        return dict(value=2.0 * len(va) * N * soa * E / ms / 1e6, ms=ms, best_ms=float(tm.min()) * 1e3, cores=cores, kind="reference",
+                    sample="2^14 of the workload's elements, %d reps, median; libxsmm_create_xcsr_soa kernel, OpenMP over elements" % reps)
     if wl["kind"] == "spmdm":
         t = wl["trans"]
         A, B, C0 = w.spmdm_inputs(wl["M"], wl["N"], wl["K"], wl["density"], dtype=wl["dtype"], seed=1, transa=t[0], transb=t[1], transc=t[2])
@@ -464,7 +530,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--others", default="c1,c4,c4-tnt,c4-ntn,c3-b1,c3-hex,c3-tet", help="extra workloads reported inside the line (N=1 only); '' = none")
+    ap.add_argument("--others", default="c1,c4,c4-tnt,c4-ntn,c3-b1,c3-hex,c3-tet,soa", help="extra workloads reported inside the line (N=1 only); '' = none")
     ap.add_argument("--sharded", default="c3,c5", help="column-sharded fsspmdm configs reported in `column_sharded` at every N (strong scaling); '' = none")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of reference CPU time for the headline cpu_baseline (a quarter of it per secondary workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -541,8 +607,12 @@ def main():
         if sampler:
             sampler.start()
             time.sleep(0.3)
-        gen = run_spmdm_gpu(xs, wl_, args.steps, args.warmup, want_e2e) if wl_["kind"] == "spmdm" else \
-            run_fs_gpu(xs, wl_, args.steps, args.warmup, shard, want_e2e, rank if shard > 1 else 0)
+        if wl_["kind"] == "soa":
+            want_e2e = False
+            gen = run_soa_gpu(xs, wl_, args.steps, args.warmup)
+        else:
+            gen = run_spmdm_gpu(xs, wl_, args.steps, args.warmup, want_e2e) if wl_["kind"] == "spmdm" else \
+                run_fs_gpu(xs, wl_, args.steps, args.warmup, shard, want_e2e, rank if shard > 1 else 0)
         assert next(gen) == "ready"
         barrier()
         res = next(gen)
@@ -602,7 +672,7 @@ def main():
                    "per_gpu": ("replicas: every rank multiplies its own 4096-column panel with its own copy of A (weak scaling; BASELINE.json names no sharding for this config); "
                                "the column-SHARDED configs (C3, C5) are in `column_sharded`" if spm else
                                "one N/%d-column panel of the global problem per rank, operator replicated, no collective on the data path (strong scaling)" % world),
-                   "global_N": (wl["N"] * world if spm else wl["N"]), **({"numa": numa} if numa else {}), "inputs": "bf16" if wl["dtype"] == "bf16" else wl["dtype"],
+                   "global_N": (wl.get("N", 0) * world if spm else wl.get("N", 0)), **({"numa": numa} if numa else {}), "inputs": "bf16" if wl["dtype"] == "bf16" else wl["dtype"],
                    "l2_policy": "inputs larger than L2: ring of %d input sets = %.0f MB, a different set every step" % (res["ring_sets"], res["ring_bytes"] / 1e6),
                    "geometry": res["geo"], "nnz": res["nnz"], "step": "createSparseSlice (all blocks) + compute (all blocks)" if spm else "execute"},
         "hbm_gbs": res["step_bytes"] * world / (ms_per_step * 1e6),

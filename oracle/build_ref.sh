@@ -43,7 +43,7 @@ gcc -shared -fcommon -o "$OUT/libxsmm_ref$SUFFIX.so" "$OBJ"/*.o -lm -ldl -lpthre
 # samples/spmdm/spmdm.c:88-111 and samples/pyfr/pyfr_driver_asp_reg.c:297-308 do.
 DRV="$OUT/drv$SUFFIX"; mkdir -p "$DRV"
 gcc -O2 -fPIC -fopenmp -fcommon -c -I"$HERE/../include" -o "$DRV/ref_driver.o" "$HERE/ref_driver.c"
-gcc -O2 -fPIC -fcommon -w -c -I"$OUT/include" -I"$REF/include" -o "$DRV/ref_driver_soa.o" "$HERE/ref_driver_soa.c"
+gcc -O2 -fPIC -fopenmp -fcommon -w -c -I"$OUT/include" -I"$REF/include" -o "$DRV/ref_driver_soa.o" "$HERE/ref_driver_soa.c"
 gcc -shared -fopenmp -fcommon -o "$OUT/libref_driver$SUFFIX.so" "$DRV/ref_driver.o" "$DRV/ref_driver_soa.o" \
     -L"$OUT" -l:libxsmm_ref$SUFFIX.so -Wl,-rpath,'$ORIGIN' -lm
 echo "build_ref: wrote $OUT/libxsmm_ref$SUFFIX.so and $OUT/libref_driver$SUFFIX.so"

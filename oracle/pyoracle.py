@@ -237,6 +237,23 @@ class Ref:
             raise ValueError("SoA width of the arrays is %d, the reference's generator uses %d on this host" % (soa, used.value))
         return used.value
 
+    def csr_soa_bench(self, rowptr, colidx, values, B, C, N, beta=0.0, threads=0, reps=1):
+        """the reference's SoA kernel over all elements with OpenMP, timed; returns seconds per repetition."""
+        values = np.ascontiguousarray(values)
+        dbl = 1 if values.dtype == np.float64 else 0
+        E, K, ldb, soa = B.shape
+        M, ldc = C.shape[1], C.shape[2]
+        rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
+        times = np.zeros(reps, np.float64)
+        f = self.lib.refdrv_csr_soa_bench
+        f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double] + [ctypes.c_void_p] * 5 + [ctypes.c_long] * 3 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        rc = f(dbl, M, N, K, ldb, ldc, float(beta), _ptr(rowptr), _ptr(colidx), _ptr(values), _ptr(B), _ptr(C), E, K * ldb * soa, M * ldc * soa,
+               threads, reps, _ptr(times))
+        if rc != 0:
+            raise RuntimeError("reference csr_soa kernel could not be generated (rc=%d)" % rc)
+        return times
+
     def mm_rm(self, a, B, C, beta=1.0, nblock=16, lda=None):
         """libxsmm_[sd]mmdispatch applied to a row-major panel like samples/pyfr/pyfr_gemm_rm.c:98-122; in place on C."""
         a = np.ascontiguousarray(a)

@@ -66,3 +66,34 @@ int refdrv_mm_rm_run(int dbl, int M, int N, int K, int lda_op, int ld, double be
   }
   return 0;
 }
+
+/* the same kernel timed the way an element loop would run it on the host: OpenMP over elements, reps repetitions */
+#include <omp.h>
+int refdrv_csr_soa_bench(int dbl, int M, int N, int K, int ldb, int ldc, double beta,
+                         const unsigned int* rowptr, const unsigned int* colidx, const void* values,
+                         const void* B, void* C, long n_elem, long stride_b, long stride_c, int threads, int reps, double* times)
+{
+  libxsmm_descriptor_blob blob;
+  const int flags = LIBXSMM_GEMM_FLAGS('N', 'N');
+  const libxsmm_gemm_descriptor* d;
+  libxsmm_xmmfunction kern;
+  int r; long e;
+  libxsmm_init();
+  if (threads <= 0) threads = omp_get_max_threads();
+  d = dbl ? libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F64, M, N, K, 0, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE)
+          : libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F32, M, N, K, 0, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
+  if (0 == d) return -1;
+  kern = libxsmm_create_xcsr_soa(d, rowptr, colidx, values);
+  if (0 == kern.dmm) return -1;
+  for (r = 0; r < reps; ++r) {
+    const double t0 = omp_get_wtime();
+#   pragma omp parallel for num_threads(threads) schedule(static)
+    for (e = 0; e < n_elem; ++e) {
+      if (dbl) kern.dmm((const double*)values, (const double*)B + e * stride_b, (double*)C + e * stride_c);
+      else kern.smm((const float*)values, (const float*)B + e * stride_b, (float*)C + e * stride_c);
+    }
+    if (times) times[r] = omp_get_wtime() - t0;
+  }
+  libxsmm_release_kernel((const void*)kern.dmm);
+  return 0;
+}
