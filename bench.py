@@ -72,6 +72,8 @@ WORKLOADS = {
 # element ([35][9][8] doubles = 20 KB per tensor), 2^16 mesh elements per step
 WORKLOADS["soa"] = dict(kind="soa", case="tet4_4_stiffV_0_d", dtype="f64", elements=1 << 16, beta=1.0,
                         desc="dcsr_soa EDGE tet4 order 4 stiffV_0 (35x35, 108 nnz) x [35][9][8] tensors, 65536 elements, beta=1")
+WORKLOADS["soa-b"] = dict(kind="soa", case="bsp_tet4_4_stiffV_0_d", sparse="B", dtype="f64", elements=1 << 16, beta=1.0,
+                          desc="dcsr_soa, B sparse: [9][35][8] tensors x EDGE tet4 order 4 stiffV_0 (35x35, 108 nnz), 65536 elements, beta=1")
 FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4: 148 SMs x 128 FMA lanes at the 1965 MHz the CUDA-core kernels run at (nominal; no measured figure in MEASURED_PEAKS.json)
 L2_BYTES = 126 << 20
 
@@ -223,8 +225,9 @@ def run_soa_gpu(xs, wl, steps, warmup):
     rp, ci, va = d[key + "_rowptr"], d[key + "_colidx"], d[key + "_values"]
     E = wl["elements"]
     esz = va.dtype.itemsize
-    bB, bC = E * K * N * soa * esz, E * M * N * soa * esz
-    op = xs.CsrSoa(M, N, K, rp, ci, va, soa, beta=wl["beta"])
+    bsp = wl.get("sparse", "A") == "B"
+    bB, bC = E * (M * K if bsp else K * N) * soa * esz, E * M * N * soa * esz
+    op = xs.CsrSoa(M, N, K, rp, ci, va, soa, beta=wl["beta"], sparse="B" if bsp else "A")
     nsets = max(1, int(np.ceil(2.5 * L2_BYTES / (bB + bC))))
     ring = []
     for s_ in range(nsets):
@@ -247,10 +250,18 @@ def run_soa_gpu(xs, wl, steps, warmup):
     total_ms = t0.elapsed_ms(t1)
     xs.check()
     nnz = len(va)
-    rows_touched = int(np.count_nonzero(np.diff(rp)))       # rows without nonzeros are neither read nor written,
-    cols_used = int(len(np.unique(ci)))                      # B rows no nonzero refers to are never read
-    bytes_ = esz * E * N * soa * (cols_used + rows_touched * (2 if float(wl["beta"]) != 0.0 else 1))
-    yield dict(total_ms=total_ms, launches=xs.launch_count() - l0, nnz=nnz, flops=2.0 * nnz * N * soa * E, geo=dict(baked=op.is_baked, M=M, K=K, N=N, soa=soa, elements=E),
+    if bsp:      # A [M][K][soa]: the rows k with nonzeros in B are read.  beta = 0: columns 0 .. ncols-1 of C are written (ncols =
+        k_used = int(np.count_nonzero(np.diff(rp)))       # 1 + the largest column index of B); beta = 1: a column without nonzeros
+        ncols = int(ci.max()) + 1 if len(ci) else 0       # keeps its content, so only the columns WITH nonzeros are read and written
+        c_cols = 2 * int(len(np.unique(ci[ci < N]))) if float(wl["beta"]) != 0.0 else ncols
+        bytes_ = esz * E * M * soa * (k_used + c_cols)
+        flops = 2.0 * nnz * M * soa * E
+    else:
+        rows_touched = int(np.count_nonzero(np.diff(rp)))       # rows without nonzeros are neither read nor written,
+        cols_used = int(len(np.unique(ci)))                      # B rows no nonzero refers to are never read
+        bytes_ = esz * E * N * soa * (cols_used + rows_touched * (2 if float(wl["beta"]) != 0.0 else 1))
+        flops = 2.0 * nnz * N * soa * E
+    yield dict(total_ms=total_ms, launches=xs.launch_count() - l0, nnz=nnz, flops=flops, geo=dict(baked=op.is_baked, M=M, K=K, N=N, soa=soa, elements=E, sparse_operand="B" if bsp else "A"),
                kernel_ms=total_ms / steps, kernel_bytes=bytes_, kernel_name=xs.last_compute_kernel(), parts={}, step_bytes=bytes_, ring_sets=nsets, ring_bytes=nsets * (bB + bC))
     for bufs in ring:
         for b in bufs:
@@ -460,12 +471,14 @@ def cpu_reference(wl, budget_s, reps_min=1, reps_max=50):
             raise RuntimeError("host without AVX-512: the reference's SoA width differs from the workload's")
         E = min(wl["elements"], 1 << 14)                      # bounded sample: 2^14 elements (~0.65 GB of tensors)
         rng = np.random.default_rng(3)
-        B = rng.random((E, K, N, soa)).astype(va.dtype); C = np.zeros((E, M, N, soa), va.dtype)
-        tm = ref.csr_soa_bench(rp, ci, va, B, C, N, wl["beta"], threads=cores, reps=1)
+        bsp = wl.get("sparse", "A") == "B"
+        B = rng.random((E, M, K, soa) if bsp else (E, K, N, soa)).astype(va.dtype); C = np.zeros((E, M, N, soa), va.dtype)
+        timed = ref.csr_soa_bsparse_bench if bsp else ref.csr_soa_bench
+        tm = timed(rp, ci, va, B, C, N, wl["beta"], threads=cores, reps=1)
         reps = int(min(reps_max, max(reps_min, budget_s / max(tm[0], 1e-4))))
-        tm = ref.csr_soa_bench(rp, ci, va, B, C, N, wl["beta"], threads=cores, reps=reps)
+        tm = timed(rp, ci, va, B, C, N, wl["beta"], threads=cores, reps=reps)
         ms = float(np.median(tm)) * 1e3
-        return dict(value=2.0 * len(va) * N * soa * E / ms / 1e6, ms=ms, best_ms=float(tm.min()) * 1e3, cores=cores, kind="reference",
+        return dict(value=2.0 * len(va) * (M if bsp else N) * soa * E / ms / 1e6, ms=ms, best_ms=float(tm.min()) * 1e3, cores=cores, kind="reference",
                     sample="2^14 of the workload's elements, %d reps, median; libxsmm_create_xcsr_soa kernel, OpenMP over elements" % reps)
     if wl["kind"] == "spmdm":
         t = wl["trans"]
@@ -530,7 +543,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--others", default="c1,c4,c4-tnt,c4-ntn,c3-b1,c3-hex,c3-tet,soa", help="extra workloads reported inside the line (N=1 only); '' = none")
+    ap.add_argument("--others", default="c1,c4,c4-tnt,c4-ntn,c3-b1,c3-hex,c3-tet,soa,soa-b", help="extra workloads reported inside the line (N=1 only); '' = none")
     ap.add_argument("--sharded", default="c3,c5", help="column-sharded fsspmdm configs reported in `column_sharded` at every N (strong scaling); '' = none")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of reference CPU time for the headline cpu_baseline (a quarter of it per secondary workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -120,25 +120,33 @@ LIBXSMM_API void libxsmm_b200_csr_free(unsigned int* row_ptr, unsigned int* col_
 LIBXSMM_API libxsmm_dfsspmdm* libxsmm_b200_dfsspmdm_create_mtx(const char* path, int N, int ldb, int ldc, double beta, int* M, int* K);
 LIBXSMM_API libxsmm_sfsspmdm* libxsmm_b200_sfsspmdm_create_mtx(const char* path, int N, int ldb, int ldc, float beta, int* M, int* K);
 
-/* CSR "A sparse" x dense SoA kernels: the GPU counterpart of
- *     kernel = libxsmm_create_xcsr_soa(descriptor(m, n, k, lda = 0, ldb, ldc, alpha = 1, beta), row_ptr, column_idx, values)
- *     kernel(values, B, C)                                   once per mesh element
- * (reference src/template/libxsmm.h:283-293, src/libxsmm_main.c:2423-2447, src/generator_spgemm_csr_asparse_soa.c; caller
- * samples/edge/asparse_srsoa.c:148-160).  B is [k][ldb][soa_width], C is [m][ldc][soa_width] per element;
- *     C[m][n][s] = (beta == 0 ? 0 : C[m][n][s]) + sum over row m's nonzeros z, in CSR order, of values[z] * B[column_idx[z]][n][s]
- * with one fused multiply-add per nonzero (beta is 0 or 1, as for the reference's descriptor); rows WITHOUT nonzeros are
- * left untouched, like the reference's emitted code.
- * soa_width is a property of the caller's tensors (the reference's generator fixes it per host: 8 doubles / 16 floats with
- * AVX-512, 4 / 8 otherwise).  One element is far too small for a launch, so execute is BATCHED: n_elements elements, element
- * e at d_B + e * stride_b and d_C + e * stride_c (strides in scalars), asynchronous on `stream`.  The operator's values are
- * fixed at create (the reference's kernel re-reads them at every call from its first argument; callers pass the same array). */
+/* CSR x dense SoA kernels: the GPU counterpart of
+ *     kernel = libxsmm_create_xcsr_soa(descriptor(m, n, k, lda, ldb, ldc, alpha = 1, beta), row_ptr, column_idx, values)
+ *     kernel(a, b, c)                                        once per mesh element
+ * (reference src/template/libxsmm.h:283-293, src/libxsmm_main.c:2423-2447, src/generator_spgemm_csr_asparse_soa.c,
+ * src/generator_spgemm_csr_bsparse_soa.c; callers samples/edge/asparse_srsoa.c:148-160, samples/edge/bsparse_srsoa.c:160-176).
+ * As in the reference's descriptor exactly one of lda / ldb is 0 and names the SPARSE operand (CSR):
+ *   lda == 0  A sparse (CSR over its m rows), B dense [k][ldb][soa_width], C [m][ldc][soa_width]:
+ *             C[m][n][s] = (beta == 0 ? 0 : C[m][n][s]) + sum over row m's nonzeros z, in CSR order, of values[z] * B[column_idx[z]][n][s];
+ *             rows of A WITHOUT nonzeros leave their C rows untouched, like the reference's emitted code;
+ *   ldb == 0  B sparse (CSR over its k rows), A dense [m][lda][soa_width], C [m][ldc][soa_width]:
+ *             C[m][n][s] = (beta == 0 ? 0 : C[m][n][s]) + sum over k ascending, over row k's nonzeros (k, n), of A[m][k][s] * values[z];
+ *             columns 0 .. ncols-1 of C are written, ncols = 1 + the largest column index any nonzero of B holds (an empty
+ *             column below ncols gives beta * C; columns from ncols on are never touched, not even for beta = 0 -- the
+ *             reference's generator, generator_spgemm_csr_bsparse_soa.c:161-167); nonzeros with column >= n are not
+ *             multiplied; ncols > ldc is rejected.
+ * One fused multiply-add per nonzero; beta is 0 or 1, as for the reference's descriptor.  soa_width is a property of the caller's
+ * tensors (the reference's generator fixes it per host: 8 doubles / 16 floats with AVX-512, 4 / 8 otherwise).  One element is far
+ * too small for a launch, so execute is BATCHED: n_elements elements, the dense operand of element e at d_X + e * stride_x and its
+ * C at d_C + e * stride_c (strides in scalars), asynchronous on `stream`.  The sparse operand's values are fixed at create (the
+ * reference's kernel re-reads them at every call; its callers pass the same array). */
 typedef struct libxsmm_b200_csr_soa libxsmm_b200_csr_soa;
-LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_dcsr_soa_create(int M, int N, int K, int ldb, int ldc, int soa_width, double beta,
+LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_dcsr_soa_create(int M, int N, int K, int lda, int ldb, int ldc, int soa_width, double beta,
   const unsigned int* row_ptr, const unsigned int* column_idx, const double* values);
-LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_scsr_soa_create(int M, int N, int K, int ldb, int ldc, int soa_width, float beta,
+LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_scsr_soa_create(int M, int N, int K, int lda, int ldb, int ldc, int soa_width, float beta,
   const unsigned int* row_ptr, const unsigned int* column_idx, const float* values);
-LIBXSMM_API void libxsmm_b200_csr_soa_execute(const libxsmm_b200_csr_soa* handle, const void* d_B, void* d_C, long long n_elements,
-  long long stride_b, long long stride_c, void* stream);
+LIBXSMM_API void libxsmm_b200_csr_soa_execute(const libxsmm_b200_csr_soa* handle, const void* d_X, void* d_C, long long n_elements,
+  long long stride_x, long long stride_c, void* stream);
 LIBXSMM_API int libxsmm_b200_csr_soa_is_baked(const libxsmm_b200_csr_soa* handle);
 LIBXSMM_API void libxsmm_b200_csr_soa_destroy(libxsmm_b200_csr_soa* handle);
 

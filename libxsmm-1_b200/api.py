@@ -665,23 +665,25 @@ class MmDispatch:
 
 
 class CsrSoa:
-    """CSR operator applied to [element][row][column][soa] tensors (libxsmm_b200_[sd]csr_soa_*; the batched GPU counterpart of
-    libxsmm_create_xcsr_soa, reference samples/edge/asparse_srsoa.c:148-160)."""
+    """CSR operand applied to [element][row][column][soa] tensors (libxsmm_b200_[sd]csr_soa_*; the batched GPU counterpart of
+    libxsmm_create_xcsr_soa).  sparse="A": reference samples/edge/asparse_srsoa.c (the CSR matrix is M x K, the dense operand
+    B is [K][ldb][soa]); sparse="B": samples/edge/bsparse_srsoa.c (the CSR matrix is K x N, the dense operand A is [M][lda][soa])."""
 
-    def __init__(self, M, N, K, rowptr, colidx, values, soa_width, ldb=None, ldc=None, beta=0.0):
+    def __init__(self, M, N, K, rowptr, colidx, values, soa_width, lda=None, ldb=None, ldc=None, beta=0.0, sparse="A"):
         require_gpu()
         L = load()
         values = np.ascontiguousarray(values)
-        assert values.dtype in (np.float64, np.float32)
+        assert values.dtype in (np.float64, np.float32) and sparse in ("A", "B")
         self.double = values.dtype == np.float64
         rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
         f = L.libxsmm_b200_dcsr_soa_create if self.double else L.libxsmm_b200_scsr_soa_create
         f.restype = ctypes.c_void_p
-        f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double if self.double else ctypes.c_float] + [ctypes.c_void_p] * 3
-        self.M, self.N, self.K, self.soa = M, N, K, soa_width
-        self.ldb = N if ldb is None else ldb
+        f.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double if self.double else ctypes.c_float] + [ctypes.c_void_p] * 3
+        self.M, self.N, self.K, self.soa, self.sparse = M, N, K, soa_width, sparse
+        self.lda = 0 if sparse == "A" else (K if lda is None else lda)
+        self.ldb = 0 if sparse == "B" else (N if ldb is None else ldb)
         self.ldc = N if ldc is None else ldc
-        self.handle = f(M, N, K, self.ldb, self.ldc, soa_width, float(beta), rowptr.ctypes.data, colidx.ctypes.data, values.ctypes.data)
+        self.handle = f(M, N, K, self.lda, self.ldb, self.ldc, soa_width, float(beta), rowptr.ctypes.data, colidx.ctypes.data, values.ctypes.data)
         if not self.handle:
             code, msg = last_error()
             clear_error()
@@ -692,13 +694,14 @@ class CsrSoa:
     def is_baked(self):
         return bool(load().libxsmm_b200_csr_soa_is_baked(ctypes.c_void_p(self.handle)))
 
-    def execute(self, d_B, d_C, n_elements, stride_b=None, stride_c=None, stream=None):
+    def execute(self, d_X, d_C, n_elements, stride_x=None, stride_c=None, stream=None):
         L = load()
         L.libxsmm_b200_csr_soa_execute.restype = None
         L.libxsmm_b200_csr_soa_execute.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]
-        sb = self.K * self.ldb * self.soa if stride_b is None else stride_b
+        dense = self.K * self.ldb if self.sparse == "A" else self.M * self.lda
+        sx = dense * self.soa if stride_x is None else stride_x
         sc = self.M * self.ldc * self.soa if stride_c is None else stride_c
-        L.libxsmm_b200_csr_soa_execute(self.handle, _addr(d_B), _addr(d_C), n_elements, sb, sc, _sptr(stream))
+        L.libxsmm_b200_csr_soa_execute(self.handle, _addr(d_X), _addr(d_C), n_elements, sx, sc, _sptr(stream))
 
     def destroy(self):
         if self.handle:

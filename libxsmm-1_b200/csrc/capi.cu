@@ -827,15 +827,17 @@ int libxsmm_sfsspmdm_is_tensor_core(const libxsmm_sfsspmdm* handle) { return fs_
 // ---- CSR "A sparse" x dense SoA kernels -------------------------------------------------------
 // GPU counterpart of libxsmm_create_xcsr_soa + kernel(values, B, C) (reference src/libxsmm_main.c:2423-2447,
 // src/generator_spgemm_csr_asparse_soa.c; caller samples/edge/asparse_srsoa.c:148-160), batched over mesh elements because
-// one element's [m][n][soa] tensor is far too small for a launch.  The operator's values are fixed at create (the
-// reference's kernel re-reads them from its first argument at every call; its callers pass the same array).
+// one element's [m][n][soa] tensor is far too small for a launch.  Like the reference's descriptor, lda == 0 means A is the
+// sparse operand (samples/edge/asparse_srsoa.c) and ldb == 0 means B is (samples/edge/bsparse_srsoa.c); the other operand
+// and C are dense SoA tensors.  The operator's values are fixed at create (the reference's kernel re-reads them from its
+// argument at every call; its callers pass the same array).
 struct libxsmm_b200_csr_soa;
-libxsmm_b200_csr_soa* libxsmm_b200_dcsr_soa_create(int M, int N, int K, int ldb, int ldc, int soa_width, double beta,
+libxsmm_b200_csr_soa* libxsmm_b200_dcsr_soa_create(int M, int N, int K, int lda, int ldb, int ldc, int soa_width, double beta,
   const unsigned int* row_ptr, const unsigned int* column_idx, const double* values)
-{ return (libxsmm_b200_csr_soa*)fs_create_csr(1, M, N, K, ldb, ldc, soa_width, beta, row_ptr, column_idx, values); }
-libxsmm_b200_csr_soa* libxsmm_b200_scsr_soa_create(int M, int N, int K, int ldb, int ldc, int soa_width, float beta,
+{ return (libxsmm_b200_csr_soa*)fs_create_csr(1, M, N, K, lda, ldb, ldc, soa_width, beta, row_ptr, column_idx, values); }
+libxsmm_b200_csr_soa* libxsmm_b200_scsr_soa_create(int M, int N, int K, int lda, int ldb, int ldc, int soa_width, float beta,
   const unsigned int* row_ptr, const unsigned int* column_idx, const float* values)
-{ return (libxsmm_b200_csr_soa*)fs_create_csr(0, M, N, K, ldb, ldc, soa_width, (double)beta, row_ptr, column_idx, values); }
+{ return (libxsmm_b200_csr_soa*)fs_create_csr(0, M, N, K, lda, ldb, ldc, soa_width, (double)beta, row_ptr, column_idx, values); }
 void libxsmm_b200_csr_soa_execute(const libxsmm_b200_csr_soa* handle, const void* d_B, void* d_C, long long n_elements,
   long long stride_b, long long stride_c, void* stream)
 {

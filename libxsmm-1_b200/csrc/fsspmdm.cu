@@ -37,6 +37,8 @@ struct FsOperator {
   std::vector<double> val;
   FsJit* jit;
   FsTc* tc;            // tensor-core kernel for dense float operators (fsspmdm_tc.cu), or NULL
+  // CSR x SoA (fs_create_csr): the batched apply sees every element as `items` items of `item_cols` columns
+  long long items, item_cols, item_b, item_c;
 };
 
 // ---- branch rule of the reference ------------------------------------------------------------------
@@ -72,7 +74,8 @@ static long long fs_x86_code_size(const FsOperator& o)
 struct FsDev {
   int M, beta_one, skip_empty;
   long long ldb, ldc;
-  long long J, sb, sc;   // batched form (CSR x SoA): columns per element and element strides; J = 0: plain column panel
+  long long J, sb, sc;   // batched form (CSR x SoA): columns per item and element strides; J = 0: plain column panel
+  long long ipe, ib, ic; // items per element and item strides
   const int* rowptr;
   const int* col;
   const void* val;
@@ -85,7 +88,10 @@ __global__ void __launch_bounds__(256) fs_generic_kernel(const FsDev p, const T*
   if (n >= ncols) return;
   const T* __restrict__ val = (const T*)p.val;
   long long nb = n, nc = n;
-  if (p.J > 0) { const long long e = n / p.J, j = n - e * p.J; nb = e * p.sb + j; nc = e * p.sc + j; }   // (element, column) form: VEC == 1
+  if (p.J > 0) {   // (element, item, column) form: VEC == 1
+    const long long item = n / p.J, j = n - item * p.J, e = item / p.ipe, i = item - e * p.ipe;
+    nb = e * p.sb + i * p.ib + j; nc = e * p.sc + i * p.ic + j;
+  }
   const T* Bn = B + nb;
   for (int m = 0; m < p.M; ++m) {
     const int lo = __ldg(p.rowptr + m), hi = __ldg(p.rowptr + m + 1);
@@ -237,7 +243,7 @@ void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, 
   FsDev d;
   d.M = o->M; d.beta_one = o->beta_one; d.skip_empty = o->sparse_branch;
   d.ldb = ldb; d.ldc = ldc; d.rowptr = o->d_rowptr; d.col = o->d_col; d.val = o->d_val;
-  d.J = 0; d.sb = 0; d.sc = 0;
+  d.J = 0; d.sb = 0; d.sc = 0; d.ipe = 1; d.ib = 0; d.ic = 0;
   const int threads = 256;
   if (o->is_double) {
     const bool v2 = (0 == (ldb & 1)) && (0 == (ldc & 1)) && (0 == (((uintptr_t)dB | (uintptr_t)dC) & 15));
@@ -270,60 +276,90 @@ void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, 
 // 213-420): per row with nonzeros an in-order chain of fused multiply-adds from C (beta != 0) or from zero; rows without
 // nonzeros are skipped.  With the SoA lanes as innermost columns this IS the fixed-operator apply over N * soa columns
 // with row pitches ldb * soa / ldc * soa, so it reuses the baked kernel (batched over mesh elements).
-FsOperator* fs_create_csr(int is_double, int M, int N, int K, int ldb, int ldc, int soa, double beta,
+FsOperator* fs_create_csr(int is_double, int M, int N, int K, int lda, int ldb, int ldc, int soa, double beta,
                           const unsigned int* rowptr, const unsigned int* colidx, const void* values)
 {
-  if (M <= 0 || N <= 0 || K <= 0 || soa <= 0 || ldb < N || ldc < N || 0 == rowptr || 0 == colidx || 0 == values
+  // like the reference's descriptor: lda == 0 <=> A is the sparse operand (CSR over its M rows), ldb == 0 <=> B is (CSR over its K rows)
+  const bool a_sparse = (0 == lda && ldb > 0), b_sparse = (lda > 0 && 0 == ldb);
+  if (M <= 0 || N <= 0 || K <= 0 || soa <= 0 || !(a_sparse || b_sparse) || ldc < N || (a_sparse && ldb < N) || (b_sparse && lda < K)
+      || 0 == rowptr || 0 == colidx || 0 == values
       || !(0.0 == beta || 1.0 == beta)) {   // the reference's descriptor (libxsmm_gemm_descriptor_dinit) exists for beta 0 and 1 only
-    set_error(-60, "csr_soa_create: bad argument (M=%d N=%d K=%d ldb=%d ldc=%d soa=%d)", M, N, K, ldb, ldc, soa);
+    set_error(-60, "csr_soa_create: bad argument (M=%d N=%d K=%d lda=%d ldb=%d ldc=%d soa=%d beta=%g; exactly one of lda / ldb is 0)", M, N, K, lda, ldb, ldc, soa, beta);
     return 0;
   }
-  for (int m = 0; m < M; ++m) if (rowptr[m + 1] < rowptr[m]) { set_error(-61, "csr_soa_create: row pointers not monotone"); return 0; }
-  for (unsigned int z = rowptr[0]; z < rowptr[M]; ++z) if (colidx[z] >= (unsigned int)K) { set_error(-62, "csr_soa_create: column index out of range"); return 0; }
+  const int srows = a_sparse ? M : K, scols = a_sparse ? K : N;       // shape of the sparse operand
+  for (int r = 0; r < srows; ++r) if (rowptr[r + 1] < rowptr[r]) { set_error(-61, "csr_soa_create: row pointers not monotone"); return 0; }
+  for (unsigned int z = rowptr[0]; z < rowptr[srows]; ++z) if (a_sparse && colidx[z] >= (unsigned int)scols) { set_error(-62, "csr_soa_create: column index out of range"); return 0; }
   FsOperator* o = new FsOperator();
-  o->M = M; o->N = N * soa; o->K = K; o->ldb = ldb * soa; o->ldc = ldc * soa;
   o->a_dense = 0; o->kernel = 0; o->jit = 0; o->tc = 0;
   o->is_double = is_double; o->beta_one = (0.0 != beta);
   o->d_rowptr = 0; o->d_col = 0; o->d_val = 0;
-  o->sparse_branch = 1;                                          // rows without nonzeros are skipped
   o->n_unique = 0; o->x86_code_size = 0; o->N_chunksize = soa;
-  o->rowptr.assign(M + 1, 0);
-  for (int m = 0; m <= M; ++m) o->rowptr[m] = (int)(rowptr[m] - rowptr[0]);
-  o->nnz = o->rowptr[M];
-  o->col.resize((size_t)o->nnz); o->val.resize((size_t)o->nnz);
-  for (int z = 0; z < o->nnz; ++z) {
-    o->col[z] = (int)colidx[rowptr[0] + z];
-    o->val[z] = is_double ? ((const double*)values)[rowptr[0] + z] : (double)((const float*)values)[rowptr[0] + z];
+  auto value_at = [&](unsigned int z) -> double { return is_double ? ((const double*)values)[z] : (double)((const float*)values)[z]; };
+  if (a_sparse) {
+    // C[m][(n, s)] = sum_z a[z] B[col z][(n, s)]: the operator is A itself, an item is a whole element with N * soa columns
+    o->M = M; o->K = K; o->N = N * soa; o->ldb = ldb * soa; o->ldc = ldc * soa;
+    o->items = 1; o->item_cols = (long long)N * soa; o->item_b = 0; o->item_c = 0;
+    o->sparse_branch = 1;                                          // rows without nonzeros are skipped (generator_spgemm_csr_asparse_soa.c:249)
+    o->rowptr.assign(M + 1, 0);
+    for (int m = 0; m <= M; ++m) o->rowptr[m] = (int)(rowptr[m] - rowptr[0]);
+    o->nnz = o->rowptr[M];
+    o->col.resize((size_t)o->nnz); o->val.resize((size_t)o->nnz);
+    for (int z = 0; z < o->nnz; ++z) { o->col[z] = (int)colidx[rowptr[0] + z]; o->val[z] = value_at(rowptr[0] + z); }
+  }
+  else {
+    // C[m][n][s] = sum_k A[m][k][s] b[k][n]: for one m this is the operator B^T applied to the item A[m] = [k][soa]; an
+    // element has M items of soa columns, lda * soa / ldc * soa apart.  Row n of B^T holds column n of B in ascending k, the
+    // order of the reference's k loop (generator_spgemm_csr_bsparse_soa.c:208-292).  The reference works on columns
+    // 0 .. ncols-1 only, ncols = 1 + the largest column index of any nonzero (:161-167): empty columns below ncols are
+    // written, columns from ncols on are never touched -- so B^T gets ncols rows, not N.  Nonzeros with column >= N count
+    // towards ncols but are not multiplied (:213,233).
+    int ncols = 0;
+    for (unsigned int z = rowptr[0]; z < rowptr[K]; ++z) if (colidx[z] >= (unsigned int)ncols) ncols = (int)colidx[z] + 1;
+    if (ncols > ldc) { set_error(-62, "csr_soa_create: column index %d of B reaches past ldc=%d", ncols - 1, ldc); fs_destroy(o); return 0; }
+    o->M = ncols; o->K = K; o->N = soa; o->ldb = soa; o->ldc = soa;
+    o->items = M; o->item_cols = soa; o->item_b = (long long)lda * soa; o->item_c = (long long)ldc * soa;
+    o->sparse_branch = 0;
+    std::vector<int> cnt((size_t)ncols + 1, 0);
+    for (unsigned int z = rowptr[0]; z < rowptr[K]; ++z) if (colidx[z] < (unsigned int)N) ++cnt[colidx[z] + 1];
+    o->rowptr.assign((size_t)ncols + 1, 0);
+    for (int n = 0; n < ncols; ++n) o->rowptr[n + 1] = o->rowptr[n] + cnt[n + 1];
+    o->nnz = o->rowptr[ncols];
+    o->col.resize((size_t)o->nnz); o->val.resize((size_t)o->nnz);
+    std::vector<int> fill(o->rowptr.begin(), o->rowptr.end() - 1);
+    for (int k = 0; k < K; ++k) for (unsigned int z = rowptr[k]; z < rowptr[k + 1]; ++z) if (colidx[z] < (unsigned int)N) {
+      const int d = fill[colidx[z]]++;
+      o->col[d] = k; o->val[d] = value_at(z);
+    }
   }
   const size_t nalloc = (size_t)(o->nnz > 0 ? o->nnz : 1);
-  XB_CUDA(cudaMalloc(&o->d_rowptr, sizeof(int) * (M + 1)));
+  XB_CUDA(cudaMalloc(&o->d_rowptr, sizeof(int) * (o->M + 1)));
   XB_CUDA(cudaMalloc(&o->d_col, sizeof(int) * nalloc));
   XB_CUDA(cudaMalloc(&o->d_val, 8 * nalloc));
   if (0 == o->d_rowptr || 0 == o->d_col || 0 == o->d_val) { fs_destroy(o); return 0; }
-  XB_CUDA(cudaMemcpy(o->d_rowptr, o->rowptr.data(), sizeof(int) * (M + 1), cudaMemcpyHostToDevice));
+  XB_CUDA(cudaMemcpy(o->d_rowptr, o->rowptr.data(), sizeof(int) * (o->M + 1), cudaMemcpyHostToDevice));
   if (o->nnz > 0) {
     XB_CUDA(cudaMemcpy(o->d_col, o->col.data(), sizeof(int) * (size_t)o->nnz, cudaMemcpyHostToDevice));
     if (is_double) XB_CUDA(cudaMemcpy(o->d_val, o->val.data(), 8 * (size_t)o->nnz, cudaMemcpyHostToDevice));
     else { std::vector<float> vf(o->val.begin(), o->val.end()); XB_CUDA(cudaMemcpy(o->d_val, vf.data(), 4 * (size_t)o->nnz, cudaMemcpyHostToDevice)); }
   }
-  o->jit = fs_jit_build(is_double, 0, M, K, o->beta_one, 1, o->rowptr.data(), o->col.data(), o->val.data(), 1 /*batched*/);
+  if (o->M > 0) o->jit = fs_jit_build(is_double, 0, o->M, o->K, o->beta_one, o->sparse_branch, o->rowptr.data(), o->col.data(), o->val.data(), 1 /*batched*/);
   o->kernel = o->jit;
   return o;
 }
 
 void fs_execute_batched(const FsOperator* o, const void* dB, void* dC, long long n_elem, long long stride_b, long long stride_c, cudaStream_t stream)
 {
-  if (0 == o || n_elem <= 0) return;
+  if (0 == o || n_elem <= 0 || o->M <= 0) return;   // B sparse without a single nonzero: the reference's kernel touches nothing
   count_launch(1);
-  const long long J = o->N;
-  if (o->jit && fs_jit_launch_batched(o->jit, dB, dC, n_elem, J, o->ldb, o->ldc, stride_b, stride_c, stream)) { note_compute_kernel("fs_baked (batched)"); return; }
+  if (o->jit && fs_jit_launch_batched(o->jit, dB, dC, n_elem, o->items, o->item_cols, o->ldb, o->ldc, stride_b, stride_c, o->item_b, o->item_c, stream)) { note_compute_kernel("fs_baked (batched)"); return; }
   note_compute_kernel("fs_generic_kernel (batched)");
   FsDev d;
-  d.M = o->M; d.beta_one = o->beta_one; d.skip_empty = 1;
+  d.M = o->M; d.beta_one = o->beta_one; d.skip_empty = o->sparse_branch;
   d.ldb = o->ldb; d.ldc = o->ldc; d.rowptr = o->d_rowptr; d.col = o->d_col; d.val = o->d_val;
-  d.J = J; d.sb = stride_b; d.sc = stride_c;
+  d.J = o->item_cols; d.sb = stride_b; d.sc = stride_c; d.ipe = o->items; d.ib = o->item_b; d.ic = o->item_c;
   const int threads = 256;
-  const long long total = n_elem * J, blocks = (total + threads - 1) / threads;
+  const long long total = n_elem * o->items * o->item_cols, blocks = (total + threads - 1) / threads;
   if (o->is_double) fs_generic_kernel<double, 1><<<(unsigned)blocks, threads, 0, stream>>>(d, (const double*)dB, (double*)dC, total);
   else fs_generic_kernel<float, 1><<<(unsigned)blocks, threads, 0, stream>>>(d, (const float*)dB, (float*)dC, total);
   XB_CUDA(cudaGetLastError());

@@ -189,21 +189,24 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
   std::string s;
   s.reserve(96 * (size_t)rowptr[M] * cpt + 8192);
   s += ".version 8.6\n.target sm_100a\n.address_size 64\n\n";
-  if (batched) s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC, .param .u64 pJ, .param .u64 pSB, .param .u64 pSC)\n";
+  if (batched) s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC, .param .u64 pJ, .param .u64 pSB, .param .u64 pSC, .param .u64 pIPE, .param .u64 pIB, .param .u64 pIC)\n";
   else s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC)\n";
   append(s, ".maxntid %d, 1, 1\n", kBlock);
   s += "{\n";
-  s += "  .reg .pred %p, %pf;\n  .reg .b32 %r<4>;\n  .reg .b64 %rd<20>;\n";
+  s += "  .reg .pred %p, %pf;\n  .reg .b32 %r<4>;\n  .reg .b64 %rd<28>;\n";
   append(s, "  .reg .%s %%bx<%d>, %%by<%d>, %%cx<%d>, %%cy<%d>, %%ax, %%ay;\n", ty, K, K, M, M);
   s += "  ld.param.u64 %rd0, [pB];\n  ld.param.u64 %rd1, [pC];\n  ld.param.u64 %rd2, [pN];\n  ld.param.u64 %rd3, [pLDB];\n  ld.param.u64 %rd4, [pLDC];\n";
   s += "  mov.u32 %r0, %ctaid.x;\n  mov.u32 %r1, %tid.x;\n";
   append(s, "  mul.wide.u32 %%rd5, %%r0, %d;\n  cvt.u64.u32 %%rd6, %%r1;\n  add.s64 %%rd5, %%rd5, %%rd6;\n", kBlock);
   if (2 == cpt) s += "  shl.b64 %rd5, %rd5, 1;\n";
   s += "  setp.ge.s64 %p, %rd5, %rd2;\n  @%p bra DONE;\n";
-  if (batched) {   // element e = n / J, column j = n % J: b = B + e * SB + j, c = C + e * SC + j
+  if (batched) {   // item = n / J, column j = n % J; element e = item / IPE, i = item % IPE: b = B + e * SB + i * IB + j, c likewise
     s += "  ld.param.u64 %rd12, [pJ];\n  ld.param.u64 %rd13, [pSB];\n  ld.param.u64 %rd14, [pSC];\n";
-    s += "  div.u64 %rd15, %rd5, %rd12;\n  mul.lo.s64 %rd16, %rd15, %rd12;\n  sub.s64 %rd16, %rd5, %rd16;\n";
-    s += "  mad.lo.s64 %rd17, %rd15, %rd13, %rd16;\n  mad.lo.s64 %rd18, %rd15, %rd14, %rd16;\n";
+    s += "  ld.param.u64 %rd20, [pIPE];\n  ld.param.u64 %rd21, [pIB];\n  ld.param.u64 %rd22, [pIC];\n";
+    s += "  div.u64 %rd15, %rd5, %rd12;\n  mul.lo.s64 %rd16, %rd15, %rd12;\n  sub.s64 %rd16, %rd5, %rd16;\n";      // rd15 = item, rd16 = j
+    s += "  div.u64 %rd23, %rd15, %rd20;\n  mul.lo.s64 %rd24, %rd23, %rd20;\n  sub.s64 %rd24, %rd15, %rd24;\n";    // rd23 = e, rd24 = i
+    s += "  mad.lo.s64 %rd17, %rd23, %rd13, %rd16;\n  mad.lo.s64 %rd17, %rd24, %rd21, %rd17;\n";
+    s += "  mad.lo.s64 %rd18, %rd23, %rd14, %rd16;\n  mad.lo.s64 %rd18, %rd24, %rd22, %rd18;\n";
     append(s, "  mad.lo.s64 %%rd0, %%rd17, %d, %%rd0;\n  mad.lo.s64 %%rd1, %%rd18, %d, %%rd1;\n", esz, esz);
   }
   else
@@ -548,13 +551,14 @@ bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, lo
   return true;
 }
 
-bool fs_jit_launch_batched(const FsJit* j, const void* dB, void* dC, long long n_elem, long long cols_per_elem, long long ldb, long long ldc,
-                           long long stride_b, long long stride_c, cudaStream_t stream)
+bool fs_jit_launch_batched(const FsJit* j, const void* dB, void* dC, long long n_elem, long long items_per_elem, long long cols_per_item, long long ldb, long long ldc,
+                           long long stride_b, long long stride_c, long long item_b, long long item_c, cudaStream_t stream)
 {
   if (!j->batched) return false;
-  long long total = n_elem * cols_per_elem;
+  long long total = n_elem * items_per_elem * cols_per_item;
   const long long blocks = (total + j->block - 1) / j->block;
-  void* args[] = { (void*)&dB, (void*)&dC, (void*)&total, (void*)&ldb, (void*)&ldc, (void*)&cols_per_elem, (void*)&stride_b, (void*)&stride_c };
+  void* args[] = { (void*)&dB, (void*)&dC, (void*)&total, (void*)&ldb, (void*)&ldc, (void*)&cols_per_item, (void*)&stride_b, (void*)&stride_c,
+                   (void*)&items_per_elem, (void*)&item_b, (void*)&item_c };
   const cudaError_t e = cudaLaunchKernel((const void*)j->kern, dim3((unsigned)blocks, 1, 1), dim3((unsigned)j->block, 1, 1), args, 0, stream);
   if (cudaSuccess != e) { set_error((int)e, "csr_soa: baked kernel launch failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return false; }
   return true;

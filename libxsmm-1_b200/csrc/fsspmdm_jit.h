@@ -10,9 +10,10 @@ struct FsJit;
 // generic kernel) or when NVRTC is not available (reported through set_error).
 FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int skip_empty_rows,
                     const int* rowptr, const int* col, const double* val, int batched = 0);
-// batched form: thread n -> element n / cols_per_elem, column n % cols_per_elem; B / C of an element start at element * stride
-bool fs_jit_launch_batched(const FsJit* j, const void* dB, void* dC, long long n_elem, long long cols_per_elem, long long ldb, long long ldc,
-                           long long stride_b, long long stride_c, cudaStream_t stream);
+// batched form: thread n -> item n / cols_per_item (element item / items_per_elem, item-in-element item % items_per_elem), column
+// n % cols_per_item; B / C of an item start at element * stride + item-in-element * item stride
+bool fs_jit_launch_batched(const FsJit* j, const void* dB, void* dC, long long n_elem, long long items_per_elem, long long cols_per_item, long long ldb, long long ldc,
+                           long long stride_b, long long stride_c, long long item_b, long long item_c, cudaStream_t stream);
 bool fs_jit_launch(const FsJit* j, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream);
 void fs_jit_destroy(FsJit* j);
 // 0: outside what can be baked (generic kernel), 1: B rows in registers, 2: B strip staged in shared memory by TMA

@@ -200,3 +200,37 @@ void orc_csr_soa_execute(int dbl, int M, int N, int K, int ldb, int ldc, int soa
     }
   }
 }
+
+/*
+ * The same entry with B sparse (descriptor lda > 0, ldb == 0; src/generator_spgemm_csr_bsparse_soa.c:60-250; caller
+ * samples/edge/bsparse_srsoa.c): A dense [m][lda][soa], B in CSR over its K rows, C [m][ldc][soa],
+ *     C[m][n][s] = (beta == 0 ? 0 : C[m][n][s]) + sum over k ascending, over the nonzeros (k, n) of B's row k, of A[m][k][s] * b.
+ * The emitted code works on columns 0 .. ncols-1 only, ncols = 1 + the LARGEST column index any nonzero of B holds
+ * (:161-167): it loads (or zeroes) all ncols accumulators chunk by chunk, walks k = 0 .. K-1 with one fused multiply-add
+ * per nonzero of row k, and stores all ncols accumulators (:187-205, :208-292, :295-305).  So a column WITHOUT nonzeros
+ * is written (zero for beta = 0) when a later column has one, and columns >= ncols are never touched, not even for
+ * beta = 0 (PyFR's tet4_5_stiffT_1 has 56 columns, the last 21 empty: C keeps its old content there).  Nonzeros with
+ * column >= N take no part in the multiply (:213,233) but still count towards ncols.
+ */
+void orc_csr_soa_bsparse_execute(int dbl, int M, int N, int K, int lda, int ldc, int soa, double beta,
+                                 const uint32_t* rowptr, const uint32_t* colidx, const void* values,
+                                 const void* A, void* C, long n_elem, long stride_a, long stride_c)
+{
+  long e; int m, n, s, k, ncols = 0; uint32_t z;
+  for (z = 0; z < rowptr[K]; ++z) if ((int)colidx[z] >= ncols) ncols = (int)colidx[z] + 1;
+  for (e = 0; e < n_elem; ++e) for (m = 0; m < M; ++m) for (n = 0; n < ncols; ++n) for (s = 0; s < soa; ++s) {
+    const size_t cat = (size_t)e * stride_c + ((size_t)m * ldc + n) * soa + s;
+    if (dbl) {
+      double acc = (0.0 == beta) ? 0.0 : ((double*)C)[cat];
+      for (k = 0; k < K; ++k) for (z = rowptr[k]; z < rowptr[k + 1]; ++z) if ((int)colidx[z] == n && n < N)
+        acc = fma(((const double*)A)[(size_t)e * stride_a + ((size_t)m * lda + k) * soa + s], ((const double*)values)[z], acc);
+      ((double*)C)[cat] = acc;
+    }
+    else {
+      float acc = (0.0 == beta) ? 0.f : ((float*)C)[cat];
+      for (k = 0; k < K; ++k) for (z = rowptr[k]; z < rowptr[k + 1]; ++z) if ((int)colidx[z] == n && n < N)
+        acc = fmaf(((const float*)A)[(size_t)e * stride_a + ((size_t)m * lda + k) * soa + s], ((const float*)values)[z], acc);
+      ((float*)C)[cat] = acc;
+    }
+  }
+}

@@ -189,6 +189,23 @@ class Oracle:
         return C
 
 
+    def csr_soa_bsparse_execute(self, rowptr, colidx, values, A, C, N, beta=0.0):
+        """B sparse (CSR over K rows): in place on C.  A: [E][M][lda][soa], C: [E][M][ldc][soa]."""
+        values = np.ascontiguousarray(values)
+        dbl = 1 if values.dtype == np.float64 else 0
+        assert A.dtype == values.dtype and C.dtype == values.dtype and A.flags.c_contiguous and C.flags.c_contiguous
+        if A.ndim == 3:
+            A = A[None]; C = C[None]
+        E, M, lda, soa = A.shape
+        K = len(rowptr) - 1
+        rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
+        f = self.lib.orc_csr_soa_bsparse_execute
+        f.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double] + [ctypes.c_void_p] * 5 + [ctypes.c_long] * 3
+        f.restype = None
+        f(dbl, M, N, K, lda, C.shape[2], soa, float(beta), _ptr(rowptr), _ptr(colidx), _ptr(values), _ptr(A), _ptr(C), E, M * lda * soa, M * C.shape[2] * soa)
+        return C
+
+
 class Ref:
     """The compiled reference.  ``Ref.available()`` is False where oracle/_ref is absent."""
 
@@ -237,6 +254,28 @@ class Ref:
             raise ValueError("SoA width of the arrays is %d, the reference's generator uses %d on this host" % (soa, used.value))
         return used.value
 
+    def csr_soa_bsparse(self, rowptr, colidx, values, A, C, N, beta=0.0):
+        """libxsmm_create_xcsr_soa with B sparse (descriptor lda > 0, ldb = 0): A [E][M][lda][soa] dense, in place on C [E][M][ldc][soa]."""
+        values = np.ascontiguousarray(values)
+        dbl = 1 if values.dtype == np.float64 else 0
+        assert A.dtype == values.dtype and C.dtype == values.dtype and A.flags.c_contiguous and C.flags.c_contiguous
+        if A.ndim == 3:
+            A = A[None]; C = C[None]
+        E, M, lda, soa = A.shape
+        K, ldc = len(rowptr) - 1, C.shape[2]
+        rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
+        used = ctypes.c_int(0)
+        f = self.lib.refdrv_csr_soa_run_ex
+        f.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double] + [ctypes.c_void_p] * 5 + [ctypes.c_long] * 3 + [ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        rc = f(dbl, M, N, K, lda, 0, ldc, float(beta), _ptr(rowptr), _ptr(colidx), _ptr(values), _ptr(A), _ptr(C), E, M * lda * soa, M * ldc * soa,
+               ctypes.cast(ctypes.byref(used), ctypes.c_void_p))
+        if rc != 0:
+            raise RuntimeError("reference csr_soa (B sparse) kernel could not be generated (rc=%d)" % rc)
+        if used.value != soa:
+            raise ValueError("SoA width of the arrays is %d, the reference's generator uses %d on this host" % (soa, used.value))
+        return used.value
+
     def csr_soa_bench(self, rowptr, colidx, values, B, C, N, beta=0.0, threads=0, reps=1):
         """the reference's SoA kernel over all elements with OpenMP, timed; returns seconds per repetition."""
         values = np.ascontiguousarray(values)
@@ -252,6 +291,23 @@ class Ref:
                threads, reps, _ptr(times))
         if rc != 0:
             raise RuntimeError("reference csr_soa kernel could not be generated (rc=%d)" % rc)
+        return times
+
+    def csr_soa_bsparse_bench(self, rowptr, colidx, values, A, C, N, beta=0.0, threads=0, reps=1):
+        """the reference's B-sparse SoA kernel over all elements with OpenMP, timed; returns seconds per repetition."""
+        values = np.ascontiguousarray(values)
+        dbl = 1 if values.dtype == np.float64 else 0
+        E, M, lda, soa = A.shape
+        K, ldc = len(rowptr) - 1, C.shape[2]
+        rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
+        times = np.zeros(reps, np.float64)
+        f = self.lib.refdrv_csr_soa_bench_ex
+        f.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double] + [ctypes.c_void_p] * 5 + [ctypes.c_long] * 3 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        rc = f(dbl, M, N, K, lda, 0, ldc, float(beta), _ptr(rowptr), _ptr(colidx), _ptr(values), _ptr(A), _ptr(C), E, M * lda * soa, M * ldc * soa,
+               threads, reps, _ptr(times))
+        if rc != 0:
+            raise RuntimeError("reference csr_soa (B sparse) kernel could not be generated (rc=%d)" % rc)
         return times
 
     def mm_rm(self, a, B, C, beta=1.0, nblock=16, lda=None):

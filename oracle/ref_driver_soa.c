@@ -11,9 +11,20 @@
  * n_elem elements, strides in scalars.  Returns 0, or -1 if the kernel could not be generated.
  */
 #include "libxsmm.h"
+int refdrv_csr_soa_run_ex(int dbl, int M, int N, int K, int lda, int ldb, int ldc, double beta,
+                          const unsigned int* rowptr, const unsigned int* colidx, const void* values,
+                          const void* X, void* C, long n_elem, long stride_x, long stride_c, int* soa_width_used);
+
 int refdrv_csr_soa_run(int dbl, int M, int N, int K, int ldb, int ldc, double beta,
                        const unsigned int* rowptr, const unsigned int* colidx, const void* values,
                        const void* B, void* C, long n_elem, long stride_b, long stride_c, int* soa_width_used)
+{ return refdrv_csr_soa_run_ex(dbl, M, N, K, 0, ldb, ldc, beta, rowptr, colidx, values, B, C, n_elem, stride_b, stride_c, soa_width_used); }
+
+/* lda == 0: A sparse (CSR over m), X = B dense [k][ldb][soa], kernel(values, X, C).
+ * ldb == 0: B sparse (CSR over k), X = A dense [m][lda][soa], kernel(X, values, C)  (samples/edge/bsparse_srsoa.c:160-176). */
+int refdrv_csr_soa_run_ex(int dbl, int M, int N, int K, int lda, int ldb, int ldc, double beta,
+                          const unsigned int* rowptr, const unsigned int* colidx, const void* values,
+                          const void* B, void* C, long n_elem, long stride_b, long stride_c, int* soa_width_used)
 {
   libxsmm_descriptor_blob blob;
   const int flags = LIBXSMM_GEMM_FLAGS('N', 'N');
@@ -24,17 +35,23 @@ int refdrv_csr_soa_run(int dbl, int M, int N, int K, int ldb, int ldc, double be
     *soa_width_used = dbl ? (avx512 ? 8 : 4) : (avx512 ? 16 : 8);
   }
   if (dbl) {
-    const libxsmm_gemm_descriptor* d = libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F64, M, N, K, 0, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
+    const libxsmm_gemm_descriptor* d = libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F64, M, N, K, lda, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
     libxsmm_dmmfunction kern = (0 != d) ? libxsmm_create_xcsr_soa(d, rowptr, colidx, values).dmm : 0;
     if (0 == kern) return -1;
-    for (e = 0; e < n_elem; ++e) kern((const double*)values, (const double*)B + e * stride_b, (double*)C + e * stride_c);
+    for (e = 0; e < n_elem; ++e) {
+      if (0 == lda) kern((const double*)values, (const double*)B + e * stride_b, (double*)C + e * stride_c);
+      else kern((const double*)B + e * stride_b, (const double*)values, (double*)C + e * stride_c);
+    }
     libxsmm_release_kernel((const void*)kern);
   }
   else {
-    const libxsmm_gemm_descriptor* d = libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F32, M, N, K, 0, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
+    const libxsmm_gemm_descriptor* d = libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F32, M, N, K, lda, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
     libxsmm_smmfunction kern = (0 != d) ? libxsmm_create_xcsr_soa(d, rowptr, colidx, values).smm : 0;
     if (0 == kern) return -1;
-    for (e = 0; e < n_elem; ++e) kern((const float*)values, (const float*)B + e * stride_b, (float*)C + e * stride_c);
+    for (e = 0; e < n_elem; ++e) {
+      if (0 == lda) kern((const float*)values, (const float*)B + e * stride_b, (float*)C + e * stride_c);
+      else kern((const float*)B + e * stride_b, (const float*)values, (float*)C + e * stride_c);
+    }
     libxsmm_release_kernel((const void*)kern);
   }
   return 0;
@@ -69,9 +86,9 @@ int refdrv_mm_rm_run(int dbl, int M, int N, int K, int lda_op, int ld, double be
 
 /* the same kernel timed the way an element loop would run it on the host: OpenMP over elements, reps repetitions */
 #include <omp.h>
-int refdrv_csr_soa_bench(int dbl, int M, int N, int K, int ldb, int ldc, double beta,
-                         const unsigned int* rowptr, const unsigned int* colidx, const void* values,
-                         const void* B, void* C, long n_elem, long stride_b, long stride_c, int threads, int reps, double* times)
+int refdrv_csr_soa_bench_ex(int dbl, int M, int N, int K, int lda, int ldb, int ldc, double beta,
+                            const unsigned int* rowptr, const unsigned int* colidx, const void* values,
+                            const void* X, void* C, long n_elem, long stride_x, long stride_c, int threads, int reps, double* times)
 {
   libxsmm_descriptor_blob blob;
   const int flags = LIBXSMM_GEMM_FLAGS('N', 'N');
@@ -80,8 +97,8 @@ int refdrv_csr_soa_bench(int dbl, int M, int N, int K, int ldb, int ldc, double 
   int r; long e;
   libxsmm_init();
   if (threads <= 0) threads = omp_get_max_threads();
-  d = dbl ? libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F64, M, N, K, 0, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE)
-          : libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F32, M, N, K, 0, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
+  d = dbl ? libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F64, M, N, K, lda, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE)
+          : libxsmm_gemm_descriptor_dinit(&blob, LIBXSMM_GEMM_PRECISION_F32, M, N, K, lda, ldb, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
   if (0 == d) return -1;
   kern = libxsmm_create_xcsr_soa(d, rowptr, colidx, values);
   if (0 == kern.dmm) return -1;
@@ -89,11 +106,22 @@ int refdrv_csr_soa_bench(int dbl, int M, int N, int K, int ldb, int ldc, double 
     const double t0 = omp_get_wtime();
 #   pragma omp parallel for num_threads(threads) schedule(static)
     for (e = 0; e < n_elem; ++e) {
-      if (dbl) kern.dmm((const double*)values, (const double*)B + e * stride_b, (double*)C + e * stride_c);
-      else kern.smm((const float*)values, (const float*)B + e * stride_b, (float*)C + e * stride_c);
+      if (0 == lda) {   /* A sparse: kernel(values, B, C) */
+        if (dbl) kern.dmm((const double*)values, (const double*)X + e * stride_x, (double*)C + e * stride_c);
+        else kern.smm((const float*)values, (const float*)X + e * stride_x, (float*)C + e * stride_c);
+      }
+      else {            /* B sparse: kernel(A, values, C) */
+        if (dbl) kern.dmm((const double*)X + e * stride_x, (const double*)values, (double*)C + e * stride_c);
+        else kern.smm((const float*)X + e * stride_x, (const float*)values, (float*)C + e * stride_c);
+      }
     }
     if (times) times[r] = omp_get_wtime() - t0;
   }
   libxsmm_release_kernel((const void*)kern.dmm);
   return 0;
 }
+
+int refdrv_csr_soa_bench(int dbl, int M, int N, int K, int ldb, int ldc, double beta,
+                         const unsigned int* rowptr, const unsigned int* colidx, const void* values,
+                         const void* B, void* C, long n_elem, long stride_b, long stride_c, int threads, int reps, double* times)
+{ return refdrv_csr_soa_bench_ex(dbl, M, N, K, 0, ldb, ldc, beta, rowptr, colidx, values, B, C, n_elem, stride_b, stride_c, threads, reps, times); }

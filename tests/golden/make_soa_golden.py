@@ -61,8 +61,29 @@ def main():
                 C = C0.copy()
                 ref.csr_soa(rp, ci, va, B, C, N, beta)
                 out[key + "_out%d" % int(beta)] = C
-    np.savez_compressed(os.path.join(HERE, "csr_soa.npz"), names=np.array(names), **out)
-    print("wrote csr_soa.npz:", len(names), "cases")
+    # ---- B sparse (descriptor lda > 0, ldb = 0; samples/edge/bsparse_srsoa.c): 9 quantities x basis functions, right-multiplied
+    #      by a stiffness / flux operator (K x N)
+    bnames = []
+    for f in ("tet4_4_stiffV_0_csr.mtx", "tet4_5_stiffT_1_csr.mtx", "tet4_4_fluxN_3_csr.mtx", "tet4_4_fluxT_2_csr.mtx"):
+        b64 = w.read_mtx(os.path.join(MATS, f))
+        for dt in (np.float64, np.float32):
+            b = b64.astype(dt)
+            rp, ci, va = csr_of(b)
+            K, N = b.shape
+            M, E = 9, 2
+            soa = ref.soa_width(dt)
+            A = rng.uniform(-1, 1, (E, M, K, soa)).astype(dt); C0 = rng.uniform(-1, 1, (E, M, N, soa)).astype(dt)
+            key = "bsp_%s_%s" % (f[:-8], "d" if dt == np.float64 else "s")
+            bnames.append(key)
+            out[key + "_shape"] = np.array([M, K, N, soa, E], np.int32)
+            out[key + "_rowptr"], out[key + "_colidx"], out[key + "_values"] = rp, ci, va
+            out[key + "_A"], out[key + "_C0"] = A, C0
+            for beta in (0.0, 1.0):
+                C = C0.copy()
+                ref.csr_soa_bsparse(rp, ci, va, A, C, N, beta)
+                out[key + "_out%d" % int(beta)] = C
+    np.savez_compressed(os.path.join(HERE, "csr_soa.npz"), names=np.array(names), bnames=np.array(bnames), **out)
+    print("wrote csr_soa.npz:", len(names), "A-sparse and", len(bnames), "B-sparse cases")
 
 
 if __name__ == "__main__":

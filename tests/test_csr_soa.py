@@ -52,6 +52,83 @@ def test_oracle_matches_compiled_reference(oracle, ref):
             assert np.array_equal(bits(C[:, :, N:]), bits(C0[:, :, N:]))          # columns past N untouched
 
 
+def test_oracle_matches_reference_outputs_b_sparse(oracle, cases):
+    d, _ = cases
+    bnames = [str(n) for n in d["bnames"]]
+    assert len(bnames) >= 8
+    for key in bnames:
+        M, K, N, soa, E = (int(x) for x in d[key + "_shape"])
+        for beta in (0.0, 1.0):
+            C = d[key + "_C0"].copy()
+            oracle.csr_soa_bsparse_execute(d[key + "_rowptr"], d[key + "_colidx"], d[key + "_values"], d[key + "_A"], C, N, beta=beta)
+            assert np.array_equal(bits(C), bits(d[key + "_out%d" % int(beta)])), "%s beta=%g" % (key, beta)
+
+
+def test_oracle_matches_compiled_reference_b_sparse(oracle, ref):
+    """pitches lda > K, ldc > N; an all-zero column (still written: beta C or 0) and an all-zero row of B"""
+    rng = np.random.default_rng(5)
+    for dt in (np.float64, np.float32):
+        soa = ref.soa_width(dt)
+        for (M, K, N, lda, ldc, dens, beta) in ((9, 35, 35, 35, 35, 0.2, 0.0), (9, 56, 35, 60, 40, 0.1, 1.0), (4, 20, 28, 24, 28, 0.5, 0.0), (5, 10, 10, 10, 12, 1.0, 1.0)):
+            b = np.where(rng.random((K, N)) < dens, rng.uniform(-1, 1, (K, N)), 0).astype(dt)
+            b[:, 3] = 0; b[2, :] = 0
+            rp, ci, va = [0], [], []
+            for i in range(K):
+                nz = np.nonzero(b[i])[0]
+                ci += list(nz); va += list(b[i, nz]); rp.append(len(ci))
+            rp, ci, va = np.array(rp, np.uint32), np.array(ci, np.uint32), np.array(va, dt)
+            A = rng.uniform(-1, 1, (2, M, lda, soa)).astype(dt); C0 = rng.uniform(-1, 1, (2, M, ldc, soa)).astype(dt)
+            C = C0.copy(); ref.csr_soa_bsparse(rp, ci, va, A, C, N, beta)
+            OC = C0.copy(); oracle.csr_soa_bsparse_execute(rp, ci, va, A, OC, N, beta=beta)
+            assert np.array_equal(bits(C), bits(OC)), (dt.__name__, M, K, N, dens, beta)
+            if beta == 0.0:
+                assert not C[:, :, 3].any()
+            assert np.array_equal(bits(C[:, :, N:]), bits(C0[:, :, N:]))
+
+
+@pytest.mark.gpu
+def test_gpu_b_sparse_matches_reference_and_oracle(gpu, oracle, cases):
+    d, _ = cases
+    for key in [str(n) for n in d["bnames"]]:
+        M, K, N, soa, E = (int(x) for x in d[key + "_shape"])
+        for beta in (0.0, 1.0):
+            op = gpu.CsrSoa(M, N, K, d[key + "_rowptr"], d[key + "_colidx"], d[key + "_values"], soa, beta=beta, sparse="B")
+            assert op.is_baked, key
+            dA, dC = gpu.DeviceBuffer.from_numpy(d[key + "_A"]), gpu.DeviceBuffer.from_numpy(d[key + "_C0"])
+            op.execute(dA, dC, E)
+            gpu.synchronize()
+            C = dC.to_numpy(d[key + "_C0"].dtype, d[key + "_C0"].shape)
+            dA.free(); dC.free(); op.destroy()
+            assert np.array_equal(bits(C), bits(d[key + "_out%d" % int(beta)])), "%s beta=%g" % (key, beta)
+    # many elements, padded pitches and element strides, an empty column and an empty row of B, against the oracle
+    rng = np.random.default_rng(10)
+    for dt, soa in ((np.float64, 8), (np.float32, 16)):
+        M, K, N, lda, ldc, E, pad = 9, 35, 20, 40, 24, 300, 16
+        b = np.where(rng.random((K, N)) < 0.2, rng.uniform(-1, 1, (K, N)), 0).astype(dt)
+        b[:, 5] = 0; b[7, :] = 0
+        rp, ci, va = [0], [], []
+        for i in range(K):
+            nz = np.nonzero(b[i])[0]
+            ci += list(nz); va += list(b[i, nz]); rp.append(len(ci))
+        rp, ci, va = np.array(rp, np.uint32), np.array(ci, np.uint32), np.array(va, dt)
+        sa, sc = M * lda * soa + pad, M * ldc * soa + pad
+        Af = rng.uniform(-1, 1, E * sa).astype(dt); Cf = rng.uniform(-1, 1, E * sc).astype(dt)
+        want = Cf.copy()
+        for e in range(E):
+            Ae = np.ascontiguousarray(Af[e * sa:e * sa + M * lda * soa].reshape(M, lda, soa))
+            Ce = np.ascontiguousarray(want[e * sc:e * sc + M * ldc * soa].reshape(M, ldc, soa))
+            oracle.csr_soa_bsparse_execute(rp, ci, va, Ae, Ce, N, beta=1.0)
+            want[e * sc:e * sc + M * ldc * soa] = Ce.ravel()
+        op = gpu.CsrSoa(M, N, K, rp, ci, va, soa, lda=lda, ldc=ldc, beta=1.0, sparse="B")
+        dA, dC = gpu.DeviceBuffer.from_numpy(Af), gpu.DeviceBuffer.from_numpy(Cf)
+        op.execute(dA, dC, E, sa, sc)
+        gpu.synchronize()
+        C = dC.to_numpy(dt, Cf.shape)
+        dA.free(); dC.free(); op.destroy()
+        assert np.array_equal(bits(C), bits(want)), dt.__name__
+    gpu.check()
+
+
 @pytest.mark.gpu
 def test_gpu_matches_reference_outputs(gpu, cases):
     d, names = cases
