@@ -145,6 +145,15 @@ LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_dcsr_soa_create(int M, int N, int
   const unsigned int* row_ptr, const unsigned int* column_idx, const double* values);
 LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_scsr_soa_create(int M, int N, int K, int lda, int ldb, int ldc, int soa_width, float beta,
   const unsigned int* row_ptr, const unsigned int* column_idx, const float* values);
+/* libxsmm_create_xcsc_soa + kernel(a, values, c) (reference src/template/libxsmm.h:283-293, src/libxsmm_main.c:2450-2474,
+ * src/generator_spgemm_csc_bsparse_soa.c; caller samples/edge/bsparse_scsoa.c:327-354): B sparse in CSC (column_ptr over its n
+ * columns, row_idx = k), A dense [m][lda][soa_width], C [m][ldc][soa_width];
+ *     C[m][n][s] = (beta == 0 ? 0 : C[m][n][s]) + sum over k ascending of A[m][k][s] * (the first entry of column n with row index k).
+ * All n columns are written.  The handle is executed (d_X = A) and destroyed with the csr_soa entries below. */
+LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_dcsc_soa_create(int M, int N, int K, int lda, int ldc, int soa_width, double beta,
+                                                               const unsigned int* column_ptr, const unsigned int* row_idx, const double* values);
+LIBXSMM_API libxsmm_b200_csr_soa* libxsmm_b200_scsc_soa_create(int M, int N, int K, int lda, int ldc, int soa_width, float beta,
+                                                               const unsigned int* column_ptr, const unsigned int* row_idx, const float* values);
 LIBXSMM_API void libxsmm_b200_csr_soa_execute(const libxsmm_b200_csr_soa* handle, const void* d_X, void* d_C, long long n_elements,
   long long stride_x, long long stride_c, void* stream);
 LIBXSMM_API int libxsmm_b200_csr_soa_is_baked(const libxsmm_b200_csr_soa* handle);

@@ -52,7 +52,7 @@ ADDED_SYMBOLS = [
     "libxsmm_b200_sparse_matmul", "libxsmm_b200_sparse_matmul_cache_entries", "libxsmm_b200_sparse_matmul_cache_clear",
     "libxsmm_b200_csr_read_mtx", "libxsmm_b200_csr_free", "libxsmm_b200_dfsspmdm_create_mtx", "libxsmm_b200_sfsspmdm_create_mtx",
     "libxsmm_b200_dcsr_soa_create", "libxsmm_b200_scsr_soa_create", "libxsmm_b200_csr_soa_execute", "libxsmm_b200_csr_soa_is_baked",
-    "libxsmm_b200_csr_soa_destroy",
+    "libxsmm_b200_csr_soa_destroy", "libxsmm_b200_dcsc_soa_create", "libxsmm_b200_scsc_soa_create",
     "libxsmm_b200_dmmdispatch", "libxsmm_b200_smmdispatch", "libxsmm_b200_mm_execute", "libxsmm_b200_mm_kernel", "libxsmm_b200_mm_release",
 ]
 
@@ -669,21 +669,29 @@ class CsrSoa:
     libxsmm_create_xcsr_soa).  sparse="A": reference samples/edge/asparse_srsoa.c (the CSR matrix is M x K, the dense operand
     B is [K][ldb][soa]); sparse="B": samples/edge/bsparse_srsoa.c (the CSR matrix is K x N, the dense operand A is [M][lda][soa])."""
 
-    def __init__(self, M, N, K, rowptr, colidx, values, soa_width, lda=None, ldb=None, ldc=None, beta=0.0, sparse="A"):
+    def __init__(self, M, N, K, rowptr, colidx, values, soa_width, lda=None, ldb=None, ldc=None, beta=0.0, sparse="A", fmt="csr"):
+        """fmt="csc" (sparse="B" only): rowptr / colidx are the column pointers / row indices of B (libxsmm_create_xcsc_soa,
+        reference samples/edge/bsparse_scsoa.c)."""
         require_gpu()
         L = load()
         values = np.ascontiguousarray(values)
-        assert values.dtype in (np.float64, np.float32) and sparse in ("A", "B")
+        assert values.dtype in (np.float64, np.float32) and sparse in ("A", "B") and fmt in ("csr", "csc") and (fmt == "csr" or sparse == "B")
         self.double = values.dtype == np.float64
         rowptr = np.ascontiguousarray(rowptr, np.uint32); colidx = np.ascontiguousarray(colidx, np.uint32)
-        f = L.libxsmm_b200_dcsr_soa_create if self.double else L.libxsmm_b200_scsr_soa_create
-        f.restype = ctypes.c_void_p
-        f.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double if self.double else ctypes.c_float] + [ctypes.c_void_p] * 3
         self.M, self.N, self.K, self.soa, self.sparse = M, N, K, soa_width, sparse
         self.lda = 0 if sparse == "A" else (K if lda is None else lda)
         self.ldb = 0 if sparse == "B" else (N if ldb is None else ldb)
         self.ldc = N if ldc is None else ldc
-        self.handle = f(M, N, K, self.lda, self.ldb, self.ldc, soa_width, float(beta), rowptr.ctypes.data, colidx.ctypes.data, values.ctypes.data)
+        if fmt == "csc":
+            f = L.libxsmm_b200_dcsc_soa_create if self.double else L.libxsmm_b200_scsc_soa_create
+            f.restype = ctypes.c_void_p
+            f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double if self.double else ctypes.c_float] + [ctypes.c_void_p] * 3
+            self.handle = f(M, N, K, self.lda, self.ldc, soa_width, float(beta), rowptr.ctypes.data, colidx.ctypes.data, values.ctypes.data)
+        else:
+            f = L.libxsmm_b200_dcsr_soa_create if self.double else L.libxsmm_b200_scsr_soa_create
+            f.restype = ctypes.c_void_p
+            f.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double if self.double else ctypes.c_float] + [ctypes.c_void_p] * 3
+            self.handle = f(M, N, K, self.lda, self.ldb, self.ldc, soa_width, float(beta), rowptr.ctypes.data, colidx.ctypes.data, values.ctypes.data)
         if not self.handle:
             code, msg = last_error()
             clear_error()

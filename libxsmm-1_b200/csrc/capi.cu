@@ -838,6 +838,13 @@ libxsmm_b200_csr_soa* libxsmm_b200_dcsr_soa_create(int M, int N, int K, int lda,
 libxsmm_b200_csr_soa* libxsmm_b200_scsr_soa_create(int M, int N, int K, int lda, int ldb, int ldc, int soa_width, float beta,
   const unsigned int* row_ptr, const unsigned int* column_idx, const float* values)
 { return (libxsmm_b200_csr_soa*)fs_create_csr(0, M, N, K, lda, ldb, ldc, soa_width, (double)beta, row_ptr, column_idx, values); }
+// libxsmm_create_xcsc_soa (reference src/libxsmm_main.c:2450-2474): B sparse in CSC; the handle is executed / destroyed like a CSR one
+libxsmm_b200_csr_soa* libxsmm_b200_dcsc_soa_create(int M, int N, int K, int lda, int ldc, int soa_width, double beta,
+                                                   const unsigned int* column_ptr, const unsigned int* row_idx, const double* values)
+{ return (libxsmm_b200_csr_soa*)fs_create_csc(1, M, N, K, lda, ldc, soa_width, beta, column_ptr, row_idx, values); }
+libxsmm_b200_csr_soa* libxsmm_b200_scsc_soa_create(int M, int N, int K, int lda, int ldc, int soa_width, float beta,
+                                                   const unsigned int* column_ptr, const unsigned int* row_idx, const float* values)
+{ return (libxsmm_b200_csr_soa*)fs_create_csc(0, M, N, K, lda, ldc, soa_width, (double)beta, column_ptr, row_idx, values); }
 void libxsmm_b200_csr_soa_execute(const libxsmm_b200_csr_soa* handle, const void* d_B, void* d_C, long long n_elements,
   long long stride_b, long long stride_c, void* stream)
 {

@@ -187,6 +187,8 @@ char* fs_kernel_source(const FsOperator* o);
 FsOperator* fs_create(int is_double, int M, int N, int K, int lda, int ldb, int ldc, double beta, const void* a_dense);
 FsOperator* fs_create_csr(int is_double, int M, int N, int K, int lda, int ldb, int ldc, int soa, double beta,
                           const unsigned int* rowptr, const unsigned int* colidx, const void* values);
+FsOperator* fs_create_csc(int is_double, int M, int N, int K, int lda, int ldc, int soa, double beta,
+                          const unsigned int* colptr, const unsigned int* rowidx, const void* values);
 void fs_execute_batched(const FsOperator* o, const void* dB, void* dC, long long n_elem, long long stride_b, long long stride_c, cudaStream_t stream);
 void fs_execute(const FsOperator* op, const void* dB, void* dC, long long ncols, long long ldb, long long ldc, cudaStream_t stream);
 int fs_is_sparse_branch(const FsOperator* o);

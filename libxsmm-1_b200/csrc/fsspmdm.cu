@@ -3,6 +3,7 @@
 // Replaces reference src/libxsmm_fsspmdm.c (create :48-257, execute :260-291, destroy :294-329)
 // and the kernel emitted by src/generator_spgemm_csr_asparse_reg.c:196-300.
 #include "common.cuh"
+#include <algorithm>
 #include "fsspmdm_jit.h"
 #include <vector>
 #include <cstring>
@@ -270,6 +271,26 @@ void fs_execute(const FsOperator* o, const void* dB, void* dC, long long ncols, 
   XB_CUDA(cudaGetLastError());
 }
 
+// device copy of the operator rows (for the generic kernel) + the baked, batched kernel: common tail of the SoA creators
+static FsOperator* fs_finish_soa(FsOperator* o)
+{
+  const size_t nalloc = (size_t)(o->nnz > 0 ? o->nnz : 1);
+  XB_CUDA(cudaMalloc(&o->d_rowptr, sizeof(int) * (o->M + 1)));
+  XB_CUDA(cudaMalloc(&o->d_col, sizeof(int) * nalloc));
+  XB_CUDA(cudaMalloc(&o->d_val, 8 * nalloc));
+  if (0 == o->d_rowptr || 0 == o->d_col || 0 == o->d_val) { fs_destroy(o); return 0; }
+  XB_CUDA(cudaMemcpy(o->d_rowptr, o->rowptr.data(), sizeof(int) * (o->M + 1), cudaMemcpyHostToDevice));
+  if (o->nnz > 0) {
+    XB_CUDA(cudaMemcpy(o->d_col, o->col.data(), sizeof(int) * (size_t)o->nnz, cudaMemcpyHostToDevice));
+    if (o->is_double) XB_CUDA(cudaMemcpy(o->d_val, o->val.data(), 8 * (size_t)o->nnz, cudaMemcpyHostToDevice));
+    else { std::vector<float> vf(o->val.begin(), o->val.end()); XB_CUDA(cudaMemcpy(o->d_val, vf.data(), 4 * (size_t)o->nnz, cudaMemcpyHostToDevice)); }
+  }
+  if (o->M > 0) o->jit = fs_jit_build(o->is_double, 0, o->M, o->K, o->beta_one, o->sparse_branch, o->rowptr.data(), o->col.data(), o->val.data(), 1 /*batched*/);
+  o->kernel = o->jit;
+  return o;
+}
+
+
 // ---- CSR x dense SoA ----------------------------------------------------------------------------
 // The operator arrives as CSR (reference libxsmm_create_xcsr_soa, src/libxsmm_main.c:2423-2447) and is applied to
 // [row][column][soa] tensors.  Arithmetic of the reference's emitted kernel (src/generator_spgemm_csr_asparse_soa.c:
@@ -332,20 +353,46 @@ FsOperator* fs_create_csr(int is_double, int M, int N, int K, int lda, int ldb, 
       o->col[d] = k; o->val[d] = value_at(z);
     }
   }
-  const size_t nalloc = (size_t)(o->nnz > 0 ? o->nnz : 1);
-  XB_CUDA(cudaMalloc(&o->d_rowptr, sizeof(int) * (o->M + 1)));
-  XB_CUDA(cudaMalloc(&o->d_col, sizeof(int) * nalloc));
-  XB_CUDA(cudaMalloc(&o->d_val, 8 * nalloc));
-  if (0 == o->d_rowptr || 0 == o->d_col || 0 == o->d_val) { fs_destroy(o); return 0; }
-  XB_CUDA(cudaMemcpy(o->d_rowptr, o->rowptr.data(), sizeof(int) * (o->M + 1), cudaMemcpyHostToDevice));
-  if (o->nnz > 0) {
-    XB_CUDA(cudaMemcpy(o->d_col, o->col.data(), sizeof(int) * (size_t)o->nnz, cudaMemcpyHostToDevice));
-    if (is_double) XB_CUDA(cudaMemcpy(o->d_val, o->val.data(), 8 * (size_t)o->nnz, cudaMemcpyHostToDevice));
-    else { std::vector<float> vf(o->val.begin(), o->val.end()); XB_CUDA(cudaMemcpy(o->d_val, vf.data(), 4 * (size_t)o->nnz, cudaMemcpyHostToDevice)); }
+  return fs_finish_soa(o);
+}
+
+// libxsmm_create_xcsc_soa (reference src/libxsmm_main.c:2450-2474, src/generator_spgemm_csc_bsparse_soa.c:143-435; caller
+// samples/edge/bsparse_scsoa.c:327-354): B sparse in CSC (column pointers over its N columns, row indices = k), A dense
+// [m][lda][soa], C [m][ldc][soa].  The generator walks k = 0 .. K-1 and, per column of the chunk, takes the FIRST entry of the column
+// whose row index equals k (:270-279): one fused multiply-add per (k, n) in ascending k whatever the order inside the column, later
+// duplicates and rows >= K never used.  Its trailing-empty-column rule (:185-190) cannot fire -- the loop does not stop at the first
+// match, so the last assignment is always n -- hence all N columns are written (unlike the CSR form above).
+FsOperator* fs_create_csc(int is_double, int M, int N, int K, int lda, int ldc, int soa, double beta,
+                          const unsigned int* colptr, const unsigned int* rowidx, const void* values)
+{
+  if (M <= 0 || N <= 0 || K <= 0 || soa <= 0 || lda < K || ldc < N || 0 == colptr || 0 == rowidx || 0 == values || !(0.0 == beta || 1.0 == beta)) {
+    set_error(-60, "csc_soa_create: bad argument (M=%d N=%d K=%d lda=%d ldc=%d soa=%d beta=%g)", M, N, K, lda, ldc, soa, beta);
+    return 0;
   }
-  if (o->M > 0) o->jit = fs_jit_build(is_double, 0, o->M, o->K, o->beta_one, o->sparse_branch, o->rowptr.data(), o->col.data(), o->val.data(), 1 /*batched*/);
-  o->kernel = o->jit;
-  return o;
+  for (int n = 0; n < N; ++n) if (colptr[n + 1] < colptr[n]) { set_error(-61, "csc_soa_create: column pointers not monotone"); return 0; }
+  FsOperator* o = new FsOperator();
+  o->a_dense = 0; o->kernel = 0; o->jit = 0; o->tc = 0;
+  o->is_double = is_double; o->beta_one = (0.0 != beta);
+  o->d_rowptr = 0; o->d_col = 0; o->d_val = 0;
+  o->n_unique = 0; o->x86_code_size = 0; o->N_chunksize = soa;
+  o->M = N; o->K = K; o->N = soa; o->ldb = soa; o->ldc = soa;
+  o->items = M; o->item_cols = soa; o->item_b = (long long)lda * soa; o->item_c = (long long)ldc * soa;
+  o->sparse_branch = 0;
+  o->rowptr.assign((size_t)N + 1, 0);
+  std::vector<std::pair<unsigned int, unsigned int> > ent;     // (k, position) of one column
+  for (int n = 0; n < N; ++n) {
+    ent.clear();
+    for (unsigned int z = colptr[n]; z < colptr[n + 1]; ++z) if (rowidx[z] < (unsigned int)K) ent.push_back(std::make_pair(rowidx[z], z));
+    std::stable_sort(ent.begin(), ent.end(), [](const std::pair<unsigned int, unsigned int>& x, const std::pair<unsigned int, unsigned int>& y) { return x.first < y.first; });
+    for (size_t i = 0; i < ent.size(); ++i) {
+      if (i > 0 && ent[i].first == ent[i - 1].first) continue;          // the first entry with this k wins
+      o->col.push_back((int)ent[i].first);
+      o->val.push_back(is_double ? ((const double*)values)[ent[i].second] : (double)((const float*)values)[ent[i].second]);
+    }
+    o->rowptr[n + 1] = (int)o->col.size();
+  }
+  o->nnz = o->rowptr[N];
+  return fs_finish_soa(o);
 }
 
 void fs_execute_batched(const FsOperator* o, const void* dB, void* dC, long long n_elem, long long stride_b, long long stride_c, cudaStream_t stream)

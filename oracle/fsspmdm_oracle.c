@@ -234,3 +234,38 @@ void orc_csr_soa_bsparse_execute(int dbl, int M, int N, int K, int lda, int ldc,
     }
   }
 }
+
+/*
+ * libxsmm_create_xcsc_soa (src/libxsmm_main.c:2450-2474; src/generator_spgemm_csc_bsparse_soa.c:143-435; caller
+ * samples/edge/bsparse_scsoa.c:327-354): B sparse in CSC (colptr over its N columns, rowidx = k), A dense [m][lda][soa],
+ * C [m][ldc][soa].  Per chunk of columns the emitted code loads (or zeroes) the accumulators (:206-224), walks k = 0 .. K-1
+ * and for every column of the chunk searches the column for the FIRST entry whose row index is k (:270-279; the KNM
+ * "qmadd" variant :231-268 is not what any host here generates), one fused multiply-add each (:345-400), then stores
+ * (:406-415).  The "max column" loop (:185-190) tests colptr[n'] == colptr[N] for every n' WITHOUT stopping, so its last
+ * assignment is always N: all N columns are written, also trailing empty ones.
+ */
+void orc_csc_soa_execute(int dbl, int M, int N, int K, int lda, int ldc, int soa, double beta,
+                         const uint32_t* colptr, const uint32_t* rowidx, const void* values,
+                         const void* A, void* C, long n_elem, long stride_a, long stride_c)
+{
+  long e; int m, n, s, k; uint32_t z;
+  for (e = 0; e < n_elem; ++e) for (m = 0; m < M; ++m) for (n = 0; n < N; ++n) for (s = 0; s < soa; ++s) {
+    const size_t cat = (size_t)e * stride_c + ((size_t)m * ldc + n) * soa + s;
+    if (dbl) {
+      double acc = (0.0 == beta) ? 0.0 : ((double*)C)[cat];
+      for (k = 0; k < K; ++k) for (z = colptr[n]; z < colptr[n + 1]; ++z) if ((int)rowidx[z] == k) {
+        acc = fma(((const double*)A)[(size_t)e * stride_a + ((size_t)m * lda + k) * soa + s], ((const double*)values)[z], acc);
+        break;
+      }
+      ((double*)C)[cat] = acc;
+    }
+    else {
+      float acc = (0.0 == beta) ? 0.f : ((float*)C)[cat];
+      for (k = 0; k < K; ++k) for (z = colptr[n]; z < colptr[n + 1]; ++z) if ((int)rowidx[z] == k) {
+        acc = fmaf(((const float*)A)[(size_t)e * stride_a + ((size_t)m * lda + k) * soa + s], ((const float*)values)[z], acc);
+        break;
+      }
+      ((float*)C)[cat] = acc;
+    }
+  }
+}

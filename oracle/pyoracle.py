@@ -206,6 +206,23 @@ class Oracle:
         return C
 
 
+    def csc_soa_execute(self, colptr, rowidx, values, A, C, N, beta=0.0, K=None):
+        """B sparse in CSC (colptr over N columns): in place on C.  A: [E][M][lda][soa], C: [E][M][ldc][soa]; K = lda unless given."""
+        values = np.ascontiguousarray(values)
+        dbl = 1 if values.dtype == np.float64 else 0
+        assert A.dtype == values.dtype and C.dtype == values.dtype and A.flags.c_contiguous and C.flags.c_contiguous
+        if A.ndim == 3:
+            A = A[None]; C = C[None]
+        E, M, lda, soa = A.shape
+        colptr = np.ascontiguousarray(colptr, np.uint32); rowidx = np.ascontiguousarray(rowidx, np.uint32)
+        assert len(colptr) == N + 1
+        f = self.lib.orc_csc_soa_execute
+        f.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double] + [ctypes.c_void_p] * 5 + [ctypes.c_long] * 3
+        f.restype = None
+        f(dbl, M, N, lda if K is None else K, lda, C.shape[2], soa, float(beta), _ptr(colptr), _ptr(rowidx), _ptr(values), _ptr(A), _ptr(C), E, M * lda * soa, M * C.shape[2] * soa)
+        return C
+
+
 class Ref:
     """The compiled reference.  ``Ref.available()`` is False where oracle/_ref is absent."""
 
@@ -272,6 +289,28 @@ class Ref:
                ctypes.cast(ctypes.byref(used), ctypes.c_void_p))
         if rc != 0:
             raise RuntimeError("reference csr_soa (B sparse) kernel could not be generated (rc=%d)" % rc)
+        if used.value != soa:
+            raise ValueError("SoA width of the arrays is %d, the reference's generator uses %d on this host" % (soa, used.value))
+        return used.value
+
+    def csc_soa(self, colptr, rowidx, values, A, C, N, beta=0.0):
+        """libxsmm_create_xcsc_soa (B sparse, CSC): A [E][M][lda][soa] dense (K = lda), in place on C [E][M][ldc][soa]."""
+        values = np.ascontiguousarray(values)
+        dbl = 1 if values.dtype == np.float64 else 0
+        assert A.dtype == values.dtype and C.dtype == values.dtype and A.flags.c_contiguous and C.flags.c_contiguous
+        if A.ndim == 3:
+            A = A[None]; C = C[None]
+        E, M, lda, soa = A.shape
+        ldc = C.shape[2]
+        colptr = np.ascontiguousarray(colptr, np.uint32); rowidx = np.ascontiguousarray(rowidx, np.uint32)
+        used = ctypes.c_int(0)
+        f = self.lib.refdrv_csc_soa_run
+        f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double] + [ctypes.c_void_p] * 5 + [ctypes.c_long] * 3 + [ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        rc = f(dbl, M, N, lda, lda, ldc, float(beta), _ptr(colptr), _ptr(rowidx), _ptr(values), _ptr(A), _ptr(C), E, M * lda * soa, M * ldc * soa,
+               ctypes.cast(ctypes.byref(used), ctypes.c_void_p))
+        if rc != 0:
+            raise RuntimeError("reference csc_soa kernel could not be generated (rc=%d)" % rc)
         if used.value != soa:
             raise ValueError("SoA width of the arrays is %d, the reference's generator uses %d on this host" % (soa, used.value))
         return used.value

@@ -125,3 +125,30 @@ int refdrv_csr_soa_bench(int dbl, int M, int N, int K, int ldb, int ldc, double 
                          const unsigned int* rowptr, const unsigned int* colidx, const void* values,
                          const void* B, void* C, long n_elem, long stride_b, long stride_c, int threads, int reps, double* times)
 { return refdrv_csr_soa_bench_ex(dbl, M, N, K, 0, ldb, ldc, beta, rowptr, colidx, values, B, C, n_elem, stride_b, stride_c, threads, reps, times); }
+
+/* libxsmm_create_xcsc_soa, called like samples/edge/bsparse_scsoa.c:327-354: descriptor (m, n, k, lda, 0, ldc), kernel(A, values, C) */
+int refdrv_csc_soa_run(int dbl, int M, int N, int K, int lda, int ldc, double beta,
+                       const unsigned int* colptr, const unsigned int* rowidx, const void* values,
+                       const void* A, void* C, long n_elem, long stride_a, long stride_c, int* soa_width_used)
+{
+  libxsmm_descriptor_blob blob;
+  const int flags = LIBXSMM_GEMM_FLAGS('N', 'N');
+  const libxsmm_gemm_descriptor* d;
+  libxsmm_xmmfunction kern;
+  long e;
+  libxsmm_init();
+  if (soa_width_used) {
+    const int avx512 = (libxsmm_get_target_archid() >= LIBXSMM_X86_AVX512);
+    *soa_width_used = dbl ? (avx512 ? 8 : 4) : (avx512 ? 16 : 8);
+  }
+  d = libxsmm_gemm_descriptor_dinit(&blob, dbl ? LIBXSMM_GEMM_PRECISION_F64 : LIBXSMM_GEMM_PRECISION_F32, M, N, K, lda, 0, ldc, 1.0, beta, flags, LIBXSMM_GEMM_PREFETCH_NONE);
+  if (0 == d) return -1;
+  kern = libxsmm_create_xcsc_soa(d, colptr, rowidx, values);
+  if (0 == kern.dmm) return -1;
+  for (e = 0; e < n_elem; ++e) {
+    if (dbl) kern.dmm((const double*)A + e * stride_a, (const double*)values, (double*)C + e * stride_c);
+    else kern.smm((const float*)A + e * stride_a, (const float*)values, (float*)C + e * stride_c);
+  }
+  libxsmm_release_kernel((const void*)kern.dmm);
+  return 0;
+}

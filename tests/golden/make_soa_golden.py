@@ -1,5 +1,5 @@
 """Generates tests/golden/csr_soa.npz by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref): libxsmm_create_xcsr_soa kernels
-(src/generator_spgemm_csr_asparse_soa.c) on real EDGE operators shipped under /root/reference/samples/edge/mats
+(src/generator_spgemm_csr_asparse_soa.c, _csr_bsparse_soa.c) and libxsmm_create_xcsc_soa kernels (_csc_bsparse_soa.c) on real EDGE operators shipped under /root/reference/samples/edge/mats
 (tet4_<order>_stiffV / stiffT / fluxN, CSR files) and two synthetic ones (a dense operator, one with empty rows), for
 double (SoA width 8) and float (16), beta = 0 and 1, two mesh elements each -- driven like samples/edge/asparse_srsoa.c.
 
@@ -82,8 +82,37 @@ def main():
                 C = C0.copy()
                 ref.csr_soa_bsparse(rp, ci, va, A, C, N, beta)
                 out[key + "_out%d" % int(beta)] = C
-    np.savez_compressed(os.path.join(HERE, "csr_soa.npz"), names=np.array(names), bnames=np.array(bnames), **out)
-    print("wrote csr_soa.npz:", len(names), "A-sparse and", len(bnames), "B-sparse cases")
+    # ---- B sparse in CSC (libxsmm_create_xcsc_soa; samples/edge/bsparse_scsoa.c and its *_csc.mtx operators); one synthetic
+    #      operator with UNSORTED row indices inside the columns and trailing empty columns
+    cnames = []
+    cops = [(f[:-8], w.read_mtx(os.path.join(MATS, f)), False) for f in ("tet4_4_stiffV_1_csc.mtx", "tet4_5_stiffT_1_csc.mtx", "tet4_4_fluxN_7_csc.mtx")]
+    syn = np.where(rng.random((24, 30)) < 0.25, rng.uniform(-1, 1, (24, 30)), 0.0); syn[:, 26:] = 0; syn[:, 4] = 0
+    cops.append(("synthetic_unsorted", syn, True))
+    for name, b64, shuffle in cops:
+        for dt in (np.float64, np.float32):
+            b = b64.astype(dt)
+            K, N = b.shape
+            cp, ri, va = [0], [], []
+            for n in range(N):
+                ks = list(np.nonzero(b[:, n])[0])
+                if shuffle:
+                    rng.shuffle(ks)
+                ri += ks; va += [b[k, n] for k in ks]; cp.append(len(ri))
+            cp, ri, va = np.array(cp, np.uint32), np.array(ri, np.uint32), np.array(va, dt)
+            M, E = 9, 2
+            soa = ref.soa_width(dt)
+            A = rng.uniform(-1, 1, (E, M, K, soa)).astype(dt); C0 = rng.uniform(-1, 1, (E, M, N, soa)).astype(dt)
+            key = "csc_%s_%s" % (name, "d" if dt == np.float64 else "s")
+            cnames.append(key)
+            out[key + "_shape"] = np.array([M, K, N, soa, E], np.int32)
+            out[key + "_colptr"], out[key + "_rowidx"], out[key + "_values"] = cp, ri, va
+            out[key + "_A"], out[key + "_C0"] = A, C0
+            for beta in (0.0, 1.0):
+                C = C0.copy()
+                ref.csc_soa(cp, ri, va, A, C, N, beta)
+                out[key + "_out%d" % int(beta)] = C
+    np.savez_compressed(os.path.join(HERE, "csr_soa.npz"), names=np.array(names), bnames=np.array(bnames), cnames=np.array(cnames), **out)
+    print("wrote csr_soa.npz:", len(names), "A-sparse,", len(bnames), "B-sparse CSR and", len(cnames), "B-sparse CSC cases")
 
 
 if __name__ == "__main__":

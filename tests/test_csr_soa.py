@@ -86,6 +86,79 @@ def test_oracle_matches_compiled_reference_b_sparse(oracle, ref):
             assert np.array_equal(bits(C[:, :, N:]), bits(C0[:, :, N:]))
 
 
+def test_oracle_matches_reference_outputs_csc(oracle, cases):
+    """libxsmm_create_xcsc_soa (B sparse in CSC): stored outputs of the compiled reference, incl. unsorted columns."""
+    d, _ = cases
+    for key in [str(n) for n in d["cnames"]]:
+        M, K, N, soa, E = (int(x) for x in d[key + "_shape"])
+        for beta in (0.0, 1.0):
+            C = d[key + "_C0"].copy()
+            oracle.csc_soa_execute(d[key + "_colptr"], d[key + "_rowidx"], d[key + "_values"], d[key + "_A"], C, N, beta=beta)
+            assert np.array_equal(bits(C), bits(d[key + "_out%d" % int(beta)])), "%s beta=%g" % (key, beta)
+
+
+def test_oracle_matches_compiled_reference_csc(oracle, ref):
+    rng = np.random.default_rng(12)
+    for dt in (np.float64, np.float32):
+        soa = ref.soa_width(dt)
+        for K, N, dens, trail in ((20, 30, 0.2, 0), (35, 35, 0.1, 6), (10, 40, 0.5, 0)):
+            b = np.where(rng.random((K, N)) < dens, rng.uniform(-1, 1, (K, N)), 0).astype(dt)
+            b[:, 3] = 0
+            if trail:
+                b[:, N - trail:] = 0
+            cp, ri, va = [0], [], []
+            for n in range(N):
+                ks = list(np.nonzero(b[:, n])[0]); rng.shuffle(ks)
+                ri += ks; va += [b[k, n] for k in ks]; cp.append(len(ri))
+            for beta in (0.0, 1.0):
+                A = rng.uniform(-1, 1, (2, 9, K, soa)).astype(dt); C0 = rng.uniform(-1, 1, (2, 9, N + 2, soa)).astype(dt)
+                C = C0.copy(); ref.csc_soa(cp, ri, np.array(va, dt), A, C, N, beta)
+                OC = C0.copy(); oracle.csc_soa_execute(cp, ri, np.array(va, dt), A, OC, N, beta=beta)
+                assert np.array_equal(bits(C), bits(OC))
+                assert np.array_equal(bits(C[:, :, N:]), bits(C0[:, :, N:]))
+
+
+@pytest.mark.gpu
+def test_gpu_csc_matches_reference_and_oracle(gpu, oracle, cases):
+    d, _ = cases
+    for key in [str(n) for n in d["cnames"]]:
+        M, K, N, soa, E = (int(x) for x in d[key + "_shape"])
+        for beta in (0.0, 1.0):
+            op = gpu.CsrSoa(M, N, K, d[key + "_colptr"], d[key + "_rowidx"], d[key + "_values"], soa, beta=beta, sparse="B", fmt="csc")
+            assert op.is_baked, key
+            dA, dC = gpu.DeviceBuffer.from_numpy(d[key + "_A"]), gpu.DeviceBuffer.from_numpy(d[key + "_C0"])
+            op.execute(dA, dC, E)
+            gpu.synchronize()
+            C = dC.to_numpy(d[key + "_C0"].dtype, d[key + "_C0"].shape)
+            dA.free(); dC.free(); op.destroy()
+            assert np.array_equal(bits(C), bits(d[key + "_out%d" % int(beta)])), "%s beta=%g" % (key, beta)
+    # duplicates inside a column (the first entry with a row index wins), rows >= K, padded pitches and strides: against the oracle
+    rng = np.random.default_rng(14)
+    for dt, soa in ((np.float64, 8), (np.float32, 16)):
+        M, K, N, lda, ldc, E, pad = 9, 24, 18, 28, 20, 200, 8
+        cp, ri, va = [0], [], []
+        for n in range(N):
+            ks = [int(k) for k in rng.integers(0, K + 3, size=int(rng.integers(0, 7)))]      # duplicates and k >= K on purpose
+            ri += ks; va += [float(v) for v in rng.uniform(-1, 1, len(ks))]; cp.append(len(ri))
+        cp, ri, va = np.array(cp, np.uint32), np.array(ri, np.uint32), np.array(va, dt)
+        sa, sc = M * lda * soa + pad, M * ldc * soa + pad
+        Af = rng.uniform(-1, 1, E * sa).astype(dt); Cf = rng.uniform(-1, 1, E * sc).astype(dt)
+        want = Cf.copy()
+        for e in range(E):
+            Ae = np.ascontiguousarray(Af[e * sa:e * sa + M * lda * soa].reshape(M, lda, soa))
+            Ce = np.ascontiguousarray(want[e * sc:e * sc + M * ldc * soa].reshape(M, ldc, soa))
+            oracle.csc_soa_execute(cp, ri, va, Ae, Ce, N, beta=0.0, K=K)
+            want[e * sc:e * sc + M * ldc * soa] = Ce.ravel()
+        op = gpu.CsrSoa(M, N, K, cp, ri, va, soa, lda=lda, ldc=ldc, beta=0.0, sparse="B", fmt="csc")
+        dA, dC = gpu.DeviceBuffer.from_numpy(Af), gpu.DeviceBuffer.from_numpy(Cf)
+        op.execute(dA, dC, E, sa, sc)
+        gpu.synchronize()
+        C = dC.to_numpy(dt, Cf.shape)
+        dA.free(); dC.free(); op.destroy()
+        assert np.array_equal(bits(C), bits(want)), dt.__name__
+    gpu.check()
+
+
 @pytest.mark.gpu
 def test_gpu_b_sparse_matches_reference_and_oracle(gpu, oracle, cases):
     d, _ = cases
