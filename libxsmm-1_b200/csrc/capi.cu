@@ -97,6 +97,7 @@ struct SpmdmCtx {
   unsigned long long* d_acc;      // device counters {sum, slices done}
   bool aux_written;               // the auxiliary per-nonzero words of the current slices are valid
   bool dense_written;             // ... and so is their dense tile image
+  bool sp_written;                // ... and so are the words of the structured-sparse tensor-core kernel (SliceArena::tcsp)
   bool captured;                  // the current slices were (are being) produced under stream capture
   size_t dense_bytes;
 };
@@ -127,12 +128,14 @@ static bool stream_is_capturing(cudaStream_t stream)
 static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole, cudaStream_t stream)
 {
   a->acc = c->d_acc; a->host_total = c->d_nnz; a->total_slices = c->g.mb * c->g.kb;
-  a->write_dense = 0;
+  a->write_dense = 0; a->write_sp = 0;
   if (!whole) {
     // legacy per-block call: the block gets its auxiliary words, its part of a dense image (if any) is now stale.  Whether
     // ALL slices carry auxiliary words is unchanged: they do only if the last whole pass wrote them.
     a->write_aux = 1;
+    a->write_sp = 0;
     c->dense_written = false;
+    c->sp_written = false;
     return;
   }
   // Under stream capture the decisions must not depend on the handle's history (the graph is replayed on other inputs) and
@@ -165,6 +168,17 @@ static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole, cud
   c->dense_written = (0 != a->write_dense);
   if (a->write_dense && !capturing) a->write_aux = 0;   // the image replaces the per-nonzero words: every tensor-core kernel that could read them reads the image instead
   c->aux_written = (0 != a->write_aux);
+  // bf16: the word per nonzero the structured-sparse tensor-core kernel needs (one more array of the arena's capacity,
+  // allocated when the first bf16 matrix shows up; never under capture)
+  if (is_bf16 && a->write_aux) {
+    if (0 == c->arena.tcsp && !capturing) {
+      const size_t bytes = (size_t)c->g.mb * c->g.kb * (size_t)c->g.bm * c->g.bk * 4;
+      if (cudaSuccess != cudaMalloc((void**)&c->arena.tcsp, bytes)) { (void)cudaGetLastError(); c->arena.tcsp = 0; }
+    }
+    a->out.tcsp = c->arena.tcsp;
+    a->write_sp = c->arena.tcsp ? 1 : 0;
+  }
+  c->sp_written = slices_get_sp_words(*a);
 }
 
 static int compute_policy(const SpmdmCtx* c, int is_bf16, bool transb, bool transc)
@@ -261,7 +275,7 @@ static void compute_whole(const libxsmm_spmdm_handle* handle, char transb, char 
   a.ldb = a.transb ? c->g.k : c->g.n;
   a.ldc = a.transc ? c->g.m : c->g.n;
   a.beta = beta; a.g = c->g; a.mb_first = 0; a.mb_count = c->g.mb;
-  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16, 0 != a.transb, 0 != a.transc); a.density_hint = density_estimate(c); a.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0; a.aux_valid = c->aux_written ? 1 : 0;
+  a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16, 0 != a.transb, 0 != a.transc); a.density_hint = density_estimate(c); a.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0; a.aux_valid = c->aux_written ? 1 : 0; a.sp_valid = (c->sp_written && c->aux_written) ? 1 : 0;
   launch_compute(a, stream);
 }
 
@@ -319,7 +333,7 @@ static void compute_block(const libxsmm_spmdm_handle* handle, char transb, char 
   const bool dev_b = is_device_ptr(b_in), dev_c = is_device_ptr(c_in);
   ComputeArgs a = ComputeArgs();
   a.sl = c->arena; a.transb = tb; a.transc = tc; a.is_bf16 = is_bf16; a.beta = beta; a.g = g;
-  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1; a.density_hint = -1.f; a.dense_valid = 0; a.aux_valid = 0;   // legacy block: no tensor-core twin
+  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1; a.density_hint = -1.f; a.dense_valid = 0; a.aux_valid = 0; a.sp_valid = 0;   // legacy block: no tensor-core twin
   char* slab = c->staging + (size_t)tid * c->staging_per_tid;
   const size_t slab_b_bytes = (((size_t)g.k * g.bn * 4) + 255) & ~(size_t)255;
   float* c_stage = (float*)(slab + slab_b_bytes);
@@ -389,7 +403,7 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena_base = 0; c->staging = 0; c->table = 0;
   const size_t nnz_bytes = ((ns * 4) + 255) & ~(size_t)255;
   const size_t lb_bytes = ((ns * 4 * 8) + 255) & ~(size_t)255;     // look-back words of the split slicing kernels + {epoch, done counter}
-  XB_CUDA(cudaMalloc(&c->arena_base, row_bytes + col_bytes + val_bytes + val_bytes + nnz_bytes + lb_bytes + 256));
+  XB_CUDA(cudaMalloc(&c->arena_base, row_bytes + col_bytes + val_bytes + val_bytes + nnz_bytes + lb_bytes + 256 + nnz_bytes));
   // per-tid staging slab for the legacy per-block entries on HOST matrices: an A block, or a B panel
   // (k x bn) followed by a C tile (bm x bn); the reference's slab holds the latter two (:148-155)
   {
@@ -415,8 +429,9 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena.slice_nnz = (uint32_t*)((char*)c->arena_base + row_bytes + col_bytes + val_bytes + val_bytes);
   c->arena.lookback = (unsigned long long*)((char*)c->arena.slice_nnz + nnz_bytes);
   c->arena.epoch = (uint32_t*)((char*)c->arena.lookback + lb_bytes);
-  XB_CUDA(cudaMemset(c->arena.slice_nnz, 0, nnz_bytes + lb_bytes + 256));
-  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->captured = false; c->dense_bytes = 0; c->arena.dense = 0;
+  c->arena.slice_ovf = (uint32_t*)((char*)c->arena.epoch + 256);
+  XB_CUDA(cudaMemset(c->arena.slice_nnz, 0, nnz_bytes + lb_bytes + 256 + nnz_bytes));
+  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->sp_written = false; c->captured = false; c->dense_bytes = 0; c->arena.dense = 0; c->arena.tcsp = 0;
   if (cudaSuccess == cudaHostAlloc((void**)&c->h_nnz, sizeof(unsigned long long), cudaHostAllocMapped)) {
     *c->h_nnz = ~0ull;
     if (cudaSuccess != cudaHostGetDevicePointer((void**)&c->d_nnz, c->h_nnz, 0)) c->d_nnz = 0;
@@ -464,6 +479,7 @@ void libxsmm_spmdm_destroy(libxsmm_spmdm_handle* handle)
     if (c->d_c) cudaFree(c->d_c);
     cudaFree(c->arena_base);
     if (c->arena.dense) cudaFree(c->arena.dense);
+    if (c->arena.tcsp) cudaFree(c->arena.tcsp);
     cudaFree(c->staging);
     if (c->d_acc) cudaFree(c->d_acc);
     if (c->h_nnz) cudaFreeHost(c->h_nnz);
@@ -629,7 +645,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
     ca.b = (const char*)c->d_b + (tb ? (size_t)n0 * g.k : (size_t)n0) * esz;
     ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
     ca.beta = beta_f; ca.g = g; ca.mb_first = r0; ca.mb_count = rc;
-    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16, tb, tc); ca.density_hint = density_estimate(c); ca.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0; ca.aux_valid = c->aux_written ? 1 : 0;
+    ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16, tb, tc); ca.density_hint = density_estimate(c); ca.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0; ca.aux_valid = c->aux_written ? 1 : 0; ca.sp_valid = (c->sp_written && c->aux_written) ? 1 : 0;
     launch_compute(ca, c->xs[1]);
   };
   for (int d = 0; d < nd; ++d) {
@@ -667,7 +683,9 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
       sa.write_aux = write_aux;                 // one decision for all row blocks of this multiply
       sa.write_dense = (write_dense && c->arena.dense) ? 1 : 0;
       sa.out = c->arena;
+      sa.write_sp = (is_bf16 && write_aux && c->arena.tcsp) ? 1 : 0;
       c->aux_written = (0 != write_aux);
+      c->sp_written = slices_get_sp_words(sa);
       c->dense_written = (0 != sa.write_dense);
       c->captured = false;
       launch_slices(sa, g.kb, c->xs[1]);

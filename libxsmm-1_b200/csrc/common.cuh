@@ -44,6 +44,10 @@ struct SliceArena {
   uint16_t* tcoff;   // auxiliary (not part of the reference's slice), same indexing as colidx: where the nonzero
                      // goes in the tensor-core branch's shared-memory A tile (fp32 slices: xb_tc_pack)
   uint32_t* tcpk;    // the same memory seen as 32-bit words (bf16 slices: xb_tc16_pack, value and position in one word)
+  uint32_t* slice_ovf;   // auxiliary: overflow entries (see tcsp) of every slice, written by the slicing kernel that writes tcsp
+  uint32_t* tcsp;    // auxiliary, bf16 slices sliced by the wide kernel: one more word per nonzero for the 2:4 structured-sparse
+                     // tensor-core kernel (spmdm_compute_tc16s.cu): metadata of the row's 16-k span << 16 | overflow << 15 |
+                     // position of the kept element in the compressed A tile (xb_sp_pos)
   float* dense;      // auxiliary, optional (fp32 slices of dense matrices): the slice once more as the tensor-core kernel's
                      // shared-memory image -- per (slice, 128-row tile, 64-k half) 64 KiB: a_hi chunk 0, 1, a_lo chunk 0, 1,
                      // each [128 rows x 32 k] fp32, K-major, SWIZZLE_128B -- so that K4 fetches a half with one bulk copy
@@ -74,6 +78,34 @@ __host__ __device__ __forceinline__ uint32_t xb_tc16_pack(int r, int k, uint32_t
 }
 #endif
 
+// 2:4 structured-sparse tensor-core kernel (spmdm_compute_tc16s.cu, tcgen05.mma.sp kind::f16): of every four consecutive k
+// of a row the tensor core takes two KEPT elements plus a 4-bit nibble (position of the first | position of the second << 2,
+// first < second).  A group of four with one nonzero at p keeps it in slot p & 1 under the nibble (0,1) or (2,3); with two or
+// more nonzeros the first two are kept and the others are OVERFLOW entries, which a CUDA-core pass adds afterwards.
+// Compressed A tile per (128 rows, 128 k): [128 rows x 64 kept bf16], K-major SWIZZLE_128B (16 KiB).
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__ uint32_t xb_sp_pos(uint32_t row, uint32_t slot)   // (byte offset in the compressed tile) >> 1
+{
+  return (((row >> 3) & 15u) * 1024u + (row & 7u) * 128u + ((((slot >> 3) ^ row) & 7u) << 4) + ((slot & 7u) << 1)) >> 1;
+}
+// nibble of a group from its 4-bit nonzero mask (table of 16 nibbles in two words)
+__host__ __device__ __forceinline__ uint32_t xb_sp_nibble(uint32_t gm)
+{
+  return (((gm & 8u) ? 0x498E4DCEu : 0x498E4444u) >> ((gm & 7u) * 4u)) & 15u;
+}
+// slot (0 / 1) of the nonzero at position p of a group with mask gm; bit 1 set: overflow (third or fourth nonzero)
+__host__ __device__ __forceinline__ uint32_t xb_sp_slot(uint32_t gm, uint32_t p)
+{
+#if defined(__CUDA_ARCH__)
+  const uint32_t rank = (uint32_t)__popc(gm & ((1u << p) - 1u));
+#else
+  const uint32_t rank = (uint32_t)__builtin_popcount(gm & ((1u << p) - 1u));
+#endif
+  if (0 == (gm & (gm - 1u))) return p & 1u;
+  return rank >= 2u ? 3u : rank;
+}
+#endif
+
 constexpr int kSliceStripRows = 64;   // rows of one slice handled by one CTA of the slicing kernel
 
 struct SliceArgs {
@@ -95,6 +127,7 @@ struct SliceArgs {
   int total_slices;
   int write_aux;        // 0: skip the auxiliary per-nonzero words (tensor-core kernels will not be enqueued)
   int write_dense;      // 1: also write the dense tile image (SliceArena::dense; fp32, transa = 'N', complete k-blocks)
+  int write_sp;         // 1: also write the per-nonzero word of the structured-sparse tensor-core kernel (SliceArena::tcsp; wide bf16 kernel only)
 };
 
 #if defined(__CUDACC__)
@@ -147,6 +180,7 @@ struct ComputeArgs {
   int tc_twin;
   unsigned long long tc_min_nnz;
   int aux_valid;        // the slices' per-nonzero auxiliary words (tcoff / tcpk) were written for ALL slices by the pass these slices come from
+  int sp_valid;         // ... and so were the words of the structured-sparse kernel (tcsp)
   int dense_valid;      // the slices' dense tile image (SliceArena::dense) was written by the slicing pass these slices come from
   float density_hint;   // host's lagging estimate of nnz / (M*K) from the last completed slicing pass, < 0: unknown (performance only)
   int debug_flags;  // developer timing aid (LIBXSMM_B200_K2S_DEBUG; results are wrong when set): 1 = skip the multiply-adds, 2 = skip the B tile loads
@@ -177,6 +211,8 @@ bool launch_compute_sp(const ComputeArgs& args, cudaStream_t stream);    // K2s:
 bool launch_compute_tc(const ComputeArgs& args, cudaStream_t stream);
 bool launch_compute_tc16(const ComputeArgs& args, cudaStream_t stream);   // tcgen05 branch for bf16 inputs
 bool launch_compute_tc16p(const ComputeArgs& args, cudaStream_t stream);
+bool launch_compute_tc16s(const ComputeArgs& args, cudaStream_t stream);  // 2:4 structured-sparse CTA-pair kernel (needs SliceArena::tcsp)
+bool slices_get_sp_words(const SliceArgs& args);                          // would launch_slices() write tcsp for these arguments?
 bool launch_compute_tcq(const ComputeArgs& args, cudaStream_t stream);    // fp32 CTA-pair kernel (needs the slices' dense image)  // CTA-pair (cta_group::2) persistent form of it
 
 // ---- FSSPMDM --------------------------------------------------------------------------------

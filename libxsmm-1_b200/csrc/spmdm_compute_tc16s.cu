@@ -1,0 +1,555 @@
+// K4s: the CTA-pair tensor-core kernel of the bf16 spmdm compute step on the 2:4 STRUCTURED-SPARSE tensor-core path
+// (tcgen05.mma.sp.cta_group::2.kind::f16), for matrices that are sparse but not sparse enough for the CUDA-core kernels.
+//
+//   C[256 rows, 256 cols] = beta*C + sum_kb compress(slices(kb, rows))[256 x 64 kept] * B[kb*128 .. +128, 256 cols]
+//
+// K4p (spmdm_compute_tc16p.cu) multiplies the densified A tile: at 1 % density 99 % of what the tensor core multiplies is
+// zero, and the kernel sits at the floor of that formulation (137 GFLOP of dense work for 4096^3).  The sparse tensor-core
+// instruction takes A as two kept elements of every four consecutive k plus a 4-bit nibble naming their positions, and
+// runs K = 32 in the time the dense one runs K = 16 (measured: 181 against 173 clocks per M = 256, N = 256 instruction,
+// tools/umma_probe/probe_sp_rate.cu).  A random matrix of a few per cent density almost is such a matrix: of the 4.2 M
+// groups of 4096^2 at 1 % about 17 hold three or four nonzeros.  So:
+//   * the slicing kernel (K1x) writes one more word per nonzero (SliceArena::tcsp): where it goes in the COMPRESSED A
+//     tile, the 16-bit metadata word of its row's 16-k span, and whether it is an OVERFLOW entry (third / fourth nonzero
+//     of its group);
+//   * the workers of this kernel patch the compressed tile (128 rows x 64 kept bf16 = 16 KiB per 128-k block, half of
+//     K4p's) and a 2 KiB image of the block's metadata in shared memory, then move that image into tensor memory
+//     (tcgen05.st, four columns per k-block) -- the layout was pinned with tools/umma_probe/probe_sp.cu;
+//   * the overflow entries are added by the epilogue thread that owns the row (value * B[k, :] onto the accumulator it
+//     drains, slices in ascending k-block, entries in ascending k): deterministic, correct at ANY density (it just gets
+//     slow when many groups overflow, which is why the host only picks this kernel for matrices its density estimate puts
+//     below kSpMaxDensity).  A first version did this in a second kernel: 16-27 us for a handful of rows.
+// The accumulator is double buffered in tensor memory like K4p's (a first version with one accumulator and a separate
+// metadata ring ran every SM through its store phase at the same time: 30 us of HBM-write-bound epilogues for 4096^3).
+// Roles per CTA (22 warps): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only) and TMEM owner, warps 2-17 workers
+// (four groups taking k-blocks in turn, one A buffer each), warps 18-21 epilogue.  Same 1e-2 contract as K4p (observed 1e-6).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cstdlib>
+#include <cstdio>
+
+namespace xb {
+
+constexpr int S_BM = 128;                       // rows per CTA
+constexpr int S_BN = 256;                       // columns per pair tile
+constexpr int S_BNH = 128;                      // columns of B staged per CTA
+constexpr int S_KH = 64;                        // k per B stage
+constexpr int S_NG = 4;                         // worker groups (four warps each) taking k-blocks in turn
+constexpr int S_NB = 8;                         // B stages: at two instructions (~360 clocks) per stage the ring has to cover L2 latency plus the hand-shake
+constexpr int S_NA = S_NG;                      // A k-block buffers: every worker group owns one
+constexpr int S_NQ = 4;                         // nonzeros per thread and k-block kept in registers
+constexpr int S_NE = 4;                         // epilogue warps (one per TMEM lane quarter)
+constexpr int S_A_BUF = S_BM * 128;             // 16 KiB: 128 rows x 64 kept bf16
+constexpr int S_META = S_BM * 16;               // 2 KiB: per TMEM lane four 32-bit metadata columns
+constexpr int S_B_STAGE = S_KH * S_BNH * 2;     // 16 KiB
+constexpr int S_THREADS = (2 + 4 * S_NG + S_NE) * 32;
+constexpr int S_SMEM_A = 0;
+constexpr int S_SMEM_B = S_SMEM_A + S_NA * S_A_BUF;
+constexpr int S_SMEM_META = S_SMEM_B + S_NB * S_B_STAGE;
+constexpr int S_SMEM_STAGE = S_SMEM_META + S_NA * S_META;      // per epilogue warp a [32 rows x 32 columns] fp32 box for the TMA store of C
+constexpr int S_STAGE = 32 * 128;
+constexpr int S_SMEM_BAR = S_SMEM_STAGE + S_NE * S_STAGE;
+constexpr int S_NOVF = 4;                       // overflow entries of a row an epilogue thread keeps in registers
+static_assert(0 == (S_SMEM_STAGE & 1023), "SWIZZLE_128B boxes sit on 1 KiB boundaries");
+constexpr int S_SMEM_BYTES = S_SMEM_BAR + 256;
+// Tensor memory: two accumulators of 256 columns fill it.  The metadata ring of a tile (4 columns per k-block buffer) lives
+// in the first columns of the accumulator the tile does NOT accumulate into: that accumulator belongs to the epilogue of the
+// previous tile, which drains those columns first and says so (meta_free); the next tile's first MMA overwrites them only
+// after this tile's MMAs, issued before it, have read them.
+constexpr float kSpMaxDensity = 0.06f;          // above it the overflow pass costs more than the sparse instruction saves
+
+struct SpTile { int mbi, ml0, rows, n0; };
+
+__device__ __forceinline__ void tc_mma_bf16_sp_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t tmem_e, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, %5, 0;\n\t"
+    "tcgen05.mma.sp.cta_group::2.kind::f16 [%0], %1, %2, [%3], %4, p;\n\t}\n"
+    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(tmem_e), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S_THREADS, 1)
+spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const int c_tma, const ComputeArgs p)
+{
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar = (uint64_t*)(smem + S_SMEM_BAR);
+  uint64_t* b_full = bar;                   // [NB] leader: both halves of the B stage landed
+  uint64_t* b_free = b_full + S_NB;         // [NB] both: MMAs that read the stage have completed
+  uint64_t* a_ready = b_free + S_NB;        // [NA] leader: the workers of both CTAs built the k-block (tile and metadata)
+  uint64_t* a_free = a_ready + S_NA;        // [NA] both: MMAs that read the k-block have completed
+  uint64_t* acc_full = a_free + S_NA;       // [2]  both: all MMAs of the tile have completed
+  uint64_t* acc_empty = acc_full + 2;       // [2]  leader: the epilogue warps of both CTAs drained the accumulator
+  uint64_t* meta_free = acc_empty + 2;      // [1]  this CTA: the epilogue has read the columns the next tile's metadata goes to
+  uint32_t* tmem_slot = (uint32_t*)(meta_free + 1);
+
+  const Geom& g = p.g;
+  if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // uniform over the grid
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+  const int tiles_per_mb = (g.bm + S_BM - 1) / S_BM;
+  const int ctiles_m = p.mb_count * tiles_per_mb;
+  const int pair_m = (ctiles_m + 1) >> 1;
+  const int n_tiles = (p.ncols + S_BN - 1) / S_BN;
+  const int total = pair_m * n_tiles;
+  const int nkb = g.kb;
+  const uint32_t sbase = smem_u32(smem);
+
+  auto tile_of = [&](int idx) -> SpTile {
+    SpTile t;
+    const int ct = 2 * (idx % pair_m) + (int)rank;
+    t.n0 = (idx / pair_m) * S_BN;
+    t.mbi = p.mb_first + ct / tiles_per_mb;
+    t.ml0 = (ct % tiles_per_mb) * S_BM;
+    t.rows = 0;
+    if (ct < ctiles_m) t.rows = max(0, min(S_BM, min(g.bm, g.m - t.mbi * g.bm) - t.ml0));
+    return t;
+  };
+
+  // work list of this pair: q full tiles, then (when the rest is at most half as many tiles as pairs) one HALF tile
+  const int wq = total / npairs, wrem = total - wq * npairs;
+  const bool wsplit = wrem > 0 && 2 * wrem <= npairs;
+  const int nwork = wq + ((wsplit ? (pair < 2 * wrem) : (pair < wrem)) ? 1 : 0);
+  auto work_idx = [&](int i) -> int { return i < wq ? pair + i * npairs : wq * npairs + (wsplit ? (pair >> 1) : pair); };
+  auto work_half = [&](int i) -> int { return (i < wq || !wsplit) ? -1 : (pair & 1); };
+
+  if (0 == tid) {
+#pragma unroll
+    for (int i = 0; i < S_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_free[i], 1); }
+#pragma unroll
+    for (int i = 0; i < S_NA; ++i) { mbar_init(&a_ready[i], 8); mbar_init(&a_free[i], 1); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * S_NE); }
+    mbar_init(meta_free, S_NE);
+    mbar_fence_init();
+  }
+  if (1 == warp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (0 == warp) {
+    // ---------------- TMA producer: this CTA's 128 columns of every B stage ----------------
+    if (0 == lane) {
+      tma_prefetch_desc(&tmB);
+      uint32_t gs = 0;
+      for (int wi = 0; wi < nwork; ++wi) {
+        const int idx = work_idx(wi), half = work_half(wi);
+        const int n0 = (idx / pair_m) * S_BN + (half < 0 ? (int)rank * S_BNH : half * S_BNH + (int)rank * (S_BNH / 2));
+        for (int t = 0; t < 2 * nkb; ++t, ++gs) {
+          const uint32_t s = gs % S_NB, f = gs / S_NB;
+          if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
+          if (p.debug_flags & 2) { if (0 == rank) mbar_arrive(&b_full[s]); continue; }     // timing aid: no B loads
+          if (0 == rank) mbar_arrive_expect_tx(&b_full[s], half < 0 ? 2 * S_B_STAGE : S_B_STAGE);
+          const uint32_t lbar = map_to_cta(&b_full[s], 0);
+          unsigned char* dst = smem + S_SMEM_B + s * S_B_STAGE;
+          tma_load_2d_pair(dst, &tmB, n0, t * S_KH, lbar);                         // 64 k-rows x 64 columns
+          if (half < 0) tma_load_2d_pair(dst + S_KH * 128, &tmB, n0 + 64, t * S_KH, lbar);
+        }
+      }
+    }
+  }
+  else if (1 == warp) {
+    // ---------------- MMA issuer (leader CTA) ----------------
+    if (0 == rank && 0 == lane) {
+      // sparse A, D = F32, A = B = BF16, A K-major (compressed), B MN-major, N = 256, M = 256 (pair)
+      const uint32_t idesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(S_BN >> 3) << 17) | ((uint32_t)((2 * S_BM) >> 4) << 24);
+      uint32_t gs = 0, gk = 0;
+      const bool prof = (p.debug_flags & 32) && 0 == pair;       // developer aid: where does the issuing thread wait?
+      long long t_a = 0, t_b = 0, t_acc = 0, t0 = 0, t_begin = prof ? clock64() : 0;
+      for (int wi = 0; wi < nwork; ++wi) {
+        const uint32_t acc = (uint32_t)wi & 1u;
+        const uint32_t idesc_w = (work_half(wi) < 0) ? idesc : ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(S_BNH >> 3) << 17));
+        if (prof) t0 = clock64();
+        if (wi >= 2) mbar_wait(&acc_empty[acc], (((uint32_t)wi >> 1) - 1u) & 1u);
+        if (prof) t_acc += clock64() - t0;
+        tc_fence_after();
+        const uint32_t tacc = tmem_d + acc * S_BN, tmeta = tmem_d + (acc ^ 1u) * S_BN;
+        for (int kbi = 0; kbi < nkb; ++kbi, ++gk) {
+          const uint32_t j = gk % S_NA;
+          if (prof) t0 = clock64();
+          mbar_wait(&a_ready[j], (gk / S_NA) & 1);
+          if (prof) t_a += clock64() - t0;
+          const uint32_t a_base = sbase + S_SMEM_A + j * S_A_BUF;
+#pragma unroll
+          for (int h = 0; h < 2; ++h, ++gs) {
+            const uint32_t s = gs % S_NB;
+            if (prof) t0 = clock64();
+            mbar_wait(&b_full[s], (gs / S_NB) & 1);
+            if (prof) t_b += clock64() - t0;
+            tc_fence_after();
+            const uint32_t b_base = sbase + S_SMEM_B + s * S_B_STAGE;
+            // the metadata of atoms 2h, 2h + 1 lives in columns +2h, +2h + 1: the address names the even column, the
+            // descriptor's selector bit the odd one
+            const uint32_t te = tmeta + 4u * j + 2u * (uint32_t)h;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {       // K = 32 (16 kept elements = 32 bytes of the compressed row) per instruction
+              const uint64_t da = tc_smem_desc(a_base + (2 * h + ks) * 32, 16, 1024, 2);
+              const uint64_t db = tc_smem_desc(b_base + ks * 4096, (uint32_t)(S_KH * 128), 1024, 2);
+              if (!(p.debug_flags & 16)) tc_mma_bf16_sp_pair(tacc, da, db, te, idesc_w | (uint32_t)ks, (kbi > 0 || h > 0 || ks > 0) ? 1u : 0u);
+            }
+            tc_commit_pair(&b_free[s]);
+          }
+          tc_commit_pair(&a_free[j]);
+        }
+        tc_commit_pair(&acc_full[acc]);
+      }
+      if (prof) printf("K4s issuer, pair 0: %d tiles, %u k-blocks, %lld clocks; waiting for A %lld, B %lld, accumulator %lld\n", nwork, gk, clock64() - t_begin, t_a, t_b, t_acc);
+    }
+  }
+  else if (warp < 2 + 4 * S_NG) {
+    // ---------------- workers: group grp (128 threads) builds k-blocks grp, grp + NG, ... ----------------
+    const int grp = (warp - 2) >> 2;
+    const int wt = (tid - 64) & (S_BM - 1);
+    const size_t cap = (size_t)g.bm * g.bk;
+    const uint32_t my_lane_t = (uint32_t)((warp & 3) * 32 + lane);       // the tensor-memory lane this thread can write
+    const uint32_t lead_ready0 = map_to_cta(&a_ready[0], 0);
+    // byte offset of the 16-bit metadata word of (row, 16-k span) inside the image, from the position of a kept element:
+    // tensor-memory lane = row % 8 + 8 * (span % 2) + 16 * (row / 16), column = span / 2, upper half word for rows 8..15 of 16
+    auto meta_off = [](uint32_t pos) -> uint32_t {
+      const uint32_t r7 = (pos >> 6) & 7u, span = ((pos >> 3) & 7u) ^ r7;
+      const uint32_t tl = r7 + ((span & 1u) << 3) + ((pos >> 10) << 4);
+      return tl * 16u + (span >> 1) * 4u + ((pos >> 8) & 2u);
+    };
+    int c_wi = 0, c_kb = grp, c_rows = 0, c_sidx = 0;
+    const uint16_t* c_ro = p.sl.rowidx;
+    auto seat = [&]() {
+      c_rows = 0; c_ro = p.sl.rowidx; c_sidx = 0;
+      if (c_wi < nwork) {
+        const SpTile t = tile_of(work_idx(c_wi));
+        c_sidx = c_kb * g.mb + t.mbi;
+        c_ro = p.sl.rowidx + (size_t)c_sidx * (g.bm + 1) + t.ml0;
+        c_rows = t.rows;
+      }
+    };
+    auto advance = [&]() {
+      c_kb += S_NG;
+      if (c_kb < nkb) { c_sidx += S_NG * g.mb; c_ro += (size_t)S_NG * g.mb * (g.bm + 1); }
+      else {
+        while (c_kb >= nkb && c_wi < nwork) { c_kb -= nkb; ++c_wi; }
+        seat();
+      }
+    };
+    while (c_kb >= nkb && c_wi < nwork) { c_kb -= nkb; ++c_wi; }
+    seat();
+    long long f_a = 0, f_b = 0, f_c = 0; const bool fprof = (p.debug_flags & 32) && 0 == pair && 0 == rank && 0 == grp && 0 == wt;
+    struct Ptr { int pf, sidx; };
+    // rw: xb_tc16_pack word (the bf16 value in its upper half), sw: the structured-sparse word; hs: what this thread put
+    // into the buffer the last time
+    struct Raw { int sidx, first, last, n_old; uint32_t rw[S_NQ]; uint32_t sw[S_NQ]; uint32_t hs[S_NQ]; };
+    auto fetch_ptrs = [&](Ptr& P) {
+      P.pf = 0; P.sidx = c_sidx;
+      if (c_rows > 0 && lane < 3) P.pf = (int)__ldg(c_ro + (0 == lane ? 0 : (1 == lane ? c_rows : c_rows - 1)));
+      advance();
+    };
+    auto fetch = [&](Raw& R, Ptr& P) {
+      long long f0 = fprof ? clock64() : 0;
+      const int pf = __shfl_sync(0xffffffffu, P.pf, 0), pl = __shfl_sync(0xffffffffu, P.pf, 1), pm = __shfl_sync(0xffffffffu, P.pf, 2);
+      if (fprof) { f_a += clock64() - f0 + (pf & 0); f0 = clock64(); }
+      R.sidx = P.sidx; R.first = pf;
+      R.last = (pl < pf) ? pm : pl;            // wrapped u16 counter of a full slice: the last row reads as empty
+      const uint32_t* pw = p.sl.tcpk + R.sidx * cap;
+      const uint32_t* ps = p.sl.tcsp + R.sidx * cap;
+#pragma unroll
+      for (int i = 0; i < S_NQ; ++i) {
+        if (R.first + i * S_BM >= R.last) break;           // uniform
+        const int q = R.first + wt + i * S_BM;
+        R.rw[i] = 0; R.sw[i] = 0;
+        if (q < R.last) { R.rw[i] = __ldg(pw + q); R.sw[i] = __ldg(ps + q); }
+      }
+      if (fprof) { f_b += clock64() - f0; f0 = clock64(); }
+      fetch_ptrs(P);
+      if (fprof) f_c += clock64() - f0;
+    };
+    const uint32_t gk_end = (uint32_t)nwork * (uint32_t)nkb;
+    const bool wprof = (p.debug_flags & 32) && 0 == pair && 0 == rank && 0 == grp && 0 == wt;
+    long long w_free = 0, w_meta = 0, w_patch = 0, w_st = 0, w_fetch = 0, w_t0 = 0, w_begin = wprof ? clock64() : 0;
+    uint32_t w_tile = 0, w_next = (uint32_t)nkb;       // tile (of this pair's list) the k-block gk belongs to: gk in [w_next - nkb, w_next)
+    auto step = [&](uint32_t gk, Raw& R, Ptr& P) {
+      if (gk >= gk_end) return;
+      while (gk >= w_next) { ++w_tile; w_next += (uint32_t)nkb; }
+      const uint32_t j = gk % S_NA;
+      unsigned char* abuf = smem + S_SMEM_A + j * S_A_BUF;
+      unsigned char* mimg = smem + S_SMEM_META + j * S_META;
+      const int n = R.last - R.first;
+      const bool idle = 0 != (p.debug_flags & 1);      // timing aid: hand the buffer over untouched
+      // ---- while the tensor core still reads the buffer: the k-block's metadata image (nobody but this group reads it) ----
+      // Stale metadata needs no clearing: a nibble whose two kept elements are zero contributes nothing wherever it points.
+      if (wprof) w_t0 = clock64();
+      uint4 mv = make_uint4(0, 0, 0, 0);
+      if (!idle) {
+#pragma unroll
+        for (int i = 0; i < S_NQ; ++i) {
+          if (i * S_BM >= n) break;                          // uniform
+          if (wt + i * S_BM < n) *(uint16_t*)(mimg + meta_off(R.sw[i] & 0x1FFFu)) = (uint16_t)(R.sw[i] >> 16);
+        }
+        if (n > S_NQ * S_BM) {         // denser than NQ * 128 nonzeros per tile and k-block: the rest straight from memory
+          const uint32_t* ps = p.sl.tcsp + R.sidx * cap;
+#pragma unroll 2
+          for (int q = R.first + wt + S_NQ * S_BM; q < R.last; q += S_BM) { const uint32_t s = __ldg(ps + q); *(uint16_t*)(mimg + meta_off(s & 0x1FFFu)) = (uint16_t)(s >> 16); }
+        }
+        asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_BM) : "memory");   // the image is complete
+        mv = *(const uint4*)(mimg + my_lane_t * 16u);
+      }
+      if (wprof) { w_patch += clock64() - w_t0; w_t0 = clock64(); }
+      // ---- the buffer is ours once the MMAs of the k-block that used it have completed ----
+      if (gk >= S_NA) mbar_wait(&a_free[j], ((gk / S_NA) - 1) & 1);
+      if (wprof) { w_free += clock64() - w_t0; w_t0 = clock64(); }
+      if (!idle) {
+        // clear the kept elements the previous k-block left behind (a dense one is wiped)
+        if (R.n_old > S_NQ * S_BM) {
+          uint4* z = (uint4*)abuf;
+#pragma unroll
+          for (int i = 0; i < S_A_BUF / 16 / S_BM; ++i) z[wt + i * S_BM] = make_uint4(0, 0, 0, 0);
+        }
+        else {
+#pragma unroll
+          for (int i = 0; i < S_NQ; ++i) {
+            if (i * S_BM >= R.n_old) break;                  // uniform
+            if (wt + i * S_BM < R.n_old) *(uint16_t*)(abuf + ((R.hs[i] & 0x1FFFu) << 1)) = 0;
+          }
+        }
+        // the tile accumulates into buffer w_tile & 1; its metadata goes to the head of the other one, once the epilogue of
+        // the previous tile has read those columns (a completed phase answers at once)
+        if (w_tile >= 1) { mbar_wait(meta_free, (w_tile - 1u) & 1u); tc_fence_after(); }
+        if (wprof) { w_meta += clock64() - w_t0; w_t0 = clock64(); }
+        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + ((w_tile & 1u) ^ 1u) * S_BN + 4u * j;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(mv.x), "r"(mv.y), "r"(mv.z), "r"(mv.w) : "memory");
+        asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_BM) : "memory");   // another thread may write where this one cleared
+#pragma unroll
+        for (int i = 0; i < S_NQ; ++i) {
+          if (i * S_BM >= n) break;                          // uniform
+          if (wt + i * S_BM < n) {
+            const uint32_t s = R.sw[i];
+            if (0 == (s & 0x8000u)) *(uint16_t*)(abuf + ((s & 0x1FFFu) << 1)) = (uint16_t)(R.rw[i] >> 16);   // overflow entries: the CUDA-core pass
+            R.hs[i] = s;
+          }
+        }
+        R.n_old = n;
+        if (n > S_NQ * S_BM) {
+          const uint32_t* pw = p.sl.tcpk + R.sidx * cap;
+          const uint32_t* ps = p.sl.tcsp + R.sidx * cap;
+#pragma unroll 2
+          for (int q = R.first + wt + S_NQ * S_BM; q < R.last; q += S_BM) {
+            const uint32_t w = __ldg(pw + q), s = __ldg(ps + q);
+            if (0 == (s & 0x8000u)) *(uint16_t*)(abuf + ((s & 0x1FFFu) << 1)) = (uint16_t)(w >> 16);
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        tc_fence_before();
+        fence_proxy_async();
+      }
+      __syncwarp();
+      if (0 == lane) mbar_arrive_cluster(lead_ready0 + j * 8);
+      if (wprof) { w_st += clock64() - w_t0; w_t0 = clock64(); }
+      fetch(R, P);                   // after the hand-over: this group's next k-block
+      if (wprof) w_fetch += clock64() - w_t0;
+    };
+    Ptr pa; Raw ra;
+    ra.n_old = 0;
+#pragma unroll
+    for (int i = 0; i < S_NQ; ++i) ra.hs[i] = 0;
+    fetch_ptrs(pa);
+    // the A buffer starts out zero and is only ever patched; the metadata image starts out as "kept elements at 0, 1"
+    {
+      uint4* z = (uint4*)(smem + S_SMEM_A + grp * S_A_BUF);
+#pragma unroll 4
+      for (int i = 0; i < S_A_BUF / 16 / S_BM; ++i) z[wt + i * S_BM] = make_uint4(0, 0, 0, 0);
+      ((uint4*)(smem + S_SMEM_META + grp * S_META))[wt] = make_uint4(0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u);
+    }
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_BM) : "memory");
+    fetch(ra, pa);
+    for (uint32_t gk = (uint32_t)grp; gk < gk_end; gk += S_NG) step(gk, ra, pa);
+    if (wprof) printf("K4s worker group 0: %lld clocks; waiting for the buffer %lld, for the metadata columns %lld; metadata image %lld, clear / store / patch / hand-over %lld, fetch %lld\n", clock64() - w_begin, w_free, w_meta, w_patch, w_st, w_fetch);
+    if (wprof) printf("   fetch: pointer shuffles %lld, nonzero loads %lld, next pointers %lld\n", f_a, f_b, f_c);
+  }
+  else {
+    // ---------------- epilogue: warp owns TMEM lanes 32*(warp % 4) .. +31 of this CTA and half of the tile's columns ----------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lead_empty0 = map_to_cta(&acc_empty[0], 0);
+    unsigned char* stage = smem + S_SMEM_STAGE + (warp - (2 + 4 * S_NG)) * S_STAGE;
+    const size_t cap = (size_t)g.bm * g.bk;
+    const uint16_t* Bp = (const uint16_t*)p.b;
+    for (int wi = 0; wi < nwork; ++wi) {
+      SpTile t = tile_of(work_idx(wi));
+      const int half = work_half(wi), ncw = half < 0 ? S_BN : S_BNH;
+      if (half > 0) t.n0 += S_BNH;
+      const uint32_t acc = (uint32_t)wi & 1u;
+      const int rl = t.ml0 + row;
+      const bool rvalid = row < t.rows;
+      // ---- overflow entries of this thread's row (third / fourth nonzero of a group of four consecutive k): the tensor core
+      // does not see them; the row's owner adds value * B[k, :] to the accumulator it drains, slices in ascending k-block,
+      // entries in ascending k -- one fixed order.  Only slices whose overflow count is not zero are looked at (~2 of the 32
+      // of a row block at 1 %), and all of this runs while the tensor core still works on the tile.
+      auto scan = [&](auto&& f) {
+        for (int kb0 = 0; kb0 < nkb; kb0 += 32) {
+          const int kbl = kb0 + lane;
+          uint32_t flagged = __ballot_sync(0xffffffffu, kbl < nkb && 0 != __ldg(p.sl.slice_ovf + kbl * g.mb + t.mbi));
+          for (; flagged; flagged &= flagged - 1u) {
+            const int kb = kb0 + __ffs((int)flagged) - 1;
+            const size_t s = (size_t)kb * g.mb + t.mbi;
+            int first = 0, last = 0;
+            if (rvalid) { first = (int)__ldg(p.sl.rowidx + s * (g.bm + 1) + rl); last = (int)__ldg(p.sl.rowidx + s * (g.bm + 1) + rl + 1); }
+            for (int q = first; q < last; ++q) {              // last < first: wrapped counter of a full slice, the row reads as empty
+              if (__ldg(p.sl.tcsp + s * cap + q) & 0x8000u) f(kb * g.bk + (int)__ldg(p.sl.colidx + s * cap + q), __ldg(p.sl.values + s * cap + q));
+            }
+          }
+        }
+      };
+      auto add_row = [&](uint32_t (&v)[32], int cb, int k, float a) {   // v[0..31] += a * B[k, n0 + cb .. +31]
+        const uint16_t* bp = Bp + (size_t)k * p.ldb + t.n0 + cb;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (t.n0 + cb + 8 * u + 7 < p.ncols) {
+            const uint4 b8 = __ldg((const uint4*)bp + u);
+            const uint32_t bw[4] = { b8.x, b8.y, b8.z, b8.w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[8 * u + 2 * e] = __float_as_uint(fmaf(a, __uint_as_float(bw[e] << 16), __uint_as_float(v[8 * u + 2 * e])));
+              v[8 * u + 2 * e + 1] = __float_as_uint(fmaf(a, __uint_as_float(bw[e] & 0xFFFF0000u), __uint_as_float(v[8 * u + 2 * e + 1])));
+            }
+          }
+          else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (t.n0 + cb + 8 * u + e < p.ncols) v[8 * u + e] = __float_as_uint(fmaf(a, __uint_as_float((uint32_t)__ldg(bp + 8 * u + e) << 16), __uint_as_float(v[8 * u + e])));
+          }
+        }
+      };
+      int ne = 0, ok[S_NOVF]; float ov[S_NOVF];
+#pragma unroll
+      for (int i = 0; i < S_NOVF; ++i) { ok[i] = 0; ov[i] = 0.f; }
+      scan([&](int k, float a) {
+#pragma unroll
+        for (int i = 0; i < S_NOVF; ++i) if (i == ne) { ok[i] = k; ov[i] = a; }
+        ++ne;
+      });
+      const bool many = 0 != __any_sync(0xffffffffu, ne > S_NOVF);     // warp-uniform: scan() votes
+      // C box by TMA: every row of this warp belongs to the tile, C is not read, rows are 16-byte aligned
+      const bool use_tma = (0 != c_tma) && (t.rows >= quarter * 32 + 32);
+      mbar_wait(&acc_full[acc], ((uint32_t)wi >> 1) & 1u);
+      tc_fence_after();
+      const size_t crow = (size_t)(t.mbi * g.bm + t.ml0 + row - p.row_origin);
+#pragma unroll 1
+      for (int cb = 0; cb < ncw; cb += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_d + acc * S_BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, v);
+        if (0 == cb) {         // columns 0..31 of this accumulator are read: the next tile's metadata may go there
+          tc_fence_before();
+          __syncwarp();
+          if (0 == lane) mbar_arrive(meta_free);
+        }
+        if (many) scan([&](int k, float a) { add_row(v, cb, k, a); });   // rows with many overflow entries (a dense matrix forced onto this kernel): the whole warp walks the slices again
+        else if (ne > 0) {     // rare
+#pragma unroll
+          for (int i = 0; i < S_NOVF; ++i) if (i < ne) add_row(v, cb, ok[i], ov[i]);
+        }
+        if (p.debug_flags & 4) continue;
+        if (use_tma) {
+          // thread = row: eight 16-byte units of the row's 128 bytes, swizzled like the tensor map (unit ^ row % 8): no bank
+          // conflicts, and the store engine, not the load / store unit the workers depend on, moves the box
+          if (0 == lane) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) *(uint4*)(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (0 == lane) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
+                         ::"l"(&tmC), "r"(t.n0 + cb), "r"((int)(crow - (size_t)lane)), "r"(smem_u32(stage)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          }
+        }
+        else if (rvalid) {
+          if (p.transc) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const int col = t.n0 + cb + jj;
+              if (col < p.ncols) {
+                float* dst = p.c + (size_t)col * p.ldc + crow;
+                *dst = (0.f != p.beta) ? fmaf(p.beta, *dst, __uint_as_float(v[jj])) : __uint_as_float(v[jj]);
+              }
+            }
+          }
+          else {
+            float* dst = p.c + crow * p.ldc + t.n0 + cb;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+              const int col = t.n0 + cb + jj;
+              float4 o = make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]), __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+              if (col + 3 < p.ncols) {
+                if (0.f != p.beta) {
+                  const float4 cin = *(const float4*)(dst + jj);
+                  o.x = fmaf(p.beta, cin.x, o.x); o.y = fmaf(p.beta, cin.y, o.y); o.z = fmaf(p.beta, cin.z, o.z); o.w = fmaf(p.beta, cin.w, o.w);
+                }
+                st_global_cs_f4(dst + jj, o);
+              }
+              else {
+                const float e[4] = { o.x, o.y, o.z, o.w };
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2) if (col + t2 < p.ncols) dst[jj + t2] = (0.f != p.beta) ? fmaf(p.beta, dst[jj + t2], e[t2]) : e[t2];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (0 == lane) mbar_arrive_cluster(lead_empty0 + acc * 8);
+    }
+    if (0 == lane) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // the peer's shared memory and barriers stay alive until every MMA and remote arrive has landed
+  if (1 == warp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(512) : "memory");
+  }
+}
+
+bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
+                              unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows, bool atom32);
+
+// returns false when the panel does not qualify (caller falls back to K4p)
+bool launch_compute_tc16s(const ComputeArgs& a, cudaStream_t stream)
+{
+  const char* env = getenv("LIBXSMM_B200_TC16_SPARSE");      // "0": never, "1": whenever the slices carry the words, else: by density
+  if (env && '0' == *env) return false;
+  if (0 == a.aux_valid || 0 == a.sp_valid || 0 == a.sl.tcsp || 0 == a.sl.slice_ovf) return false;
+  if (!a.is_bf16 || a.transb) return false;
+  if (!(env && '1' == *env) && !(a.density_hint >= 0.f && a.density_hint <= kSpMaxDensity)) return false;
+  if (!a.transc && (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3))) return false;
+  CUtensorMap map;
+  if (!make_tensor_map_2d_sw128(&map, a.b, 2, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 2, 64, S_KH, false)) return false;
+  ensure_smem_optin((const void*)spmdm_compute_tc16s_kernel, S_SMEM_BYTES);
+  const int pairs_max = device_sm_count() / 2 > 0 ? device_sm_count() / 2 : 1;
+  const int tiles_per_mb = (a.g.bm + S_BM - 1) / S_BM;
+  const int pair_m = (a.mb_count * tiles_per_mb + 1) / 2;
+  const int total = pair_m * ((a.ncols + S_BN - 1) / S_BN);
+  if (total <= 0) return true;
+  const int pairs = total < pairs_max ? total : pairs_max;
+  // C leaves through TMA boxes of 32 x 32 when it is only written (beta = 0) and stored row-major
+  CUtensorMap cmap = map;
+  int c_tma = 0;
+  if (!a.transc && 0.f == a.beta && !(getenv("LIBXSMM_B200_K4S_TMA_C") && '0' == *getenv("LIBXSMM_B200_K4S_TMA_C"))) {
+    const long long crows = (long long)a.g.m - a.row_origin;
+    if (crows > 0 && make_tensor_map_2d_sw128(&cmap, a.c, 4, (unsigned long long)a.ncols, (unsigned long long)crows, (unsigned long long)a.ldc * 4, 32, 32, false)) c_tma = 1;
+    else cmap = map;
+  }
+  count_launch(1);
+  note_compute_kernel("spmdm_compute_tc16s_kernel");
+  ComputeArgs a2 = a;
+  if (const char* dbg = getenv("LIBXSMM_B200_K4S_DEBUG")) a2.debug_flags = atoi(dbg);   // developer timing aid: results are wrong when set
+  spmdm_compute_tc16s_kernel<<<dim3(2u * (unsigned)pairs), S_THREADS, S_SMEM_BYTES, stream>>>(map, cmap, c_tma, a2);
+  XB_CUDA(cudaGetLastError());
+  return true;
+}
+
+}  // namespace xb

@@ -628,6 +628,7 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  if (2 == NW && 1 == P && 0 == tid && p.write_sp && p.out.tcsp) p.out.slice_ovf[s] = 0;   // counted below, after the scan's barrier
   const K1Scan sc = k1_scan<CW>(p, s, part, mine, wtot, epoch);
   uint32_t pos = sc.pos;
   if (P - 1 == part && 0 == tid) {
@@ -645,6 +646,11 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   const uint32_t rowmask = ((1u << LPR) - 1u) << (LPR * qr);   // the lanes of this lane's row
   const uint32_t before = (1u << (LPR * qr)) - 1u;             // the lanes of the rows above it in the group
   const bool aux = (0 != p.write_aux);
+  // word per nonzero for the structured-sparse tensor-core kernel: a lane's 16 elements are exactly the four groups of four
+  // whose nibbles make one 16-bit metadata word of the row, so everything is known to the lane (common.cuh: xb_sp_*)
+  const bool spw = (2 == NW) && (0 != p.write_sp) && (0 != p.out.tcsp);
+  uint32_t* sp = p.out.tcsp + (size_t)s * g.bm * g.bk;
+  uint32_t n_ovf = 0;
 #pragma unroll
   for (int it = 0; it < ITS; ++it) {
     if (row_lo + RPI * it < row_hi) {      // warp-uniform
@@ -672,6 +678,11 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
         const uint32_t rowm = (uint32_t)r & 127u;
         const uint32_t k0 = (uint32_t)hl * (8u * NW);                  // first column of this lane
         const uint32_t rbase = ((k0 >> 6) << 15) | ((rowm >> 3) * 512u + (rowm & 7u) * 64u);
+        uint32_t meta16 = 0;
+        if (spw) {
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) meta16 |= xb_sp_nibble((m >> (4 * gi)) & 15u) << (16 + 4 * gi);
+        }
 #pragma unroll
         for (int j = 0; j < NW; ++j) {             // the lane's 16-byte words: k = k0 + 8 * j + e
           const uint32_t v[4] = { w[it][j].x, w[it][j].y, w[it][j].z, w[it][j].w };
@@ -684,12 +695,19 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
             co[q] = (uint16_t)(k0 + 8u * j + (uint32_t)e);
             va[q] = __uint_as_float(vb);
             if (aux) rk[q] = vb | (base16 + (uint32_t)e);
+            if (spw) {
+              const uint32_t p16 = 8u * (uint32_t)j + (uint32_t)e, gi = p16 >> 2;
+              const uint32_t sl = xb_sp_slot((m >> (4u * gi)) & 15u, p16 & 3u);
+              sp[q] = meta16 | ((sl & 2u) << 14) | xb_sp_pos(rowm, (uint32_t)hl * 8u + 2u * gi + (sl & 1u));
+              n_ovf += sl >> 1;
+            }
           }
         }
       }
       pos += kept(0xFFFFFFFFu);
     }
   }
+  if (spw && n_ovf) atomicAdd(p.out.slice_ovf + s, n_ovf);      // rare: a group of four consecutive k holding three or four nonzeros
   if (P > 1) k1_finish(p, epoch);
 }
 
@@ -706,6 +724,22 @@ static void launch_slice_n(const SliceArgs& args, int nslices, bool full, bool s
   else spmdm_slice_n_kernel<BF16, false, ROWS, KEEP, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
 }
 
+// the wide bf16 kernel with two words per lane, one CTA per slice, is the only slicing kernel that writes SliceArena::tcsp
+static bool k1_split_env()
+{
+  static const bool split_env = [] { const char* e = getenv("LIBXSMM_B200_K1_SPLIT"); return e && '1' == *e; }();
+  return split_env;
+}
+bool slices_get_sp_words(const SliceArgs& args)
+{
+  if (args.transa || !args.is_bf16 || args.origin_is_block || 0 == args.write_sp || 0 == args.out.tcsp) return false;
+  const bool full = (0 == (args.g.k % 128)) && (args.simd_w > 1);
+  if (!(full && 0 == (args.lda & 7) && 0 == ((uintptr_t)args.a & 15) && 0 == (args.g.k & 7))) return false;
+  const char* wenv = getenv("LIBXSMM_B200_K1_WIDE");
+  const int wide = (wenv && *wenv >= '0' && *wenv <= '2') ? (*wenv - '0') : 2;
+  return wide >= 2 && !k1_split_env();
+}
+
 void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
 {
   if (nslices <= 0) return;
@@ -718,8 +752,7 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
     // LIBXSMM_B200_K1_SPLIT=1: four 8-warp CTAs per slice chained by a decoupled look-back (k1_scan).  Measured on B200 it is
     // SLOWER than one 32-warp CTA per slice (4096^2 bf16: 32.7 vs 23.3 us; 2048^2 fp32: 29.2 vs 19.0 us): the three hops
     // of the look-back cost more than the overlap of the parts' phases gains.  Kept as an experiment, off by default.
-    static const bool split_env = [] { const char* e = getenv("LIBXSMM_B200_K1_SPLIT"); return e && '1' == *e; }();
-    const bool split = split_env && nslices > 1 && !args.origin_is_block && 0 != args.out.lookback && 0 != args.out.epoch;
+    const bool split = k1_split_env() && nslices > 1 && !args.origin_is_block && 0 != args.out.lookback && 0 != args.out.epoch;
     if (args.is_bf16 && full && !args.origin_is_block && 0 == (args.lda & 7) && 0 == ((uintptr_t)args.a & 15) && 0 == (args.g.k & 7)) {
       // complete 128-column blocks, 16-byte aligned rows: the wide kernel (a lane holds 8 elements)
       const char* wenv = getenv("LIBXSMM_B200_K1_WIDE");      // developer switch, read per call (tests flip it)
@@ -1089,6 +1122,7 @@ static int tc_mode()
 static bool launch_tc_bf16(const ComputeArgs& a, cudaStream_t stream)
 {
   const char* e = getenv("LIBXSMM_B200_TC16_PAIR");
+  if (launch_compute_tc16s(a, stream)) return true;      // 2:4 structured-sparse form (low density, slices from the wide kernel)
   if (!(e && '0' == *e) && launch_compute_tc16p(a, stream)) return true;
   return launch_compute_tc16(a, stream);
 }
