@@ -39,7 +39,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
   while (!mbar_try_wait(bar, parity)) { }
 }
-
 // 2-D tiled TMA load: box of the tensor map at element coordinates (c0 = inner/column, c1 = row) -> smem,
 // completion signalled on `bar` as transaction bytes.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)

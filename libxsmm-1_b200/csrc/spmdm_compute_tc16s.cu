@@ -33,20 +33,19 @@ namespace xb {
 constexpr int S_BM = 128;                       // rows per CTA
 constexpr int S_BN = 256;                       // columns per pair tile
 constexpr int S_BNH = 128;                      // columns of B staged per CTA
-constexpr int S_KH = 64;                        // k per B stage
+constexpr int S_KB = 128;                       // k per ring slot = one k-block of the slices
 constexpr int S_NG = 4;                         // worker groups (four warps each) taking k-blocks in turn
-constexpr int S_NB = 8;                         // B stages: at two instructions (~360 clocks) per stage the ring has to cover L2 latency plus the hand-shake
-constexpr int S_NA = S_NG;                      // A k-block buffers: every worker group owns one
+constexpr int S_NA = S_NG;                      // ring slots: every worker group owns one (A tile, metadata image, B stage)
 constexpr int S_NQ = 4;                         // nonzeros per thread and k-block kept in registers
 constexpr int S_NE = 4;                         // epilogue warps (one per TMEM lane quarter)
 constexpr int S_A_BUF = S_BM * 128;             // 16 KiB: 128 rows x 64 kept bf16
 constexpr int S_META = S_BM * 16;               // 2 KiB: per TMEM lane four 32-bit metadata columns
-constexpr int S_B_STAGE = S_KH * S_BNH * 2;     // 16 KiB
+constexpr int S_B_STAGE = S_KB * S_BNH * 2;     // 32 KiB: two column blocks of [128 k x 64 columns]
 constexpr int S_THREADS = (2 + 4 * S_NG + S_NE) * 32;
 constexpr int S_SMEM_A = 0;
 constexpr int S_SMEM_B = S_SMEM_A + S_NA * S_A_BUF;
-constexpr int S_SMEM_META = S_SMEM_B + S_NB * S_B_STAGE;
-constexpr int S_SMEM_STAGE = S_SMEM_META + S_NA * S_META;      // per epilogue warp a [32 rows x 32 columns] fp32 box for the TMA store of C
+constexpr int S_SMEM_META = S_SMEM_B + S_NA * S_B_STAGE;
+constexpr int S_SMEM_STAGE = S_SMEM_META + 2 * S_NA * S_META;         // per epilogue warp a [32 rows x 32 columns] fp32 box for the TMA store of C
 constexpr int S_STAGE = 32 * 128;
 constexpr int S_SMEM_BAR = S_SMEM_STAGE + S_NE * S_STAGE;
 constexpr int S_NOVF = 4;                       // overflow entries of a row an epilogue thread keeps in registers
@@ -74,13 +73,11 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
 {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bar = (uint64_t*)(smem + S_SMEM_BAR);
-  uint64_t* b_full = bar;                   // [NB] leader: both halves of the B stage landed
-  uint64_t* b_free = b_full + S_NB;         // [NB] both: MMAs that read the stage have completed
-  uint64_t* a_ready = b_free + S_NB;        // [NA] leader: the workers of both CTAs built the k-block (tile and metadata)
-  uint64_t* a_free = a_ready + S_NA;        // [NA] both: MMAs that read the k-block have completed
+  uint64_t* a_ready = bar;                  // [NA] leader: the slot is complete -- both B halves landed (bytes) and the workers of both CTAs built A and its metadata
+  uint64_t* a_free = a_ready + S_NA;        // [NA] both: the MMAs that read the slot have completed
   uint64_t* acc_full = a_free + S_NA;       // [2]  both: all MMAs of the tile have completed
   uint64_t* acc_empty = acc_full + 2;       // [2]  leader: the epilogue warps of both CTAs drained the accumulator
-  uint64_t* meta_free = acc_empty + 2;      // [1]  this CTA: the epilogue has read the columns the next tile's metadata goes to
+  uint64_t* meta_free = acc_empty + 2;      // [1]  leader: the epilogue warps of both CTAs have read the columns the next tile's metadata goes to
   uint32_t* tmem_slot = (uint32_t*)(meta_free + 1);
 
   const Geom& g = p.g;
@@ -116,12 +113,10 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
 
   if (0 == tid) {
 #pragma unroll
-    for (int i = 0; i < S_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_free[i], 1); }
-#pragma unroll
-    for (int i = 0; i < S_NA; ++i) { mbar_init(&a_ready[i], 8); mbar_init(&a_free[i], 1); }
+    for (int i = 0; i < S_NA; ++i) { mbar_init(&a_ready[i], 9); mbar_init(&a_free[i], 1); }   // 8 worker warps (two CTAs) + the leader's producer (with the byte count)
 #pragma unroll
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * S_NE); }
-    mbar_init(meta_free, S_NE);
+    mbar_init(meta_free, 2 * S_NE);
     mbar_fence_init();
   }
   if (1 == warp) {
@@ -138,19 +133,19 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     // ---------------- TMA producer: this CTA's 128 columns of every B stage ----------------
     if (0 == lane) {
       tma_prefetch_desc(&tmB);
-      uint32_t gs = 0;
+      uint32_t gk = 0;
       for (int wi = 0; wi < nwork; ++wi) {
         const int idx = work_idx(wi), half = work_half(wi);
         const int n0 = (idx / pair_m) * S_BN + (half < 0 ? (int)rank * S_BNH : half * S_BNH + (int)rank * (S_BNH / 2));
-        for (int t = 0; t < 2 * nkb; ++t, ++gs) {
-          const uint32_t s = gs % S_NB, f = gs / S_NB;
-          if (f > 0) mbar_wait(&b_free[s], (f - 1) & 1);
-          if (p.debug_flags & 2) { if (0 == rank) mbar_arrive(&b_full[s]); continue; }     // timing aid: no B loads
-          if (0 == rank) mbar_arrive_expect_tx(&b_full[s], half < 0 ? 2 * S_B_STAGE : S_B_STAGE);
-          const uint32_t lbar = map_to_cta(&b_full[s], 0);
-          unsigned char* dst = smem + S_SMEM_B + s * S_B_STAGE;
-          tma_load_2d_pair(dst, &tmB, n0, t * S_KH, lbar);                         // 64 k-rows x 64 columns
-          if (half < 0) tma_load_2d_pair(dst + S_KH * 128, &tmB, n0 + 64, t * S_KH, lbar);
+        for (int kbi = 0; kbi < nkb; ++kbi, ++gk) {
+          const uint32_t j = gk % S_NA, f = gk / S_NA;
+          if (f > 0) mbar_wait(&a_free[j], (f - 1) & 1);
+          if (p.debug_flags & 2) { if (0 == rank) mbar_arrive(&a_ready[j]); continue; }     // timing aid: no B loads
+          if (0 == rank) mbar_arrive_expect_tx(&a_ready[j], half < 0 ? 2 * S_B_STAGE : S_B_STAGE);
+          const uint32_t lbar = map_to_cta(&a_ready[j], 0);
+          unsigned char* dst = smem + S_SMEM_B + j * S_B_STAGE;
+          tma_load_2d_pair(dst, &tmB, n0, kbi * S_KB, lbar);                       // 128 k-rows x 64 columns
+          if (half < 0) tma_load_2d_pair(dst + S_KB * 128, &tmB, n0 + 64, kbi * S_KB, lbar);
         }
       }
     }
@@ -160,14 +155,17 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     if (0 == rank && 0 == lane) {
       // sparse A, D = F32, A = B = BF16, A K-major (compressed), B MN-major, N = 256, M = 256 (pair)
       const uint32_t idesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(S_BN >> 3) << 17) | ((uint32_t)((2 * S_BM) >> 4) << 24);
-      uint32_t gs = 0, gk = 0;
+      uint32_t gk = 0;
       const bool prof = (p.debug_flags & 32) && 0 == pair;       // developer aid: where does the issuing thread wait?
-      long long t_a = 0, t_b = 0, t_acc = 0, t0 = 0, t_begin = prof ? clock64() : 0;
+      long long t_a = 0, t_acc = 0, t0 = 0, t_begin = prof ? clock64() : 0;
+      unsigned long long ns_begin = 0, ns_end = 0;
+      if (prof) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(ns_begin));
       for (int wi = 0; wi < nwork; ++wi) {
         const uint32_t acc = (uint32_t)wi & 1u;
         const uint32_t idesc_w = (work_half(wi) < 0) ? idesc : ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(S_BNH >> 3) << 17));
         if (prof) t0 = clock64();
         if (wi >= 2) mbar_wait(&acc_empty[acc], (((uint32_t)wi >> 1) - 1u) & 1u);
+        if (wi >= 1) mbar_wait(meta_free, (uint32_t)(wi - 1) & 1u);    // the epilogue of the previous tile has read the columns this tile's metadata goes to
         if (prof) t_acc += clock64() - t0;
         tc_fence_after();
         const uint32_t tacc = tmem_d + acc * S_BN, tmeta = tmem_d + (acc ^ 1u) * S_BN;
@@ -176,31 +174,28 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
           if (prof) t0 = clock64();
           mbar_wait(&a_ready[j], (gk / S_NA) & 1);
           if (prof) t_a += clock64() - t0;
-          const uint32_t a_base = sbase + S_SMEM_A + j * S_A_BUF;
+          tc_fence_after();
+          const uint32_t a_base = sbase + S_SMEM_A + j * S_A_BUF, b_base = sbase + S_SMEM_B + j * S_B_STAGE;
+          // the slot's metadata image (128 lanes x 16 bytes, lane L at byte 16 L) into its four tensor-memory columns, in both
+          // CTAs; executes in order with the MMAs that follow
+          if (!(p.debug_flags & 16)) {
+            const uint64_t dm = tc_smem_desc(sbase + S_SMEM_META + (2u * j + ((gk / S_NA) & 1u)) * S_META, 16, 128, 0);
+            asm volatile("tcgen05.cp.cta_group::2.128x128b [%0], %1;\n" ::"r"(tmeta + 4u * j), "l"(dm) : "memory");
+          }
 #pragma unroll
-          for (int h = 0; h < 2; ++h, ++gs) {
-            const uint32_t s = gs % S_NB;
-            if (prof) t0 = clock64();
-            mbar_wait(&b_full[s], (gs / S_NB) & 1);
-            if (prof) t_b += clock64() - t0;
-            tc_fence_after();
-            const uint32_t b_base = sbase + S_SMEM_B + s * S_B_STAGE;
-            // the metadata of atoms 2h, 2h + 1 lives in columns +2h, +2h + 1: the address names the even column, the
+          for (int ks = 0; ks < 4; ++ks) {         // K = 32 (16 kept elements = 32 bytes of the compressed row) per instruction
+            // the metadata of atom ks lives in column ks of the slot's four: the address names the even column, the
             // descriptor's selector bit the odd one
-            const uint32_t te = tmeta + 4u * j + 2u * (uint32_t)h;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {       // K = 32 (16 kept elements = 32 bytes of the compressed row) per instruction
-              const uint64_t da = tc_smem_desc(a_base + (2 * h + ks) * 32, 16, 1024, 2);
-              const uint64_t db = tc_smem_desc(b_base + ks * 4096, (uint32_t)(S_KH * 128), 1024, 2);
-              if (!(p.debug_flags & 16)) tc_mma_bf16_sp_pair(tacc, da, db, te, idesc_w | (uint32_t)ks, (kbi > 0 || h > 0 || ks > 0) ? 1u : 0u);
-            }
-            tc_commit_pair(&b_free[s]);
+            const uint64_t da = tc_smem_desc(a_base + ks * 32, 16, 1024, 2);
+            const uint64_t db = tc_smem_desc(b_base + ks * 4096, (uint32_t)(S_KB * 128), 1024, 2);
+            if (!(p.debug_flags & 16)) tc_mma_bf16_sp_pair(tacc, da, db, tmeta + 4u * j + (uint32_t)(ks & 2), idesc_w | (uint32_t)(ks & 1), (kbi > 0 || ks > 0) ? 1u : 0u);
           }
           tc_commit_pair(&a_free[j]);
         }
         tc_commit_pair(&acc_full[acc]);
       }
-      if (prof) printf("K4s issuer, pair 0: %d tiles, %u k-blocks, %lld clocks; waiting for A %lld, B %lld, accumulator %lld\n", nwork, gk, clock64() - t_begin, t_a, t_b, t_acc);
+      if (prof) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(ns_end));
+      if (prof) printf("K4s issuer, pair 0: %llu ns, %d tiles, %u k-blocks, %lld clocks; waiting for the slot %lld, accumulator %lld\n", ns_end - ns_begin, nwork, gk, clock64() - t_begin, t_a, t_acc);
     }
   }
   else if (warp < 2 + 4 * S_NG) {
@@ -208,7 +203,6 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     const int grp = (warp - 2) >> 2;
     const int wt = (tid - 64) & (S_BM - 1);
     const size_t cap = (size_t)g.bm * g.bk;
-    const uint32_t my_lane_t = (uint32_t)((warp & 3) * 32 + lane);       // the tensor-memory lane this thread can write
     const uint32_t lead_ready0 = map_to_cta(&a_ready[0], 0);
     // byte offset of the 16-bit metadata word of (row, 16-k span) inside the image, from the position of a kept element:
     // tensor-memory lane = row % 8 + 8 * (span % 2) + 16 * (row / 16), column = span / 2, upper half word for rows 8..15 of 16
@@ -238,20 +232,19 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     };
     while (c_kb >= nkb && c_wi < nwork) { c_kb -= nkb; ++c_wi; }
     seat();
-    long long f_a = 0, f_b = 0, f_c = 0; const bool fprof = (p.debug_flags & 32) && 0 == pair && 0 == rank && 0 == grp && 0 == wt;
     struct Ptr { int pf, sidx; };
-    // rw: xb_tc16_pack word (the bf16 value in its upper half), sw: the structured-sparse word; hs: what this thread put
-    // into the buffer the last time
-    struct Raw { int sidx, first, last, n_old; uint32_t rw[S_NQ]; uint32_t sw[S_NQ]; uint32_t hs[S_NQ]; };
+    // rw: xb_tc16_pack word (the bf16 value in its upper half), sw: the structured-sparse word.  Two sets: the loads of a
+    // k-block are issued two of this group's steps before they are used.  hs / n_old: what this thread put into the group's
+    // slot the last time.
+    struct Raw { int sidx, first, last; uint32_t rw[S_NQ]; uint32_t sw[S_NQ]; };
+    uint32_t hs[S_NQ]; int n_old = 0;
     auto fetch_ptrs = [&](Ptr& P) {
       P.pf = 0; P.sidx = c_sidx;
       if (c_rows > 0 && lane < 3) P.pf = (int)__ldg(c_ro + (0 == lane ? 0 : (1 == lane ? c_rows : c_rows - 1)));
       advance();
     };
     auto fetch = [&](Raw& R, Ptr& P) {
-      long long f0 = fprof ? clock64() : 0;
       const int pf = __shfl_sync(0xffffffffu, P.pf, 0), pl = __shfl_sync(0xffffffffu, P.pf, 1), pm = __shfl_sync(0xffffffffu, P.pf, 2);
-      if (fprof) { f_a += clock64() - f0 + (pf & 0); f0 = clock64(); }
       R.sidx = P.sidx; R.first = pf;
       R.last = (pl < pf) ? pm : pl;            // wrapped u16 counter of a full slice: the last row reads as empty
       const uint32_t* pw = p.sl.tcpk + R.sidx * cap;
@@ -263,26 +256,22 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         R.rw[i] = 0; R.sw[i] = 0;
         if (q < R.last) { R.rw[i] = __ldg(pw + q); R.sw[i] = __ldg(ps + q); }
       }
-      if (fprof) { f_b += clock64() - f0; f0 = clock64(); }
       fetch_ptrs(P);
-      if (fprof) f_c += clock64() - f0;
     };
     const uint32_t gk_end = (uint32_t)nwork * (uint32_t)nkb;
     const bool wprof = (p.debug_flags & 32) && 0 == pair && 0 == rank && 0 == grp && 0 == wt;
-    long long w_free = 0, w_meta = 0, w_patch = 0, w_st = 0, w_fetch = 0, w_t0 = 0, w_begin = wprof ? clock64() : 0;
-    uint32_t w_tile = 0, w_next = (uint32_t)nkb;       // tile (of this pair's list) the k-block gk belongs to: gk in [w_next - nkb, w_next)
+    long long w_free = 0, w_patch = 0, w_st = 0, w_fetch = 0, w_t0 = 0, w_begin = wprof ? clock64() : 0;
     auto step = [&](uint32_t gk, Raw& R, Ptr& P) {
       if (gk >= gk_end) return;
-      while (gk >= w_next) { ++w_tile; w_next += (uint32_t)nkb; }
       const uint32_t j = gk % S_NA;
       unsigned char* abuf = smem + S_SMEM_A + j * S_A_BUF;
-      unsigned char* mimg = smem + S_SMEM_META + j * S_META;
+      unsigned char* mimg = smem + S_SMEM_META + (2u * j + ((gk / S_NA) & 1u)) * S_META;
       const int n = R.last - R.first;
-      const bool idle = 0 != (p.debug_flags & 1);      // timing aid: hand the buffer over untouched
-      // ---- while the tensor core still reads the buffer: the k-block's metadata image (nobody but this group reads it) ----
-      // Stale metadata needs no clearing: a nibble whose two kept elements are zero contributes nothing wherever it points.
+      const bool idle = 0 != (p.debug_flags & 1);      // timing aid: hand the slot over untouched
+      // ---- while the tensor core still reads the slot: the k-block's metadata image.  Two images per slot: the copy of the
+      // other one into tensor memory may still be in flight.  Stale metadata needs no clearing: a nibble whose two kept
+      // elements are zero contributes nothing wherever it points.
       if (wprof) w_t0 = clock64();
-      uint4 mv = make_uint4(0, 0, 0, 0);
       if (!idle) {
 #pragma unroll
         for (int i = 0; i < S_NQ; ++i) {
@@ -294,16 +283,14 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
 #pragma unroll 2
           for (int q = R.first + wt + S_NQ * S_BM; q < R.last; q += S_BM) { const uint32_t s = __ldg(ps + q); *(uint16_t*)(mimg + meta_off(s & 0x1FFFu)) = (uint16_t)(s >> 16); }
         }
-        asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_BM) : "memory");   // the image is complete
-        mv = *(const uint4*)(mimg + my_lane_t * 16u);
       }
       if (wprof) { w_patch += clock64() - w_t0; w_t0 = clock64(); }
-      // ---- the buffer is ours once the MMAs of the k-block that used it have completed ----
+      // ---- the slot is ours once the MMAs of the k-block that used it have completed ----
       if (gk >= S_NA) mbar_wait(&a_free[j], ((gk / S_NA) - 1) & 1);
       if (wprof) { w_free += clock64() - w_t0; w_t0 = clock64(); }
       if (!idle) {
         // clear the kept elements the previous k-block left behind (a dense one is wiped)
-        if (R.n_old > S_NQ * S_BM) {
+        if (n_old > S_NQ * S_BM) {
           uint4* z = (uint4*)abuf;
 #pragma unroll
           for (int i = 0; i < S_A_BUF / 16 / S_BM; ++i) z[wt + i * S_BM] = make_uint4(0, 0, 0, 0);
@@ -311,27 +298,21 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         else {
 #pragma unroll
           for (int i = 0; i < S_NQ; ++i) {
-            if (i * S_BM >= R.n_old) break;                  // uniform
-            if (wt + i * S_BM < R.n_old) *(uint16_t*)(abuf + ((R.hs[i] & 0x1FFFu) << 1)) = 0;
+            if (i * S_BM >= n_old) break;                    // uniform
+            if (wt + i * S_BM < n_old) *(uint16_t*)(abuf + ((hs[i] & 0x1FFFu) << 1)) = 0;
           }
         }
-        // the tile accumulates into buffer w_tile & 1; its metadata goes to the head of the other one, once the epilogue of
-        // the previous tile has read those columns (a completed phase answers at once)
-        if (w_tile >= 1) { mbar_wait(meta_free, (w_tile - 1u) & 1u); tc_fence_after(); }
-        if (wprof) { w_meta += clock64() - w_t0; w_t0 = clock64(); }
-        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + ((w_tile & 1u) ^ 1u) * S_BN + 4u * j;
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(mv.x), "r"(mv.y), "r"(mv.z), "r"(mv.w) : "memory");
         asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_BM) : "memory");   // another thread may write where this one cleared
 #pragma unroll
         for (int i = 0; i < S_NQ; ++i) {
           if (i * S_BM >= n) break;                          // uniform
           if (wt + i * S_BM < n) {
             const uint32_t s = R.sw[i];
-            if (0 == (s & 0x8000u)) *(uint16_t*)(abuf + ((s & 0x1FFFu) << 1)) = (uint16_t)(R.rw[i] >> 16);   // overflow entries: the CUDA-core pass
-            R.hs[i] = s;
+            if (0 == (s & 0x8000u)) *(uint16_t*)(abuf + ((s & 0x1FFFu) << 1)) = (uint16_t)(R.rw[i] >> 16);   // overflow entries: the row's epilogue thread
+            hs[i] = s;
           }
         }
-        R.n_old = n;
+        n_old = n;
         if (n > S_NQ * S_BM) {
           const uint32_t* pw = p.sl.tcpk + R.sidx * cap;
           const uint32_t* ps = p.sl.tcsp + R.sidx * cap;
@@ -341,39 +322,39 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
             if (0 == (s & 0x8000u)) *(uint16_t*)(abuf + ((s & 0x1FFFu) << 1)) = (uint16_t)(w >> 16);
           }
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-        tc_fence_before();
         fence_proxy_async();
       }
       __syncwarp();
       if (0 == lane) mbar_arrive_cluster(lead_ready0 + j * 8);
       if (wprof) { w_st += clock64() - w_t0; w_t0 = clock64(); }
-      fetch(R, P);                   // after the hand-over: this group's next k-block
+      fetch(R, P);                   // after the hand-over: the k-block of this group's step after next
       if (wprof) w_fetch += clock64() - w_t0;
     };
-    Ptr pa; Raw ra;
-    ra.n_old = 0;
+    Ptr pa, pb; Raw ra, rb;
 #pragma unroll
-    for (int i = 0; i < S_NQ; ++i) ra.hs[i] = 0;
-    fetch_ptrs(pa);
+    for (int i = 0; i < S_NQ; ++i) hs[i] = 0;
+    fetch_ptrs(pa); fetch_ptrs(pb);            // this group's first two k-blocks
     // the A buffer starts out zero and is only ever patched; the metadata image starts out as "kept elements at 0, 1"
     {
       uint4* z = (uint4*)(smem + S_SMEM_A + grp * S_A_BUF);
 #pragma unroll 4
       for (int i = 0; i < S_A_BUF / 16 / S_BM; ++i) z[wt + i * S_BM] = make_uint4(0, 0, 0, 0);
-      ((uint4*)(smem + S_SMEM_META + grp * S_META))[wt] = make_uint4(0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u);
+      ((uint4*)(smem + S_SMEM_META + 2 * grp * S_META))[wt] = make_uint4(0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u);
+      ((uint4*)(smem + S_SMEM_META + (2 * grp + 1) * S_META))[wt] = make_uint4(0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u);
     }
     asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_BM) : "memory");
-    fetch(ra, pa);
-    for (uint32_t gk = (uint32_t)grp; gk < gk_end; gk += S_NG) step(gk, ra, pa);
-    if (wprof) printf("K4s worker group 0: %lld clocks; waiting for the buffer %lld, for the metadata columns %lld; metadata image %lld, clear / store / patch / hand-over %lld, fetch %lld\n", clock64() - w_begin, w_free, w_meta, w_patch, w_st, w_fetch);
-    if (wprof) printf("   fetch: pointer shuffles %lld, nonzero loads %lld, next pointers %lld\n", f_a, f_b, f_c);
+    fetch(ra, pa); fetch(rb, pb);              // their nonzeros; pa / pb now hold the pointers of the two after
+    for (uint32_t gk = (uint32_t)grp; gk < gk_end; gk += 2 * S_NG) {
+      step(gk, ra, pa);
+      step(gk + S_NG, rb, pb);
+    }
+    if (wprof) printf("K4s worker group 0: %lld clocks; waiting for the slot %lld; metadata image %lld, clear / patch / hand-over %lld, fetch %lld\n", clock64() - w_begin, w_free, w_patch, w_st, w_fetch);
   }
   else {
     // ---------------- epilogue: warp owns TMEM lanes 32*(warp % 4) .. +31 of this CTA and half of the tile's columns ----------------
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const uint32_t lead_empty0 = map_to_cta(&acc_empty[0], 0);
+    const uint32_t lead_empty0 = map_to_cta(&acc_empty[0], 0), lead_meta = map_to_cta(meta_free, 0);
     unsigned char* stage = smem + S_SMEM_STAGE + (warp - (2 + 4 * S_NG)) * S_STAGE;
     const size_t cap = (size_t)g.bm * g.bk;
     const uint16_t* Bp = (const uint16_t*)p.b;
@@ -443,7 +424,7 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         if (0 == cb) {         // columns 0..31 of this accumulator are read: the next tile's metadata may go there
           tc_fence_before();
           __syncwarp();
-          if (0 == lane) mbar_arrive(meta_free);
+          if (0 == lane) mbar_arrive_cluster(lead_meta);
         }
         if (many) scan([&](int k, float a) { add_row(v, cb, k, a); });   // rows with many overflow entries (a dense matrix forced onto this kernel): the whole warp walks the slices again
         else if (ne > 0) {     // rare
@@ -527,7 +508,7 @@ bool launch_compute_tc16s(const ComputeArgs& a, cudaStream_t stream)
   if (!(env && '1' == *env) && !(a.density_hint >= 0.f && a.density_hint <= kSpMaxDensity)) return false;
   if (!a.transc && (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3))) return false;
   CUtensorMap map;
-  if (!make_tensor_map_2d_sw128(&map, a.b, 2, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 2, 64, S_KH, false)) return false;
+  if (!make_tensor_map_2d_sw128(&map, a.b, 2, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 2, 64, S_KB, false)) return false;
   ensure_smem_optin((const void*)spmdm_compute_tc16s_kernel, S_SMEM_BYTES);
   const int pairs_max = device_sm_count() / 2 > 0 ? device_sm_count() / 2 : 1;
   const int tiles_per_mb = (a.g.bm + S_BM - 1) / S_BM;
