@@ -13,20 +13,30 @@
 //     tile, the 16-bit metadata word of its row's 16-k span, and whether it is an OVERFLOW entry (third / fourth nonzero
 //     of its group);
 //   * the workers of this kernel patch the compressed tile (128 rows x 64 kept bf16 = 16 KiB per 128-k block, half of
-//     K4p's) and a 2 KiB image of the block's metadata in shared memory, then move that image into tensor memory
-//     (tcgen05.st, four columns per k-block) -- the layout was pinned with tools/umma_probe/probe_sp.cu;
+//     K4p's) and a 2 KiB image of the block's metadata in shared memory (tensor-memory lane L at byte 16 L); the issuing
+//     thread copies the image into four tensor-memory columns with tcgen05.cp right in front of the block's four MMAs.
+//     Layout and nibble semantics were pinned with tools/umma_probe/probe_sp.cu;
 //   * the overflow entries are added by the epilogue thread that owns the row (value * B[k, :] onto the accumulator it
 //     drains, slices in ascending k-block, entries in ascending k): deterministic, correct at ANY density (it just gets
 //     slow when many groups overflow, which is why the host only picks this kernel for matrices its density estimate puts
 //     below kSpMaxDensity).  A first version did this in a second kernel: 16-27 us for a handful of rows.
+// One ring slot per k-block holds everything the tensor core needs for it (A tile, metadata images, this CTA's 128 k x 128
+// columns of B): the issuing thread waits once and commits once per k-block -- with separate A and B rings (three waits,
+// three commits per k-block) it could not keep the instruction queue fed at 181 clocks per instruction (87 -> 78 us).
 // The accumulator is double buffered in tensor memory like K4p's (a first version with one accumulator and a separate
-// metadata ring ran every SM through its store phase at the same time: 30 us of HBM-write-bound epilogues for 4096^3).
+// metadata ring ran every SM through its store phase at the same time: 30 us of HBM-write-bound epilogues for 4096^3), so
+// tensor memory is full; the metadata columns of a tile are the first 16 columns of the accumulator it does NOT use, once
+// the epilogue of the previous tile has read them.  C leaves through TMA boxes when it is only written (the epilogue's
+// scattered 16-byte stores held up the workers' loads and stores in the load / store unit: 97 -> 88 us).
 // Roles per CTA (22 warps): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only) and TMEM owner, warps 2-17 workers
-// (four groups taking k-blocks in turn, one A buffer each), warps 18-21 epilogue.  Same 1e-2 contract as K4p (observed 1e-6).
+// (four groups taking k-blocks in turn, one slot each), warps 18-21 epilogue.  Same 1e-2 contract as K4p (observed 1e-6).
+// LIBXSMM_B200_K4S_DEBUG (developer timing aid, results are wrong when set): 1 no worker work, 2 no B loads, 4 no C
+// stores, 16 no tensor-core instructions.  What they show on C2 (78 us): without workers 70, without stores 73, without
+// MMAs 61, the bare hand-shake skeleton 48 -- the ring of four slots is one slot short of hiding the round trip
+// commit -> 144 waiters wake -> patch -> remote arrive, and shared memory (208 of 227 KiB in the ring) has no room for a fifth.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
-#include <cstdio>
 
 namespace xb {
 
@@ -156,24 +166,16 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       // sparse A, D = F32, A = B = BF16, A K-major (compressed), B MN-major, N = 256, M = 256 (pair)
       const uint32_t idesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(S_BN >> 3) << 17) | ((uint32_t)((2 * S_BM) >> 4) << 24);
       uint32_t gk = 0;
-      const bool prof = (p.debug_flags & 32) && 0 == pair;       // developer aid: where does the issuing thread wait?
-      long long t_a = 0, t_acc = 0, t0 = 0, t_begin = prof ? clock64() : 0;
-      unsigned long long ns_begin = 0, ns_end = 0;
-      if (prof) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(ns_begin));
       for (int wi = 0; wi < nwork; ++wi) {
         const uint32_t acc = (uint32_t)wi & 1u;
         const uint32_t idesc_w = (work_half(wi) < 0) ? idesc : ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(S_BNH >> 3) << 17));
-        if (prof) t0 = clock64();
         if (wi >= 2) mbar_wait(&acc_empty[acc], (((uint32_t)wi >> 1) - 1u) & 1u);
         if (wi >= 1) mbar_wait(meta_free, (uint32_t)(wi - 1) & 1u);    // the epilogue of the previous tile has read the columns this tile's metadata goes to
-        if (prof) t_acc += clock64() - t0;
         tc_fence_after();
         const uint32_t tacc = tmem_d + acc * S_BN, tmeta = tmem_d + (acc ^ 1u) * S_BN;
         for (int kbi = 0; kbi < nkb; ++kbi, ++gk) {
           const uint32_t j = gk % S_NA;
-          if (prof) t0 = clock64();
           mbar_wait(&a_ready[j], (gk / S_NA) & 1);
-          if (prof) t_a += clock64() - t0;
           tc_fence_after();
           const uint32_t a_base = sbase + S_SMEM_A + j * S_A_BUF, b_base = sbase + S_SMEM_B + j * S_B_STAGE;
           // the slot's metadata image (128 lanes x 16 bytes, lane L at byte 16 L) into its four tensor-memory columns, in both
@@ -194,8 +196,6 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         }
         tc_commit_pair(&acc_full[acc]);
       }
-      if (prof) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(ns_end));
-      if (prof) printf("K4s issuer, pair 0: %llu ns, %d tiles, %u k-blocks, %lld clocks; waiting for the slot %lld, accumulator %lld\n", ns_end - ns_begin, nwork, gk, clock64() - t_begin, t_a, t_acc);
     }
   }
   else if (warp < 2 + 4 * S_NG) {
@@ -259,8 +259,6 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       fetch_ptrs(P);
     };
     const uint32_t gk_end = (uint32_t)nwork * (uint32_t)nkb;
-    const bool wprof = (p.debug_flags & 32) && 0 == pair && 0 == rank && 0 == grp && 0 == wt;
-    long long w_free = 0, w_patch = 0, w_st = 0, w_fetch = 0, w_t0 = 0, w_begin = wprof ? clock64() : 0;
     auto step = [&](uint32_t gk, Raw& R, Ptr& P) {
       if (gk >= gk_end) return;
       const uint32_t j = gk % S_NA;
@@ -271,7 +269,6 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       // ---- while the tensor core still reads the slot: the k-block's metadata image.  Two images per slot: the copy of the
       // other one into tensor memory may still be in flight.  Stale metadata needs no clearing: a nibble whose two kept
       // elements are zero contributes nothing wherever it points.
-      if (wprof) w_t0 = clock64();
       if (!idle) {
 #pragma unroll
         for (int i = 0; i < S_NQ; ++i) {
@@ -284,10 +281,8 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
           for (int q = R.first + wt + S_NQ * S_BM; q < R.last; q += S_BM) { const uint32_t s = __ldg(ps + q); *(uint16_t*)(mimg + meta_off(s & 0x1FFFu)) = (uint16_t)(s >> 16); }
         }
       }
-      if (wprof) { w_patch += clock64() - w_t0; w_t0 = clock64(); }
       // ---- the slot is ours once the MMAs of the k-block that used it have completed ----
       if (gk >= S_NA) mbar_wait(&a_free[j], ((gk / S_NA) - 1) & 1);
-      if (wprof) { w_free += clock64() - w_t0; w_t0 = clock64(); }
       if (!idle) {
         // clear the kept elements the previous k-block left behind (a dense one is wiped)
         if (n_old > S_NQ * S_BM) {
@@ -326,9 +321,7 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       }
       __syncwarp();
       if (0 == lane) mbar_arrive_cluster(lead_ready0 + j * 8);
-      if (wprof) { w_st += clock64() - w_t0; w_t0 = clock64(); }
       fetch(R, P);                   // after the hand-over: the k-block of this group's step after next
-      if (wprof) w_fetch += clock64() - w_t0;
     };
     Ptr pa, pb; Raw ra, rb;
 #pragma unroll
@@ -348,7 +341,6 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       step(gk, ra, pa);
       step(gk + S_NG, rb, pb);
     }
-    if (wprof) printf("K4s worker group 0: %lld clocks; waiting for the slot %lld; metadata image %lld, clear / patch / hand-over %lld, fetch %lld\n", clock64() - w_begin, w_free, w_patch, w_st, w_fetch);
   }
   else {
     // ---------------- epilogue: warp owns TMEM lanes 32*(warp % 4) .. +31 of this CTA and half of the tile's columns ----------------
