@@ -173,9 +173,11 @@ static void slice_policy(SpmdmCtx* c, SliceArgs* a, int is_bf16, bool whole, cud
   if (is_bf16 && a->write_aux) {
     if (0 == c->arena.tcsp && !capturing) {
       const size_t bytes = (size_t)c->g.mb * c->g.kb * (size_t)c->g.bm * c->g.bk * 4;
-      if (cudaSuccess != cudaMalloc((void**)&c->arena.tcsp, bytes)) { (void)cudaGetLastError(); c->arena.tcsp = 0; }
+      const size_t list_bytes = (size_t)c->g.mb * c->g.kb * xb::kSpOvfCap * sizeof(uint2);
+      if (cudaSuccess != cudaMalloc((void**)&c->arena.tcsp, bytes + list_bytes)) { (void)cudaGetLastError(); c->arena.tcsp = 0; }
+      else c->arena.ovf_list = (uint2*)((char*)c->arena.tcsp + bytes);
     }
-    a->out.tcsp = c->arena.tcsp;
+    a->out.tcsp = c->arena.tcsp; a->out.ovf_list = c->arena.ovf_list;
     a->write_sp = c->arena.tcsp ? 1 : 0;
   }
   c->sp_written = slices_get_sp_words(*a);
@@ -431,7 +433,7 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena.epoch = (uint32_t*)((char*)c->arena.lookback + lb_bytes);
   c->arena.slice_ovf = (uint32_t*)((char*)c->arena.epoch + 256);
   XB_CUDA(cudaMemset(c->arena.slice_nnz, 0, nnz_bytes + lb_bytes + 256 + nnz_bytes));
-  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->sp_written = false; c->captured = false; c->dense_bytes = 0; c->arena.dense = 0; c->arena.tcsp = 0;
+  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->sp_written = false; c->captured = false; c->dense_bytes = 0; c->arena.dense = 0; c->arena.tcsp = 0; c->arena.ovf_list = 0;
   if (cudaSuccess == cudaHostAlloc((void**)&c->h_nnz, sizeof(unsigned long long), cudaHostAllocMapped)) {
     *c->h_nnz = ~0ull;
     if (cudaSuccess != cudaHostGetDevicePointer((void**)&c->d_nnz, c->h_nnz, 0)) c->d_nnz = 0;

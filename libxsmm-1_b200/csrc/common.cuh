@@ -45,6 +45,7 @@ struct SliceArena {
                      // goes in the tensor-core branch's shared-memory A tile (fp32 slices: xb_tc_pack)
   uint32_t* tcpk;    // the same memory seen as 32-bit words (bf16 slices: xb_tc16_pack, value and position in one word)
   uint32_t* slice_ovf;   // auxiliary: overflow entries (see tcsp) of every slice, written by the slicing kernel that writes tcsp
+  uint2* ovf_list;       // auxiliary: the first kSpOvfCap overflow entries of every slice, in no particular order: {row in the slice | k in the slice << 16, value bits}
   uint32_t* tcsp;    // auxiliary, bf16 slices sliced by the wide kernel: one more word per nonzero for the 2:4 structured-sparse
                      // tensor-core kernel (spmdm_compute_tc16s.cu): metadata of the row's 16-k span << 16 | overflow << 15 |
                      // position of the kept element in the compressed A tile (xb_sp_pos)
@@ -105,6 +106,8 @@ __host__ __device__ __forceinline__ uint32_t xb_sp_slot(uint32_t gm, uint32_t p)
   return rank >= 2u ? 3u : rank;
 }
 #endif
+
+constexpr int kSpOvfCap = 256;        // overflow entries listed per slice (SliceArena::ovf_list); a slice with more is walked by its row pointers instead
 
 constexpr int kSliceStripRows = 64;   // rows of one slice handled by one CTA of the slicing kernel
 

@@ -65,7 +65,8 @@ constexpr int S_SMEM_BYTES = S_SMEM_BAR + 256;
 // in the first columns of the accumulator the tile does NOT accumulate into: that accumulator belongs to the epilogue of the
 // previous tile, which drains those columns first and says so (meta_free); the next tile's first MMA overwrites them only
 // after this tile's MMAs, issued before it, have read them.
-constexpr float kSpMaxDensity = 0.06f;          // above it the overflow pass costs more than the sparse instruction saves
+constexpr float kSpMaxDensity = 0.022f;         // measured crossover with K4p on 4096^3 (tools/crossover_sp.py): 0.5 % 70 / 95 us, 1 % 74 / 97, 2 % 90 / 101, 3 % 117 / 103 --
+                                                // the workers' patching (three shared-memory stores per nonzero) and the overflow entries grow with the density
 
 struct SpTile { int mbi, ml0, rows, n0; };
 
@@ -395,14 +396,38 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
           }
         }
       };
+      // The slicing kernel lists the overflow entries of a slice (the first kSpOvfCap, in no particular order): a thread reads
+      // the lists of the flagged slices (same address for all lanes), keeps the entries of its row -- sorted by k, slices come
+      // in ascending k-block -- and falls back to walking the row pointers (scan) when a slice has more entries than the list
+      // holds or the row more than S_NOVF.
       int ne = 0, ok[S_NOVF]; float ov[S_NOVF];
 #pragma unroll
-      for (int i = 0; i < S_NOVF; ++i) { ok[i] = 0; ov[i] = 0.f; }
-      scan([&](int k, float a) {
+      for (int i = 0; i < S_NOVF; ++i) { ok[i] = 0x7FFFFFFF; ov[i] = 0.f; }
+      for (int kb0 = 0; kb0 < nkb; kb0 += 32) {
+        const int kbl = kb0 + lane;
+        const uint32_t cnt = (kbl < nkb) ? __ldg(p.sl.slice_ovf + kbl * g.mb + t.mbi) : 0u;
+        uint32_t flagged = __ballot_sync(0xffffffffu, 0 != cnt);
+        for (; flagged; flagged &= flagged - 1u) {
+          const int src = __ffs((int)flagged) - 1, kb = kb0 + src;
+          const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
+          if (c > (uint32_t)kSpOvfCap) { ne = S_NOVF + 1; continue; }
+          const uint2* lst = p.sl.ovf_list + ((size_t)kb * g.mb + t.mbi) * kSpOvfCap;
+          for (uint32_t e = 0; e < c; ++e) {
+            const uint2 w = __ldg(lst + e);
+            if (rvalid && (int)(w.x & 0xFFFFu) == rl) {
+              const int k = kb * g.bk + (int)(w.x >> 16);
+              if (ne < S_NOVF) {       // insert by ascending k (entries of one slice come in any order)
+                int ck = k; float cv = __uint_as_float(w.y);
 #pragma unroll
-        for (int i = 0; i < S_NOVF; ++i) if (i == ne) { ok[i] = k; ov[i] = a; }
-        ++ne;
-      });
+                for (int i = 0; i < S_NOVF; ++i) {
+                  if (ck < ok[i]) { const int tk = ok[i]; const float tv = ov[i]; ok[i] = ck; ov[i] = cv; ck = tk; cv = tv; }
+                }
+              }
+              ++ne;
+            }
+          }
+        }
+      }
       const bool many = 0 != __any_sync(0xffffffffu, ne > S_NOVF);     // warp-uniform: scan() votes
       // C box by TMA: every row of this warp belongs to the tile, C is not read, rows are 16-byte aligned
       const bool use_tma = (0 != c_tma) && (t.rows >= quarter * 32 + 32);
@@ -495,7 +520,7 @@ bool launch_compute_tc16s(const ComputeArgs& a, cudaStream_t stream)
 {
   const char* env = getenv("LIBXSMM_B200_TC16_SPARSE");      // "0": never, "1": whenever the slices carry the words, else: by density
   if (env && '0' == *env) return false;
-  if (0 == a.aux_valid || 0 == a.sp_valid || 0 == a.sl.tcsp || 0 == a.sl.slice_ovf) return false;
+  if (0 == a.aux_valid || 0 == a.sp_valid || 0 == a.sl.tcsp || 0 == a.sl.slice_ovf || 0 == a.sl.ovf_list) return false;
   if (!a.is_bf16 || a.transb) return false;
   if (!(env && '1' == *env) && !(a.density_hint >= 0.f && a.density_hint <= kSpMaxDensity)) return false;
   if (!a.transc && (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3))) return false;

@@ -650,7 +650,6 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   // whose nibbles make one 16-bit metadata word of the row, so everything is known to the lane (common.cuh: xb_sp_*)
   const bool spw = (2 == NW) && (0 != p.write_sp) && (0 != p.out.tcsp);
   uint32_t* sp = p.out.tcsp + (size_t)s * g.bm * g.bk;
-  uint32_t n_ovf = 0;
 #pragma unroll
   for (int it = 0; it < ITS; ++it) {
     if (row_lo + RPI * it < row_hi) {      // warp-uniform
@@ -699,7 +698,10 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
               const uint32_t p16 = 8u * (uint32_t)j + (uint32_t)e, gi = p16 >> 2;
               const uint32_t sl = xb_sp_slot((m >> (4u * gi)) & 15u, p16 & 3u);
               sp[q] = meta16 | ((sl & 2u) << 14) | xb_sp_pos(rowm, (uint32_t)hl * 8u + 2u * gi + (sl & 1u));
-              n_ovf += sl >> 1;
+              if (sl & 2u) {       // rare: third / fourth nonzero of its group of four.  Counted per slice; the first kSpOvfCap are listed
+                const uint32_t idx = atomicAdd(p.out.slice_ovf + s, 1u);
+                if (idx < (uint32_t)kSpOvfCap) p.out.ovf_list[(size_t)s * kSpOvfCap + idx] = make_uint2((uint32_t)r | ((k0 + 8u * (uint32_t)j + (uint32_t)e) << 16), vb);
+              }
             }
           }
         }
@@ -707,7 +709,6 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
       pos += kept(0xFFFFFFFFu);
     }
   }
-  if (spw && n_ovf) atomicAdd(p.out.slice_ovf + s, n_ovf);      // rare: a group of four consecutive k holding three or four nonzeros
   if (P > 1) k1_finish(p, epoch);
 }
 
