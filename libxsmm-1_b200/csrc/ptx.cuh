@@ -39,6 +39,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
   while (!mbar_try_wait(bar, parity)) { }
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the
+// kernel before it in the stream is still running; pdl_wait() returns once that kernel has completed and its writes are visible
+// (at once when the launch carried no such attribute), pdl_trigger() lets the kernel after this one start being scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // 2-D tiled TMA load: box of the tensor map at element coordinates (c0 = inner/column, c1 = row) -> smem,
 // completion signalled on `bar` as transaction bytes.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)

@@ -3,6 +3,7 @@
 //   K2  spmdm_compute_kernel  C = beta*C + slices * B (reference compute templates)
 // Hand-written CUDA; no library calls on the data path.
 #include "common.cuh"
+#include "ptx.cuh"
 #include <map>
 #include <cooperative_groups.h>
 #include <mutex>
@@ -594,6 +595,10 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   constexpr int MB = 8 * NW;                 // mask bits per lane and iteration
   constexpr int P = 32 / CW;                 // CTAs per slice (k1_scan)
   __shared__ uint32_t wtot[CW + 1];
+  // programmatic dependent launch (launch_slices): the slices this kernel overwrites may still be read by the multiply in front of
+  // it in the stream -- wait for it before anything else; the multiply behind it may be scheduled from now on (it waits in turn)
+  pdl_wait();
+  pdl_trigger();
   const Geom& g = p.g;
   const uint32_t epoch = (P > 1) ? k1_epoch(p) : 0u;
   const int part = (int)blockIdx.x % P;
@@ -763,8 +768,16 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
           if (rpw <= 8) spmdm_slice_bf16x_kernel<8, 2, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
           else spmdm_slice_bf16x_kernel<16, 2, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
         }
-        else if (rpw <= 8) spmdm_slice_bf16x_kernel<8, 2, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
-        else spmdm_slice_bf16x_kernel<16, 2, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+        else {
+          static const bool pdl = [] { const char* e = getenv("LIBXSMM_B200_PDL"); return !(e && '0' == *e); }();
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3((unsigned)nslices); cfg.blockDim = dim3(K1N_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+          if (rpw <= 8) XB_CUDA(cudaLaunchKernelEx(&cfg, spmdm_slice_bf16x_kernel<8, 2, 32>, args));
+          else XB_CUDA(cudaLaunchKernelEx(&cfg, spmdm_slice_bf16x_kernel<16, 2, 32>, args));
+        }
         XB_CUDA(cudaGetLastError());
         return;
       }
