@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   constexpr int MB = 8 * NW;                 // mask bits per lane and iteration
   constexpr int P = 32 / CW;                 // CTAs per slice (k1_scan)
   __shared__ uint32_t wtot[CW + 1];
+  __shared__ uint2 stage[(2 == NW) ? CW : 1][32];        // per warp: the records of up to 32 outputs (stage and spread, phase 2)
   // programmatic dependent launch (launch_slices): the slices this kernel overwrites may still be read by the multiply in front of
   // it in the stream -- wait for it before anything else; the multiply behind it may be scheduled from now on (it waits in turn)
   pdl_wait();
@@ -648,6 +649,7 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   float* va = p.out.values + (size_t)s * g.bm * g.bk;
   uint32_t* rk = p.out.tcpk + (size_t)s * g.bm * g.bk;
   const uint32_t lt = (1u << lane) - 1u;
+  uint2* stg = stage[(2 == NW) ? warp : 0];
   const uint32_t rowmask = ((1u << LPR) - 1u) << (LPR * qr);   // the lanes of this lane's row
   const uint32_t before = (1u << (LPR * qr)) - 1u;             // the lanes of the rows above it in the group
   const bool aux = (0 != p.write_aux);
@@ -677,16 +679,63 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
       const uint32_t rowpos = pos + kept(before);
       const int r = row_lo + RPI * it + qr;
       if (0 == hl && r < row_hi) ro[r] = (uint16_t)rowpos;
+      if (2 == NW) {
+        // Stage and spread.  In the sparse regime a handful of the 32 lanes hold a nonzero or two, and everything a nonzero costs
+        // (four stores, the positions in the tensor-core tiles, the metadata word) would run once per loop trip of the fullest
+        // lane with one to three lanes active.  Instead every lane drops its kept elements as 8-byte records {value | its 16-bit
+        // mask, element | lane << 4} at their output index into the warp's shared-memory stage (a short divergent loop), and lane
+        // t then does all the work for output t: one pass per 32 outputs.
+        const uint32_t tot = kept(0xFFFFFFFFu);
+        if (tot) {                                        // warp-uniform
+          const uint32_t ex = kept(lt);                   // this lane's first output of the iteration (lane order = (row, column) order)
+          for (uint32_t c0 = 0; c0 < tot; c0 += 32u) {    // one chunk below ~6 % density
+            if (m) {
+              uint32_t i = ex - c0;
+#pragma unroll
+              for (int j = 0; j < NW; ++j) {
+                const uint32_t v[4] = { w[it][j].x, w[it][j].y, w[it][j].z, w[it][j].w };
+                for (uint32_t mm = (m >> (8 * j)) & 0xFFu; mm; mm &= mm - 1u, ++i) {
+                  if (i < 32u) {                          // unsigned: outputs before this chunk wrap around
+                    const int e = __ffs((int)mm) - 1;
+                    const uint32_t pr = (e & 4) ? ((e & 2) ? v[3] : v[2]) : ((e & 2) ? v[1] : v[0]);
+                    const uint32_t vb = (e & 1) ? (pr & 0xFFFF0000u) : (pr << 16);
+                    stg[i] = make_uint2(vb | m, (uint32_t)(8 * j + e) | ((uint32_t)lane << 4));
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (c0 + (uint32_t)lane < tot) {
+              const uint2 rec = stg[lane];
+              const uint32_t vb = rec.x & 0xFFFF0000u, ms = rec.x & 0xFFFFu, e16 = rec.y & 15u, sl = rec.y >> 4;
+              const uint32_t rs = (uint32_t)(row_lo + RPI * it) + sl / LPR, hs = sl % LPR, rowm = rs & 127u, k = hs * 16u + e16;
+              const uint32_t q = pos + c0 + (uint32_t)lane;
+              co[q] = (uint16_t)k;
+              va[q] = __uint_as_float(vb);
+              if (aux) rk[q] = xb_tc16_pack((int)rs, (int)k, vb);
+              if (spw) {
+                uint32_t meta16 = 0;
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) meta16 |= xb_sp_nibble((ms >> (4 * gi)) & 15u) << (16 + 4 * gi);
+                const uint32_t gi = e16 >> 2, slot = xb_sp_slot((ms >> (4u * gi)) & 15u, e16 & 3u);
+                sp[q] = meta16 | ((slot & 2u) << 14) | xb_sp_pos(rowm, hs * 8u + 2u * gi + (slot & 1u));
+                if (slot & 2u) {     // rare: third / fourth nonzero of its group of four.  Counted per slice; the first kSpOvfCap are listed
+                  const uint32_t idx = atomicAdd(p.out.slice_ovf + s, 1u);
+                  if (idx < (uint32_t)kSpOvfCap) p.out.ovf_list[(size_t)s * kSpOvfCap + idx] = make_uint2(rs | (k << 16), vb);
+                }
+              }
+            }
+            __syncwarp();                                 // the stage is rewritten by the next chunk / iteration
+          }
+        }
+        pos += tot;
+        continue;
+      }
       if (m) {   // few lanes hold nonzeros in the sparse regime
         uint32_t q = rowpos + kept(lt & rowmask);
         const uint32_t rowm = (uint32_t)r & 127u;
         const uint32_t k0 = (uint32_t)hl * (8u * NW);                  // first column of this lane
         const uint32_t rbase = ((k0 >> 6) << 15) | ((rowm >> 3) * 512u + (rowm & 7u) * 64u);
-        uint32_t meta16 = 0;
-        if (spw) {
-#pragma unroll
-          for (int gi = 0; gi < 4; ++gi) meta16 |= xb_sp_nibble((m >> (4 * gi)) & 15u) << (16 + 4 * gi);
-        }
 #pragma unroll
         for (int j = 0; j < NW; ++j) {             // the lane's 16-byte words: k = k0 + 8 * j + e
           const uint32_t v[4] = { w[it][j].x, w[it][j].y, w[it][j].z, w[it][j].w };
@@ -699,15 +748,6 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
             co[q] = (uint16_t)(k0 + 8u * j + (uint32_t)e);
             va[q] = __uint_as_float(vb);
             if (aux) rk[q] = vb | (base16 + (uint32_t)e);
-            if (spw) {
-              const uint32_t p16 = 8u * (uint32_t)j + (uint32_t)e, gi = p16 >> 2;
-              const uint32_t sl = xb_sp_slot((m >> (4u * gi)) & 15u, p16 & 3u);
-              sp[q] = meta16 | ((sl & 2u) << 14) | xb_sp_pos(rowm, (uint32_t)hl * 8u + 2u * gi + (sl & 1u));
-              if (sl & 2u) {       // rare: third / fourth nonzero of its group of four.  Counted per slice; the first kSpOvfCap are listed
-                const uint32_t idx = atomicAdd(p.out.slice_ovf + s, 1u);
-                if (idx < (uint32_t)kSpOvfCap) p.out.ovf_list[(size_t)s * kSpOvfCap + idx] = make_uint2((uint32_t)r | ((k0 + 8u * (uint32_t)j + (uint32_t)e) << 16), vb);
-              }
-            }
           }
         }
       }
