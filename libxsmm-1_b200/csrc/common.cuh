@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 namespace xb {
 
@@ -204,6 +205,23 @@ __device__ __forceinline__ unsigned long long xb_total_nnz(const uint32_t* slice
   }
   __syncthreads();
   return xb_nnz_s;
+}
+#endif
+
+#if defined(__CUDACC__)
+// Launch with programmatic stream serialization: the grid may be scheduled while the kernel in front of it in the stream is
+// still draining; the kernel itself waits (ptx.cuh: pdl_wait) before it touches anything that kernel wrote or still reads.
+// LIBXSMM_B200_PDL=0: plain stream order.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+  static const bool pdl = [] { const char* e = getenv("LIBXSMM_B200_PDL"); return !(e && '0' == *e); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif
 

@@ -57,6 +57,7 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   const Geom& g = p.g;
+  if (p.tc_twin > 0) pdl_wait();        // the twin decision reads the slices' counts
   if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // uniform over the grid
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank();
@@ -108,6 +109,7 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  if (p.tc_twin <= 0) pdl_wait();       // barriers, tensor memory and the cluster hand-shake were set up while the kernel in front was still finishing
 
   if (0 == warp) {
     // ---------------- TMA producer: this CTA's 128 columns of every B stage ----------------
@@ -381,8 +383,7 @@ bool launch_compute_tc16p(const ComputeArgs& a, cudaStream_t stream)
   const int pairs = total < pairs_max ? total : pairs_max;
   count_launch(1);
   note_compute_kernel("spmdm_compute_tc16p_kernel");
-  spmdm_compute_tc16p_kernel<<<dim3(2u * (unsigned)pairs), P_THREADS, P_SMEM_BYTES, stream>>>(map, a);
-  XB_CUDA(cudaGetLastError());
+  XB_CUDA(launch_pdl(spmdm_compute_tc16p_kernel, dim3(2u * (unsigned)pairs), dim3(P_THREADS), P_SMEM_BYTES, stream, map, a));   // may be scheduled while the slicing kernel drains (pdl_wait in the kernel)
   return true;
 }
 

@@ -563,14 +563,8 @@ bool launch_compute_tc16s(const ComputeArgs& a, cudaStream_t stream)
   ComputeArgs a2 = a;
   if (const char* dbg = getenv("LIBXSMM_B200_K4S_DEBUG")) a2.debug_flags = atoi(dbg);   // developer timing aid: results are wrong when set
   // programmatic dependent launch: the CTAs may be scheduled, and run their prologue, while the kernel in front of this one
-  // (normally the slicing kernel) is still draining; LIBXSMM_B200_PDL=0: plain stream order
-  static const bool pdl = [] { const char* e = getenv("LIBXSMM_B200_PDL"); return !(e && '0' == *e); }();
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2u * (unsigned)pairs); cfg.blockDim = dim3(S_THREADS); cfg.dynamicSmemBytes = S_SMEM_BYTES; cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  XB_CUDA(cudaLaunchKernelEx(&cfg, spmdm_compute_tc16s_kernel, map, cmap, c_tma, a2));
+  // (normally the slicing kernel) is still draining
+  XB_CUDA(launch_pdl(spmdm_compute_tc16s_kernel, dim3(2u * (unsigned)pairs), dim3(S_THREADS), S_SMEM_BYTES, stream, map, cmap, c_tma, a2));
   return true;
 }
 

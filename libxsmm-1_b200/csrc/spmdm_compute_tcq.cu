@@ -55,6 +55,7 @@ spmdm_compute_tcq_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_c
   uint32_t* tmem_slot = (uint32_t*)(bar + 17);
 
   const Geom& g = p.g;
+  if (p.tc_twin > 0) pdl_wait();        // the twin decision reads the slices' counts
   if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // sparse: the CUDA-core twin multiplies (uniform over the grid)
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank();
@@ -89,6 +90,7 @@ spmdm_compute_tcq_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_c
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  if (p.tc_twin <= 0) pdl_wait();       // barriers, tensor memory and the cluster hand-shake were set up while the kernel in front was still finishing
 
   if (0 == warp) {
     // ---------------- producer: this CTA's A half per step, its B chunk per 32 k ----------------
@@ -286,8 +288,7 @@ bool launch_compute_tcq(const ComputeArgs& a, cudaStream_t stream)
   if (total <= 0) return true;
   count_launch(1);
   note_compute_kernel("spmdm_compute_tcq_kernel");
-  spmdm_compute_tcq_kernel<<<dim3(2u * (unsigned)total), Q_THREADS, Q_SMEM_BYTES, stream>>>(mapB, mapA, a);
-  XB_CUDA(cudaGetLastError());
+  XB_CUDA(launch_pdl(spmdm_compute_tcq_kernel, dim3(2u * (unsigned)total), dim3(Q_THREADS), Q_SMEM_BYTES, stream, mapB, mapA, a));   // may be scheduled while the slicing kernel drains (pdl_wait in the kernel)
   return true;
 }
 

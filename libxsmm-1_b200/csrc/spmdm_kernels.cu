@@ -354,6 +354,8 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_n_ker
   typedef typename Raw::raw_t raw_t;
   constexpr int P = 32 / CW;
   __shared__ uint32_t wtot[CW + 1];
+  pdl_wait();          // launch_pdl: the slices may still be read by the multiply in front of this kernel in the stream
+  pdl_trigger();       // ... and the multiply behind it may be scheduled (it waits in turn)
   const Geom& g = p.g;
   const uint32_t epoch = (P > 1) ? k1_epoch(p) : 0u;
   const int part = (int)blockIdx.x % P;
@@ -766,8 +768,8 @@ static void launch_slice_n(const SliceArgs& args, int nslices, bool full, bool s
     if (full) spmdm_slice_n_kernel<BF16, true, ROWS, KEEP, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
     else spmdm_slice_n_kernel<BF16, false, ROWS, KEEP, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
   }
-  else if (full) spmdm_slice_n_kernel<BF16, true, ROWS, KEEP, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
-  else spmdm_slice_n_kernel<BF16, false, ROWS, KEEP, 32><<<(unsigned)nslices, K1N_THREADS, 0, stream>>>(args);
+  else if (full) XB_CUDA(launch_pdl(spmdm_slice_n_kernel<BF16, true, ROWS, KEEP, 32>, dim3((unsigned)nslices), dim3(K1N_THREADS), 0, stream, args));
+  else XB_CUDA(launch_pdl(spmdm_slice_n_kernel<BF16, false, ROWS, KEEP, 32>, dim3((unsigned)nslices), dim3(K1N_THREADS), 0, stream, args));
 }
 
 // the wide bf16 kernel with two words per lane, one CTA per slice, is the only slicing kernel that writes SliceArena::tcsp
@@ -809,14 +811,8 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
           else spmdm_slice_bf16x_kernel<16, 2, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
         }
         else {
-          static const bool pdl = [] { const char* e = getenv("LIBXSMM_B200_PDL"); return !(e && '0' == *e); }();
-          cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = dim3((unsigned)nslices); cfg.blockDim = dim3(K1N_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-          cudaLaunchAttribute at[1];
-          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-          cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-          if (rpw <= 8) XB_CUDA(cudaLaunchKernelEx(&cfg, spmdm_slice_bf16x_kernel<8, 2, 32>, args));
-          else XB_CUDA(cudaLaunchKernelEx(&cfg, spmdm_slice_bf16x_kernel<16, 2, 32>, args));
+          if (rpw <= 8) XB_CUDA(launch_pdl(spmdm_slice_bf16x_kernel<8, 2, 32>, dim3((unsigned)nslices), dim3(K1N_THREADS), 0, stream, args));
+          else XB_CUDA(launch_pdl(spmdm_slice_bf16x_kernel<16, 2, 32>, dim3((unsigned)nslices), dim3(K1N_THREADS), 0, stream, args));
         }
         XB_CUDA(cudaGetLastError());
         return;
