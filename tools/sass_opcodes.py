@@ -4,7 +4,7 @@ import collections, os, re, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "libxsmm-1_b200", "lib", "libxsmm_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-keys = ['UTCHMMA', 'UTCQMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMAPF', 'UBLKCP', 'SYNCS', 'FHFMA', 'FFMA', 'DFMA', 'HMMA', 'LDGSTS', 'REDUX', 'UTCBAR']
+keys = ['UTCHMMA', 'UTCQMMA', 'UTCCP', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'UBLKCP', 'SYNCS', 'FHFMA', 'FFMA', 'DFMA', 'HMMA', 'LDGSTS', 'REDUX', 'UTCBAR']
 rows = []
 for p in re.split(r'\n\s*Function : ', txt)[1:]:
     name = p.split('\n', 1)[0].strip()
@@ -23,6 +23,9 @@ for p in re.split(r'\n\s*Function : ', txt)[1:]:
                 ops['UTCHMMA.2CTA'] += 1
     rows.append((dem, n, ops))
 out = ["# SASS opcode counts per kernel of libxsmm-1_b200/lib/libxsmm_b200.so (cuobjdump -sass, sm_100a)",
+       "# tcgen05.mma.sp (2:4 structured-sparse A, spmdm_compute_tc16s_kernel) is the SAME opcode: sparsity is bit 2 of the instruction descriptor; what tells it apart",
+       "# is UTCCP = tcgen05.cp (the metadata image -> tensor memory) next to it and ncu's sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_on counter",
+       "# (profiles/r02_ncu_full_c2_compute_tc16s.json).  UTMASTG = TMA tensor store,",
        "# UTCHMMA = tcgen05.mma (UTCHMMA.2CTA: cta_group::2), LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA tensor load (cp.async.bulk.tensor),",
        "# UTMAPF = TMA L2 prefetch, SYNCS = mbarrier operations, FHFMA = mixed-precision fma.rn.f32.bf16 (K2s), DFMA = fp64 fma, LDGSTS = cp.async.",
        "# The baked fsspmdm kernels (register and strip form) are emitted as PTX at create time and assembled by the driver: they are not",
