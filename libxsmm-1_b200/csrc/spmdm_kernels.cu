@@ -597,7 +597,8 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   constexpr int MB = 8 * NW;                 // mask bits per lane and iteration
   constexpr int P = 32 / CW;                 // CTAs per slice (k1_scan)
   __shared__ uint32_t wtot[CW + 1];
-  __shared__ uint2 stage[(2 == NW) ? CW : 1][32];        // per warp: the records of up to 32 outputs (stage and spread, phase 2)
+  constexpr int SCAP = 64;                                // records per warp: all 16 rows of a warp at once up to 3 % density
+  __shared__ uint2 stage[(2 == NW) ? CW : 1][SCAP];      // per warp: the records of its outputs (stage and spread, phase 2)
   // programmatic dependent launch (launch_slices): the slices this kernel overwrites may still be read by the multiply in front of
   // it in the stream -- wait for it before anything else; the multiply behind it may be scheduled from now on (it waits in turn)
   pdl_wait();
@@ -636,6 +637,7 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  const uint32_t warp_total = mine;
   if (2 == NW && 1 == P && 0 == tid && p.write_sp && p.out.tcsp) p.out.slice_ovf[s] = 0;   // counted below, after the scan's barrier
   const K1Scan sc = k1_scan<CW>(p, s, part, mine, wtot, epoch);
   uint32_t pos = sc.pos;
@@ -659,6 +661,26 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   // whose nibbles make one 16-bit metadata word of the row, so everything is known to the lane (common.cuh: xb_sp_*)
   const bool spw = (2 == NW) && (0 != p.write_sp) && (0 != p.out.tcsp);
   uint32_t* sp = p.out.tcsp + (size_t)s * g.bm * g.bk;
+  uint32_t wdone = 0;                      // outputs of this warp's earlier iterations
+  const uint32_t pos0 = pos;               // first output of this warp
+  auto spread = [&](const uint2 rec, const uint32_t q) {      // everything one output costs, by whichever lane gets it
+    const uint32_t vb = rec.x & 0xFFFF0000u, ms = rec.x & 0xFFFFu, e16 = rec.y & 15u, sl = (rec.y >> 4) & 31u, its = rec.y >> 9;
+    const uint32_t rs = (uint32_t)row_lo + (uint32_t)RPI * its + sl / LPR, hs = sl % LPR, rowm = rs & 127u, k = hs * 16u + e16;
+    co[q] = (uint16_t)k;
+    va[q] = __uint_as_float(vb);
+    if (aux) rk[q] = xb_tc16_pack((int)rs, (int)k, vb);
+    if (spw) {
+      uint32_t meta16 = 0;
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) meta16 |= xb_sp_nibble((ms >> (4 * gi)) & 15u) << (16 + 4 * gi);
+      const uint32_t gi = e16 >> 2, slot = xb_sp_slot((ms >> (4u * gi)) & 15u, e16 & 3u);
+      sp[q] = meta16 | ((slot & 2u) << 14) | xb_sp_pos(rowm, hs * 8u + 2u * gi + (slot & 1u));
+      if (slot & 2u) {     // rare: third / fourth nonzero of its group of four.  Counted per slice; the first kSpOvfCap are listed
+        const uint32_t idx = atomicAdd(p.out.slice_ovf + s, 1u);
+        if (idx < (uint32_t)kSpOvfCap) p.out.ovf_list[(size_t)s * kSpOvfCap + idx] = make_uint2(rs | (k << 16), vb);
+      }
+    }
+  };
 #pragma unroll
   for (int it = 0; it < ITS; ++it) {
     if (row_lo + RPI * it < row_hi) {      // warp-uniform
@@ -685,52 +707,36 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
         // Stage and spread.  In the sparse regime a handful of the 32 lanes hold a nonzero or two, and everything a nonzero costs
         // (four stores, the positions in the tensor-core tiles, the metadata word) would run once per loop trip of the fullest
         // lane with one to three lanes active.  Instead every lane drops its kept elements as 8-byte records {value | its 16-bit
-        // mask, element | lane << 4} at their output index into the warp's shared-memory stage (a short divergent loop), and lane
-        // t then does all the work for output t: one pass per 32 outputs.
+        // mask, element | lane << 4 | iteration << 9} at their output index into the warp's shared-memory stage (a short
+        // divergent loop), and lane t then does all the work for output t.  When the warp's 16 rows hold at most SCAP nonzeros
+        // (always below 3 % density) all four iterations are staged first and spread in one pass after the loop.
         const uint32_t tot = kept(0xFFFFFFFFu);
         if (tot) {                                        // warp-uniform
           const uint32_t ex = kept(lt);                   // this lane's first output of the iteration (lane order = (row, column) order)
+          const bool all_at_once = warp_total <= (uint32_t)SCAP;
           for (uint32_t c0 = 0; c0 < tot; c0 += 32u) {    // one chunk below ~6 % density
             if (m) {
-              uint32_t i = ex - c0;
+              uint32_t i = all_at_once ? (wdone + ex) : (ex - c0);
 #pragma unroll
               for (int j = 0; j < NW; ++j) {
                 const uint32_t v[4] = { w[it][j].x, w[it][j].y, w[it][j].z, w[it][j].w };
                 for (uint32_t mm = (m >> (8 * j)) & 0xFFu; mm; mm &= mm - 1u, ++i) {
-                  if (i < 32u) {                          // unsigned: outputs before this chunk wrap around
+                  if (all_at_once || i < 32u) {           // unsigned: outputs before this chunk wrap around
                     const int e = __ffs((int)mm) - 1;
                     const uint32_t pr = (e & 4) ? ((e & 2) ? v[3] : v[2]) : ((e & 2) ? v[1] : v[0]);
                     const uint32_t vb = (e & 1) ? (pr & 0xFFFF0000u) : (pr << 16);
-                    stg[i] = make_uint2(vb | m, (uint32_t)(8 * j + e) | ((uint32_t)lane << 4));
+                    stg[i] = make_uint2(vb | m, (uint32_t)(8 * j + e) | ((uint32_t)lane << 4) | ((uint32_t)it << 9));
                   }
                 }
               }
             }
+            if (all_at_once) break;
             __syncwarp();
-            if (c0 + (uint32_t)lane < tot) {
-              const uint2 rec = stg[lane];
-              const uint32_t vb = rec.x & 0xFFFF0000u, ms = rec.x & 0xFFFFu, e16 = rec.y & 15u, sl = rec.y >> 4;
-              const uint32_t rs = (uint32_t)(row_lo + RPI * it) + sl / LPR, hs = sl % LPR, rowm = rs & 127u, k = hs * 16u + e16;
-              const uint32_t q = pos + c0 + (uint32_t)lane;
-              co[q] = (uint16_t)k;
-              va[q] = __uint_as_float(vb);
-              if (aux) rk[q] = xb_tc16_pack((int)rs, (int)k, vb);
-              if (spw) {
-                uint32_t meta16 = 0;
-#pragma unroll
-                for (int gi = 0; gi < 4; ++gi) meta16 |= xb_sp_nibble((ms >> (4 * gi)) & 15u) << (16 + 4 * gi);
-                const uint32_t gi = e16 >> 2, slot = xb_sp_slot((ms >> (4u * gi)) & 15u, e16 & 3u);
-                sp[q] = meta16 | ((slot & 2u) << 14) | xb_sp_pos(rowm, hs * 8u + 2u * gi + (slot & 1u));
-                if (slot & 2u) {     // rare: third / fourth nonzero of its group of four.  Counted per slice; the first kSpOvfCap are listed
-                  const uint32_t idx = atomicAdd(p.out.slice_ovf + s, 1u);
-                  if (idx < (uint32_t)kSpOvfCap) p.out.ovf_list[(size_t)s * kSpOvfCap + idx] = make_uint2(rs | (k << 16), vb);
-                }
-              }
-            }
+            if (c0 + (uint32_t)lane < tot) spread(stg[lane], pos + c0 + (uint32_t)lane);
             __syncwarp();                                 // the stage is rewritten by the next chunk / iteration
           }
         }
-        pos += tot;
+        pos += tot; wdone += tot;
         continue;
       }
       if (m) {   // few lanes hold nonzeros in the sparse regime
@@ -755,6 +761,11 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
       }
       pos += kept(0xFFFFFFFFu);
     }
+  }
+  if (2 == NW && warp_total <= (uint32_t)SCAP && warp_total > 0) {     // all iterations staged: one spread pass
+    __syncwarp();
+    for (uint32_t c0 = 0; c0 < warp_total; c0 += 32u)
+      if (c0 + (uint32_t)lane < warp_total) spread(stg[c0 + lane], pos0 + c0 + (uint32_t)lane);
   }
   if (P > 1) k1_finish(p, epoch);
 }
