@@ -157,3 +157,26 @@ def test_handle_reuse_keeps_results_deterministic(gpu, monkeypatch):
     assert np.array_equal(res[0].view(np.uint32), res[2].view(np.uint32))
     p.destroy()
     gpu.check()
+
+
+@pytest.mark.parametrize("shape,density,beta,tc", [((2048, 1024, 512), 0.01, 0, "N"), ((1200, 1000, 640), 0.02, 1, "N"), ((1024, 768, 384), 0.015, 0, "T")])
+def test_exec_host_rectangles(gpu, oracle, monkeypatch, shape, density, beta, tc):
+    """the whole-multiply host entry cuts C into row blocks x column panels: the structured-sparse kernel on sub-rectangles
+    (first row block > 0, column origin > 0, ragged last panel), C boxes by TMA into a panel of a wider C."""
+    force(monkeypatch)
+    xs = gpu
+    M, N, K = shape
+    A, B, C0 = xs.workloads.spmdm_inputs(M, N, K, density, dtype="bf16", seed=9, transc=tc)
+    h, s = xs.libxsmm_spmdm_init(M, N, K, 1)
+    try:
+        import pyoracle
+        g = pyoracle.Geometry(dict(m=h.m, n=h.n, k=h.k, bm=h.bm, bn=h.bn, bk=h.bk, mb=h.mb, nb=h.nb, kb=h.kb))
+        og, osl, OC = oracle_spmdm(oracle, g, A, B, C0, "N", "N", tc, float(beta))
+        for rep in range(2):
+            C = C0.copy()
+            xs.libxsmm_spmdm_exec_host(h, s, xs.LIBXSMM_SPMDM_DATATYPE_BFLOAT16, "N", "N", tc, A, B, beta, C)
+            xs.check()
+            assert xs.last_compute_kernel() == K4S
+            assert rel(C, OC) <= 1e-5
+    finally:
+        xs.libxsmm_spmdm_destroy(h)
