@@ -7,4 +7,4 @@ timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k re
 # (c) launch list of the bench command
 timeout -s KILL 300 python bench.py --steps 2 --warmup 3 --others '' --sharded '' --no-cpu > gpurun_out/plain_bench.log 2>&1 &&
 timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_launches_c2_bench.csv python bench.py --steps 2 --warmup 3 --others '' --sharded '' --no-cpu > gpurun_out/ncu_bench.log 2>&1
-ls -la gpurun_out/r02_c2_tc16s.ncu-rep gpurun_out/r02_c2_k1x_sp.ncu-rep gpurun_out/r02_launches_c2_bench.csv; tail -2 gpurun_out/ncu_c2s.log gpurun_out/ncu_k1x_sp.log
+ls -la gpurun_out/r02_c2_tc16s.ncu-rep gpurun_out/r02_c2_k1x_sp.ncu-rep gpurun_out/r02_launches_c2_bench.csv; tail -n 2 gpurun_out/ncu_c2s.log
