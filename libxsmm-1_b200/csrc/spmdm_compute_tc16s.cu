@@ -37,7 +37,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
-#include <cstdio>
 
 namespace xb {
 
@@ -92,10 +91,6 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
   uint64_t* meta_free = acc_empty + 2;      // [1]  leader: the epilogue warps of both CTAs have read the columns the next tile's metadata goes to
   uint32_t* tmem_slot = (uint32_t*)(meta_free + 1);
 
-  __shared__ unsigned long long dbg_ns[6];
-  const bool tprof = (p.debug_flags & 32) && 0 == blockIdx.x;
-  auto stamp = [&](int i) { if (tprof) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t)); dbg_ns[i] = t; } };
-  if (0 == threadIdx.x) stamp(0);
   const Geom& g = p.g;
   if (p.tc_twin > 0) pdl_wait();        // the twin decision reads the slices' counts
   if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // uniform over the grid
@@ -176,7 +171,6 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       // sparse A, D = F32, A = B = BF16, A K-major (compressed), B MN-major, N = 256, M = 256 (pair)
       const uint32_t idesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(S_BN >> 3) << 17) | ((uint32_t)((2 * S_BM) >> 4) << 24);
       uint32_t gk = 0;
-      stamp(1);
       for (int wi = 0; wi < nwork; ++wi) {
         const uint32_t acc = (uint32_t)wi & 1u;
         const uint32_t idesc_w = (work_half(wi) < 0) ? idesc : ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(S_BNH >> 3) << 17));
@@ -207,7 +201,6 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         }
         tc_commit_pair(&acc_full[acc]);
       }
-      stamp(2);
     }
   }
   else if (warp < 2 + 4 * S_NG) {
@@ -512,17 +505,11 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       __syncwarp();
       if (0 == lane) mbar_arrive_cluster(lead_empty0 + acc * 8);
     }
-    if (0 == lane && 18 == warp) stamp(3);
     if (0 == lane) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
-    if (0 == lane && 18 == warp) stamp(4);
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();      // the peer's shared memory and barriers stay alive until every MMA and remote arrive has landed
-  if (tprof && 0 == threadIdx.x) {
-    stamp(5);
-    printf("K4s CTA 0 (ns): entry -> issuer loop %llu, loop %llu, loop end -> last tile drained %llu, stores landed %llu, exit %llu; total %llu\n", dbg_ns[1] - dbg_ns[0], dbg_ns[2] - dbg_ns[1], dbg_ns[3] - dbg_ns[2], dbg_ns[4] - dbg_ns[3], dbg_ns[5] - dbg_ns[4], dbg_ns[5] - dbg_ns[0]);
-  }
   if (1 == warp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(512) : "memory");

@@ -594,7 +594,6 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   constexpr int LPR = 16 / NW;               // lanes per row
   constexpr int RPI = 32 / LPR;              // rows per iteration
   constexpr int ITS = (ROWS + RPI - 1) / RPI;
-  constexpr int MB = 8 * NW;                 // mask bits per lane and iteration
   constexpr int P = 32 / CW;                 // CTAs per slice (k1_scan)
   __shared__ uint32_t wtot[CW + 1];
   constexpr int SCAP = 64;                                // records per warp: all 16 rows of a warp at once up to 3 % density
