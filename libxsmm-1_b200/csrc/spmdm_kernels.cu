@@ -588,13 +588,15 @@ __global__ void __launch_bounds__(K1N_THREADS, 1) spmdm_slice_bf16w_kernel(const
 // K1x: the same with NW 16-byte words (8 * NW elements) per lane: a row is 16 / NW lanes and one iteration of the
 // positioning phase covers 2 * NW rows, which divides the number of ballot rounds per slice by NW (the kernel is
 // instruction-issue bound).  Same outputs, bit for bit.  Measured on C2: NW = 1 (K1w) 25.1 us, NW = 2 23.2 us, NW = 4 23.1 us (not instantiated).
-template <int ROWS, int NW, int CW>
-__global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x_kernel(const SliceArgs p)
+// SEQ > 1: one CTA of CW warps walks the 32 / CW parts of its slice one after the other (the running total is the next part's
+// base: no look-back between CTAs), so that two 16-warp CTAs fit an SM and one's loads overlap the other's arithmetic.
+template <int ROWS, int NW, int CW, int SEQ = 1>
+__global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : ((SEQ > 1) ? 2 : 3)) spmdm_slice_bf16x_kernel(const SliceArgs p)
 {
   constexpr int LPR = 16 / NW;               // lanes per row
   constexpr int RPI = 32 / LPR;              // rows per iteration
   constexpr int ITS = (ROWS + RPI - 1) / RPI;
-  constexpr int P = 32 / CW;                 // CTAs per slice (k1_scan)
+  constexpr int P = (SEQ > 1) ? 1 : 32 / CW; // CTAs per slice (k1_scan)
   __shared__ uint32_t wtot[CW + 1];
   constexpr int SCAP = 64;                                // records per warp: all 16 rows of a warp at once up to 3 % density
   __shared__ uint2 stage[(2 == NW) ? CW : 1][SCAP];      // per warp: the records of its outputs (stage and spread, phase 2)
@@ -604,13 +606,16 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
   pdl_trigger();
   const Geom& g = p.g;
   const uint32_t epoch = (P > 1) ? k1_epoch(p) : 0u;
-  const int part = (int)blockIdx.x % P;
   const int s = p.slice0 + ((int)blockIdx.x / P) * p.slice_step;
   const int kb = s / g.mb, mbi = s - kb * g.mb;
   const int nrows = min(g.bm, g.m - mbi * g.bm);
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qr = lane / LPR, hl = lane % LPR;       // row inside the group, segment of the row
   const int rpw = (g.bm + K1N_WARPS - 1) / K1N_WARPS;
+  uint32_t seq_base = 0;                     // SEQ > 1: kept elements of the parts already done
+#pragma unroll 1
+  for (int pass = 0; pass < SEQ; ++pass) {
+  const int part = (SEQ > 1) ? pass : (int)blockIdx.x % P;
   const int row_lo = (part * CW + warp) * rpw, row_hi = min(nrows, row_lo + rpw);
   const long long origin = p.origin_is_block ? 0ll : ((long long)mbi * g.bm * p.lda + (long long)kb * g.bk);
   const uint16_t* A = (const uint16_t*)p.a + origin + hl * (8 * NW);
@@ -637,10 +642,25 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
   const uint32_t warp_total = mine;
-  if (2 == NW && 1 == P && 0 == tid && p.write_sp && p.out.tcsp) p.out.slice_ovf[s] = 0;   // counted below, after the scan's barrier
-  const K1Scan sc = k1_scan<CW>(p, s, part, mine, wtot, epoch);
+  if (2 == NW && 1 == P && 0 == pass && 0 == tid && p.write_sp && p.out.tcsp) p.out.slice_ovf[s] = 0;   // counted below, after the scan's barrier
+  K1Scan sc;
+  if (SEQ > 1) {      // this CTA's parts in sequence: scan of the CW warp totals on top of the running total
+    if (0 == lane) wtot[warp] = mine;
+    __syncthreads();
+    const uint32_t t = (lane < CW) ? wtot[lane] : 0u;
+    uint32_t inc = t;
+#pragma unroll
+    for (int d = 1; d < CW; d <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += u;
+    }
+    sc.pos = seq_base + __shfl_sync(0xffffffffu, inc - t, warp);
+    sc.slice_total = seq_base + __shfl_sync(0xffffffffu, inc, CW - 1);
+    seq_base = sc.slice_total;
+  }
+  else sc = k1_scan<CW>(p, s, part, mine, wtot, epoch);
   uint32_t pos = sc.pos;
-  if (P - 1 == part && 0 == tid) {
+  if (((SEQ > 1) ? (SEQ - 1 == pass) : (P - 1 == part)) && 0 == tid) {
     p.out.rowidx[(size_t)s * (g.bm + 1) + nrows] = (uint16_t)sc.slice_total;   // u16 like the reference's counter
     p.out.slice_nnz[s] = sc.slice_total;
     xb_publish_nnz(p, sc.slice_total);
@@ -766,6 +786,8 @@ __global__ void __launch_bounds__(CW * 32, (32 == CW) ? 1 : 3) spmdm_slice_bf16x
     for (uint32_t c0 = 0; c0 < warp_total; c0 += 32u)
       if (c0 + (uint32_t)lane < warp_total) spread(stg[c0 + lane], pos0 + c0 + (uint32_t)lane);
   }
+  if (SEQ > 1) __syncthreads();             // wtot and the stages are reused by the next part
+  }
   if (P > 1) k1_finish(p, epoch);
 }
 
@@ -821,7 +843,12 @@ void launch_slices(const SliceArgs& args, int nslices, cudaStream_t stream)
           else spmdm_slice_bf16x_kernel<16, 2, 8><<<(unsigned)nslices * 4, 256, 0, stream>>>(args);
         }
         else {
+          // 512-row slices: one 16-warp CTA that does the two halves of its slice one after the other, two such CTAs per SM (all
+          // 256 slices of a 4096^2 matrix resident at once instead of 1.73 waves of 32-warp CTAs).  Same time for the kernel alone
+          // (18.3 us), 1.1 us less per C2 step.  LIBXSMM_B200_K1_SEQ=1 (developer switch, read per call): one 32-warp CTA per slice.
+          const char* seq = getenv("LIBXSMM_B200_K1_SEQ");
           if (rpw <= 8) XB_CUDA(launch_pdl(spmdm_slice_bf16x_kernel<8, 2, 32>, dim3((unsigned)nslices), dim3(K1N_THREADS), 0, stream, args));
+          else if (!(seq && '1' == *seq)) XB_CUDA(launch_pdl(spmdm_slice_bf16x_kernel<16, 2, 16, 2>, dim3((unsigned)nslices), dim3(512), 0, stream, args));
           else XB_CUDA(launch_pdl(spmdm_slice_bf16x_kernel<16, 2, 32>, dim3((unsigned)nslices), dim3(K1N_THREADS), 0, stream, args));
         }
         XB_CUDA(cudaGetLastError());

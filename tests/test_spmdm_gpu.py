@@ -171,12 +171,14 @@ def test_special_values_in_a(gpu, oracle):
     np.testing.assert_array_equal(C[ok].view(np.uint32), OC[ok].view(np.uint32))
 
 
-@pytest.mark.parametrize("wide", ["2", "1", "0"])
+@pytest.mark.parametrize("wide", ["2", "2-one-cta", "1", "0"])
 def test_special_values_bf16_wide_slicing(gpu, oracle, monkeypatch, wide):
     """bf16 bit patterns through the slicing kernels for complete, aligned blocks (two / one 16-byte word per lane,
     generic): +-0, NaN with either sign, +-Inf, denormals, the largest finite value, dense and empty lanes and rows --
     kept iff ordered-nonzero like the reference's vector loops (quirk Q3).  Slices bit for bit against the oracle."""
-    monkeypatch.setenv("LIBXSMM_B200_K1_WIDE", wide)
+    monkeypatch.setenv("LIBXSMM_B200_K1_WIDE", wide[0])
+    if wide.endswith("one-cta"):     # the two-word kernel as one 32-warp CTA per slice instead of a 16-warp CTA doing both halves in turn
+        monkeypatch.setenv("LIBXSMM_B200_K1_SEQ", "1")
     M, N, K = 600, 48, 256           # two complete k-blocks, row pitch 512 B; two row blocks (512 + 88 rows)
     rng = np.random.default_rng(11)
     bits = np.where(rng.random((M, K)) < 0.05, rng.integers(1, 0x7F80, (M, K)), 0).astype(np.uint16)
