@@ -178,6 +178,7 @@ spmdm_compute_sp_kernel(const __grid_constant__ CUtensorMap tmB, const ComputeAr
   uint64_t* empty = full + SP_STAGES;
 
   const Geom& g = p.g;
+  pdl_wait();     // launched with programmatic stream serialization: the CTAs of the first wave are in place when the slicing kernel ends
   if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) >= p.tc_min_nnz) return;   // the tensor-core twin does this multiply (uniform over the grid)
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -391,10 +392,12 @@ bool launch_sp(const ComputeArgs& a, cudaStream_t stream)
   cfg.blockDim = dim3(SP_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = [] { const char* e = getenv("LIBXSMM_B200_PDL"); return !(e && '0' == *e); }();
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
   count_launch(1);
   note_compute_kernel("spmdm_compute_sp_kernel");
   XB_CUDA(cudaLaunchKernelEx(&cfg, kern, map, a));
