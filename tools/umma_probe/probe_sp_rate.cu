@@ -16,7 +16,7 @@ __device__ __forceinline__ uint64_t mkdesc(uint32_t saddr, uint32_t lbo, uint32_
   d |= (uint64_t)layout << 61;
   return d;
 }
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) rate(int sparse, int iters, int n, long long* clocks)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) rate(int sparse, int iters, int n, long long* clocks, int tf32)
 {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
@@ -55,12 +55,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) rate(int spa
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   if (0 == rank && 0 == tid) {
-    const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    // bf16: A K-major, B MN-major; tf32: both K-major (32-byte k-steps inside 128-byte rows)
+    const uint32_t base = tf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24))
+                               : ((1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24));
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       const int ks = it & 3;
       const uint64_t da = mkdesc(smem_u32(sa) + ks * 32, 16, 1024, 2);
-      if (sparse) {
+      if (tf32) {
+        const uint64_t db = mkdesc(smem_u32(sb) + ks * (sparse ? 64 : 32), 16, 1024, 2);   // B K-major: 128 n-rows x 128 B
+        if (sparse) {
+          const uint32_t te = tm + 256 + (ks & ~1), idesc = base | (1u << 2) | (uint32_t)(ks & 1);
+          asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\ttcgen05.mma.sp.cta_group::2.kind::tf32 [%0], %1, %2, [%3], %4, q;\n\t}\n"
+                       ::"r"(tm), "l"(da), "l"(db), "r"(te), "r"(idesc), "r"(it > 0 ? 1u : 0u) : "memory");
+        }
+        else asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, q;\n\t}\n"
+                          ::"r"(tm), "l"(da), "l"(db), "r"(base), "r"(it > 0 ? 1u : 0u) : "memory");
+      }
+      else if (sparse) {
         const uint64_t db = mkdesc(smem_u32(sb) + ks * 4096, 16384, 1024, 2);   // B: [2 column blocks of 64][128 k][128 B]
         const uint32_t te = tm + 256 + (ks & ~1), idesc = base | (1u << 2) | (uint32_t)(ks & 1);
         asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\ttcgen05.mma.sp.cta_group::2.kind::f16 [%0], %1, %2, [%3], %4, q;\n\t}\n"
@@ -94,18 +106,18 @@ int main(int argc, char** argv)
   cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
   long long* dclk; cudaMalloc(&dclk, 128 * 8);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int pairs : { 1, 74 }) for (int n : { 256, 128 }) for (int sparse = 0; sparse < 2; ++sparse) {
+  for (int tf32 = 0; tf32 < 2; ++tf32) for (int pairs : { 74 }) for (int n : { 256 }) for (int sparse = 0; sparse < 2; ++sparse) {
     for (int rep = 0; rep < 2; ++rep) {
       cudaEventRecord(e0);
-      rate<<<2 * pairs, 128, SM>>>(sparse, iters, n, dclk);
+      rate<<<2 * pairs, 128, SM>>>(sparse, iters, n, dclk, tf32);
       cudaEventRecord(e1);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("%s\n", cudaGetErrorString(e)); return 1; }
       if (0 == rep) continue;
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       long long clk; cudaMemcpy(&clk, dclk, 8, cudaMemcpyDeviceToHost);
-      const double flops = 2.0 * 256 * n * (sparse ? 32 : 16) * (double)iters * pairs;
-      printf("pairs=%2d N=%d %s: %.1f clocks per MMA, %.3f ms, dense-equivalent %.3f PFLOP/s\n", pairs, n, sparse ? "sparse K=32" : "dense  K=16",
+      const double flops = 2.0 * 256 * n * (sparse ? 32 : 16) * (tf32 ? 0.5 : 1.0) * (double)iters * pairs;
+      printf("%s pairs=%2d N=%d %s: %.1f clocks per MMA, %.3f ms, dense-equivalent %.3f PFLOP/s\n", tf32 ? "tf32" : "bf16", pairs, n, sparse ? "sparse (2x K)" : "dense       ",
              (double)clk / iters, ms, flops / (ms * 1e-3) * 1e-15);
     }
   }
