@@ -28,12 +28,13 @@
 // tensor memory is full; the metadata columns of a tile are the first 16 columns of the accumulator it does NOT use, once
 // the epilogue of the previous tile has read them.  C leaves through TMA boxes when it is only written (the epilogue's
 // scattered 16-byte stores held up the workers' loads and stores in the load / store unit: 97 -> 88 us).
-// Roles per CTA (22 warps): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only) and TMEM owner, warps 2-17 workers
-// (four groups taking k-blocks in turn, one slot each), warps 18-21 epilogue.  Same 1e-2 contract as K4p (observed 1e-6).
+// Roles per CTA (14 warps): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only) and TMEM owner, warps 2-9 workers
+// (four groups of two warps taking k-blocks in turn, one slot each: with the metadata going through tcgen05.cp a group need
+// not cover the four tensor-memory lane quarters, and 64 waiters per slot wake faster than 128: 68.5 -> 65.9 us), warps 10-13 epilogue.  Same 1e-2 contract as K4p (observed 1e-6).
 // LIBXSMM_B200_K4S_DEBUG (developer timing aid, results are wrong when set): 1 no worker work, 2 no B loads, 4 no C
 // stores, 16 no tensor-core instructions.  What they show on C2 (78 us): without workers 70, without stores 73, without
 // MMAs 61, the bare hand-shake skeleton 48 -- the ring of four slots is one slot short of hiding the round trip
-// commit -> 144 waiters wake -> patch -> remote arrive, and shared memory (208 of 227 KiB in the ring) has no room for a fifth.
+// commit -> waiters wake -> patch -> remote arrive, and shared memory (208 of 227 KiB in the ring) has no room for a fifth.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
@@ -44,14 +45,16 @@ constexpr int S_BM = 128;                       // rows per CTA
 constexpr int S_BN = 256;                       // columns per pair tile
 constexpr int S_BNH = 128;                      // columns of B staged per CTA
 constexpr int S_KB = 128;                       // k per ring slot = one k-block of the slices
-constexpr int S_NG = 4;                         // worker groups (four warps each) taking k-blocks in turn
+constexpr int S_NG = 4;                         // worker groups taking k-blocks in turn
+constexpr int S_GW = 2;                         // warps per worker group (the metadata goes to tensor memory by tcgen05.cp: a group need not cover the four lane quarters)
+constexpr int S_GT = S_GW * 32;                 // threads per worker group
 constexpr int S_NA = S_NG;                      // ring slots: every worker group owns one (A tile, metadata image, B stage)
 constexpr int S_NQ = 4;                         // nonzeros per thread and k-block kept in registers
 constexpr int S_NE = 4;                         // epilogue warps (one per TMEM lane quarter)
 constexpr int S_A_BUF = S_BM * 128;             // 16 KiB: 128 rows x 64 kept bf16
 constexpr int S_META = S_BM * 16;               // 2 KiB: per TMEM lane four 32-bit metadata columns
 constexpr int S_B_STAGE = S_KB * S_BNH * 2;     // 32 KiB: two column blocks of [128 k x 64 columns]
-constexpr int S_THREADS = (2 + 4 * S_NG + S_NE) * 32;
+constexpr int S_THREADS = (2 + S_GW * S_NG + S_NE) * 32;
 constexpr int S_SMEM_A = 0;
 constexpr int S_SMEM_B = S_SMEM_A + S_NA * S_A_BUF;
 constexpr int S_SMEM_META = S_SMEM_B + S_NA * S_B_STAGE;
@@ -125,7 +128,7 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
 
   if (0 == tid) {
 #pragma unroll
-    for (int i = 0; i < S_NA; ++i) { mbar_init(&a_ready[i], 9); mbar_init(&a_free[i], 1); }   // 8 worker warps (two CTAs) + the leader's producer (with the byte count)
+    for (int i = 0; i < S_NA; ++i) { mbar_init(&a_ready[i], 2 * S_GW + 1); mbar_init(&a_free[i], 1); }   // the worker warps of the group in both CTAs + the leader's producer (with the byte count)
 #pragma unroll
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * S_NE); }
     mbar_init(meta_free, 2 * S_NE);
@@ -203,10 +206,10 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       }
     }
   }
-  else if (warp < 2 + 4 * S_NG) {
+  else if (warp < 2 + S_GW * S_NG) {
     // ---------------- workers: group grp (128 threads) builds k-blocks grp, grp + NG, ... ----------------
-    const int grp = (warp - 2) >> 2;
-    const int wt = (tid - 64) & (S_BM - 1);
+    const int grp = (warp - 2) / S_GW;
+    const int wt = (tid - 64) % S_GT;
     const size_t cap = (size_t)g.bm * g.bk;
     const uint32_t lead_ready0 = map_to_cta(&a_ready[0], 0);
     // byte offset of the 16-bit metadata word of (row, 16-k span) inside the image, from the position of a kept element:
@@ -256,8 +259,8 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       const uint32_t* ps = p.sl.tcsp + R.sidx * cap;
 #pragma unroll
       for (int i = 0; i < S_NQ; ++i) {
-        if (R.first + i * S_BM >= R.last) break;           // uniform
-        const int q = R.first + wt + i * S_BM;
+        if (R.first + i * S_GT >= R.last) break;           // uniform
+        const int q = R.first + wt + i * S_GT;
         R.rw[i] = 0; R.sw[i] = 0;
         if (q < R.last) { R.rw[i] = __ldg(pw + q); R.sw[i] = __ldg(ps + q); }
       }
@@ -277,47 +280,47 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       if (!idle) {
 #pragma unroll
         for (int i = 0; i < S_NQ; ++i) {
-          if (i * S_BM >= n) break;                          // uniform
-          if (wt + i * S_BM < n) *(uint16_t*)(mimg + meta_off(R.sw[i] & 0x1FFFu)) = (uint16_t)(R.sw[i] >> 16);
+          if (i * S_GT >= n) break;                          // uniform
+          if (wt + i * S_GT < n) *(uint16_t*)(mimg + meta_off(R.sw[i] & 0x1FFFu)) = (uint16_t)(R.sw[i] >> 16);
         }
-        if (n > S_NQ * S_BM) {         // denser than NQ * 128 nonzeros per tile and k-block: the rest straight from memory
+        if (n > S_NQ * S_GT) {         // denser than NQ * 64 nonzeros per tile and k-block: the rest straight from memory
           const uint32_t* ps = p.sl.tcsp + R.sidx * cap;
 #pragma unroll 2
-          for (int q = R.first + wt + S_NQ * S_BM; q < R.last; q += S_BM) { const uint32_t s = __ldg(ps + q); *(uint16_t*)(mimg + meta_off(s & 0x1FFFu)) = (uint16_t)(s >> 16); }
+          for (int q = R.first + wt + S_NQ * S_GT; q < R.last; q += S_GT) { const uint32_t s = __ldg(ps + q); *(uint16_t*)(mimg + meta_off(s & 0x1FFFu)) = (uint16_t)(s >> 16); }
         }
       }
       // ---- the slot is ours once the MMAs of the k-block that used it have completed ----
       if (gk >= S_NA) mbar_wait(&a_free[j], ((gk / S_NA) - 1) & 1);
       if (!idle) {
         // clear the kept elements the previous k-block left behind (a dense one is wiped)
-        if (n_old > S_NQ * S_BM) {
+        if (n_old > S_NQ * S_GT) {
           uint4* z = (uint4*)abuf;
 #pragma unroll
-          for (int i = 0; i < S_A_BUF / 16 / S_BM; ++i) z[wt + i * S_BM] = make_uint4(0, 0, 0, 0);
+          for (int i = 0; i < S_A_BUF / 16 / S_GT; ++i) z[wt + i * S_GT] = make_uint4(0, 0, 0, 0);
         }
         else {
 #pragma unroll
           for (int i = 0; i < S_NQ; ++i) {
-            if (i * S_BM >= n_old) break;                    // uniform
-            if (wt + i * S_BM < n_old) *(uint16_t*)(abuf + ((hs[i] & 0x1FFFu) << 1)) = 0;
+            if (i * S_GT >= n_old) break;                    // uniform
+            if (wt + i * S_GT < n_old) *(uint16_t*)(abuf + ((hs[i] & 0x1FFFu) << 1)) = 0;
           }
         }
-        asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_BM) : "memory");   // another thread may write where this one cleared
+        asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_GT) : "memory");   // another thread may write where this one cleared
 #pragma unroll
         for (int i = 0; i < S_NQ; ++i) {
-          if (i * S_BM >= n) break;                          // uniform
-          if (wt + i * S_BM < n) {
+          if (i * S_GT >= n) break;                          // uniform
+          if (wt + i * S_GT < n) {
             const uint32_t s = R.sw[i];
             if (0 == (s & 0x8000u)) *(uint16_t*)(abuf + ((s & 0x1FFFu) << 1)) = (uint16_t)(R.rw[i] >> 16);   // overflow entries: the row's epilogue thread
             hs[i] = s;
           }
         }
         n_old = n;
-        if (n > S_NQ * S_BM) {
+        if (n > S_NQ * S_GT) {
           const uint32_t* pw = p.sl.tcpk + R.sidx * cap;
           const uint32_t* ps = p.sl.tcsp + R.sidx * cap;
 #pragma unroll 2
-          for (int q = R.first + wt + S_NQ * S_BM; q < R.last; q += S_BM) {
+          for (int q = R.first + wt + S_NQ * S_GT; q < R.last; q += S_GT) {
             const uint32_t w = __ldg(pw + q), s = __ldg(ps + q);
             if (0 == (s & 0x8000u)) *(uint16_t*)(abuf + ((s & 0x1FFFu) << 1)) = (uint16_t)(w >> 16);
           }
@@ -336,11 +339,10 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     {
       uint4* z = (uint4*)(smem + S_SMEM_A + grp * S_A_BUF);
 #pragma unroll 4
-      for (int i = 0; i < S_A_BUF / 16 / S_BM; ++i) z[wt + i * S_BM] = make_uint4(0, 0, 0, 0);
-      ((uint4*)(smem + S_SMEM_META + 2 * grp * S_META))[wt] = make_uint4(0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u);
-      ((uint4*)(smem + S_SMEM_META + (2 * grp + 1) * S_META))[wt] = make_uint4(0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u);
+      for (int i = 0; i < S_A_BUF / 16 / S_GT; ++i) z[wt + i * S_GT] = make_uint4(0, 0, 0, 0);
+      for (int i = wt; i < 2 * S_META / 16; i += S_GT) ((uint4*)(smem + S_SMEM_META + 2 * grp * S_META))[i] = make_uint4(0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u);   // both images of the slot
     }
-    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_BM) : "memory");
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(S_GT) : "memory");
     fetch(ra, pa); fetch(rb, pb);              // their nonzeros; pa / pb now hold the pointers of the two after
     for (uint32_t gk = (uint32_t)grp; gk < gk_end; gk += 2 * S_NG) {
       step(gk, ra, pa);
@@ -352,7 +354,7 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lead_empty0 = map_to_cta(&acc_empty[0], 0), lead_meta = map_to_cta(meta_free, 0);
-    unsigned char* stage = smem + S_SMEM_STAGE + (warp - (2 + 4 * S_NG)) * S_STAGE;
+    unsigned char* stage = smem + S_SMEM_STAGE + (warp - (2 + S_GW * S_NG)) * S_STAGE;
     const size_t cap = (size_t)g.bm * g.bk;
     const uint16_t* Bp = (const uint16_t*)p.b;
     for (int wi = 0; wi < nwork; ++wi) {
