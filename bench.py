@@ -96,6 +96,11 @@ def tensor_pipe_info(res):
     tp, tsrc = tensor_peak()
     bf16 = name.startswith("spmdm_compute_tc16")
     ex = (1.0 if bf16 else 3.0) * res["dense_flops"] / (res["kernel_ms"] * 1e9)
+    if name.startswith("spmdm_compute_tc16s"):
+        # 2:4 structured-sparse MMAs (tcgen05.mma.sp): the tensor core skips half of every group of four k, so the dense-EQUIVALENT
+        # rate is held against twice the dense bf16 peak (the instruction itself was measured at 1.94 x, tools/umma_probe/probe_sp_rate.cu)
+        return {"executed_dense_equivalent_tflops": ex, "peak_tflops": 2.0 * tp, "frac": ex / (2.0 * tp), "peak_source": tsrc + " x 2 (2:4 structured-sparse instruction)",
+                "note": "kind::f16 structured-sparse MMAs over the compressed A tile (two kept elements of every four k); dense-equivalent, not algorithmic, flops"}
     peak = tp if bf16 else 0.5 * tp
     return {"executed_dense_tflops": ex, "peak_tflops": peak, "frac": ex / peak, "peak_source": tsrc + ("" if bf16 else " x 0.5 (tf32)"),
             "note": ("kind::f16 MMAs" if bf16 else "3 x kind::tf32 MMAs") + " over the densified A tile; executed, not algorithmic, flops"}
