@@ -98,6 +98,7 @@ struct SpmdmCtx {
   bool aux_written;               // the auxiliary per-nonzero words of the current slices are valid
   bool dense_written;             // ... and so is their dense tile image
   bool sp_written;                // ... and so are the words of the structured-sparse tensor-core kernel (SliceArena::tcsp)
+  float d_seen, d_seen_prev;      // density estimate at the last two multiplies (< 0: unknown): equal-ish = a stable regime
   bool captured;                  // the current slices were (are being) produced under stream capture
   size_t dense_bytes;
 };
@@ -116,6 +117,20 @@ static float density_estimate(const SpmdmCtx* c)
 {
   const unsigned long long n = c->h_nnz ? *(volatile unsigned long long*)c->h_nnz : ~0ull;
   return (~0ull == n) ? -1.f : (float)((double)n / ((double)c->g.m * (double)c->g.k));
+}
+
+// Called once per multiply: remembers the estimate this multiply sees and tells whether the one before saw about the same.
+// When it did not (the matrices going through this handle change density, or this is the first estimate at all), the
+// structured-sparse kernel is enqueued together with the dense one and the choice is made on the device (ComputeArgs::sp_guard):
+// a dense matrix on the overflow path of K4s would cost milliseconds.
+static void density_guard(SpmdmCtx* c, ComputeArgs* a)
+{
+  const float d = density_estimate(c);
+  const float prev = c->d_seen;
+  c->d_seen_prev = prev; c->d_seen = d;
+  const bool stable = d >= 0.f && prev >= 0.f && prev <= 2.f * d && d <= 2.f * prev;
+  a->sp_guard = stable ? 0 : 1;
+  a->sp_max_nnz = (unsigned long long)(0.03 * (double)c->g.m * (double)c->g.k);
 }
 
 static bool stream_is_capturing(cudaStream_t stream)
@@ -278,6 +293,7 @@ static void compute_whole(const libxsmm_spmdm_handle* handle, char transb, char 
   a.ldc = a.transc ? c->g.m : c->g.n;
   a.beta = beta; a.g = c->g; a.mb_first = 0; a.mb_count = c->g.mb;
   a.row_origin = 0; a.col_origin = 0; a.ncols = c->g.n; a.modes = spmdm_modes(c->g, c->simd_w); a.tc_twin = 0; a.tc_min_nnz = 0; a.tc_hint = compute_policy(c, is_bf16, 0 != a.transb, 0 != a.transc); a.density_hint = density_estimate(c); a.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0; a.aux_valid = c->aux_written ? 1 : 0; a.sp_valid = (c->sp_written && c->aux_written) ? 1 : 0;
+  density_guard(c, &a);
   launch_compute(a, stream);
 }
 
@@ -335,7 +351,7 @@ static void compute_block(const libxsmm_spmdm_handle* handle, char transb, char 
   const bool dev_b = is_device_ptr(b_in), dev_c = is_device_ptr(c_in);
   ComputeArgs a = ComputeArgs();
   a.sl = c->arena; a.transb = tb; a.transc = tc; a.is_bf16 = is_bf16; a.beta = beta; a.g = g;
-  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1; a.density_hint = -1.f; a.dense_valid = 0; a.aux_valid = 0; a.sp_valid = 0;   // legacy block: no tensor-core twin
+  a.mb_first = mbi; a.mb_count = 1; a.col_origin = n0; a.ncols = num_n; a.modes = spmdm_modes(g, c->simd_w); a.tc_twin = -1; a.tc_min_nnz = 0; a.tc_hint = 1; a.density_hint = -1.f; a.dense_valid = 0; a.aux_valid = 0; a.sp_valid = 0; a.sp_guard = 0; a.sp_max_nnz = 0;   // legacy block: no tensor-core twin
   char* slab = c->staging + (size_t)tid * c->staging_per_tid;
   const size_t slab_b_bytes = (((size_t)g.k * g.bn * 4) + 255) & ~(size_t)255;
   float* c_stage = (float*)(slab + slab_b_bytes);
@@ -433,7 +449,7 @@ void libxsmm_spmdm_init(int M, int N, int K, int max_threads, libxsmm_spmdm_hand
   c->arena.epoch = (uint32_t*)((char*)c->arena.lookback + lb_bytes);
   c->arena.slice_ovf = (uint32_t*)((char*)c->arena.epoch + 256);
   XB_CUDA(cudaMemset(c->arena.slice_nnz, 0, nnz_bytes + lb_bytes + 256 + nnz_bytes));
-  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->sp_written = false; c->captured = false; c->dense_bytes = 0; c->arena.dense = 0; c->arena.tcsp = 0; c->arena.ovf_list = 0;
+  c->h_nnz = 0; c->d_nnz = 0; c->d_acc = 0; c->aux_written = false; c->dense_written = false; c->sp_written = false; c->d_seen = -1.f; c->d_seen_prev = -1.f; c->captured = false; c->dense_bytes = 0; c->arena.dense = 0; c->arena.tcsp = 0; c->arena.ovf_list = 0;
   if (cudaSuccess == cudaHostAlloc((void**)&c->h_nnz, sizeof(unsigned long long), cudaHostAllocMapped)) {
     *c->h_nnz = ~0ull;
     if (cudaSuccess != cudaHostGetDevicePointer((void**)&c->d_nnz, c->h_nnz, 0)) c->d_nnz = 0;
@@ -648,6 +664,7 @@ void libxsmm_spmdm_exec_host(const libxsmm_spmdm_handle* handle, libxsmm_CSR_spa
     ca.c = c->d_c + (tc ? (size_t)n0 * g.m : (size_t)n0);
     ca.beta = beta_f; ca.g = g; ca.mb_first = r0; ca.mb_count = rc;
     ca.row_origin = 0; ca.col_origin = n0; ca.ncols = w; ca.modes = modes; ca.tc_twin = 0; ca.tc_min_nnz = 0; ca.tc_hint = compute_policy(c, is_bf16, tb, tc); ca.density_hint = density_estimate(c); ca.dense_valid = (c->dense_written && !is_bf16) ? 1 : 0; ca.aux_valid = c->aux_written ? 1 : 0; ca.sp_valid = (c->sp_written && c->aux_written) ? 1 : 0;
+    density_guard(c, &ca);
     launch_compute(ca, c->xs[1]);
   };
   for (int d = 0; d < nd; ++d) {

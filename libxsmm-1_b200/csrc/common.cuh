@@ -185,6 +185,11 @@ struct ComputeArgs {
   unsigned long long tc_min_nnz;
   int aux_valid;        // the slices' per-nonzero auxiliary words (tcoff / tcpk) were written for ALL slices by the pass these slices come from
   int sp_valid;         // ... and so were the words of the structured-sparse kernel (tcsp)
+  // Guarded pair K4s | K4p: the host's density estimate has just changed (or is one observation old), so it may be a dense matrix
+  // that arrives: both kernels are enqueued, each sums the slices' counts, K4s (sp_guard = 1) works iff nnz <= sp_max_nnz,
+  // K4p (sp_guard = 2) iff nnz > sp_max_nnz.  0: no guard (stable estimate: K4s alone).
+  int sp_guard;
+  unsigned long long sp_max_nnz;
   int dense_valid;      // the slices' dense tile image (SliceArena::dense) was written by the slicing pass these slices come from
   float density_hint;   // host's lagging estimate of nnz / (M*K) from the last completed slicing pass, < 0: unknown (performance only)
   int debug_flags;  // developer timing aid (LIBXSMM_B200_K2S_DEBUG; results are wrong when set): 1 = skip the multiply-adds, 2 = skip the B tile loads

@@ -57,8 +57,12 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   const Geom& g = p.g;
-  if (p.tc_twin > 0) pdl_wait();        // the twin decision reads the slices' counts
-  if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // uniform over the grid
+  if (p.tc_twin > 0 || 2 == p.sp_guard) {    // the twin / guard decision reads the slices' counts
+    pdl_wait();
+    const unsigned long long total = xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb);
+    if (p.tc_twin > 0 && total < p.tc_min_nnz) return;      // uniform over the grid
+    if (2 == p.sp_guard && total <= p.sp_max_nnz) return;   // the structured-sparse kernel enqueued in front of this one has multiplied
+  }
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank();
   const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
@@ -109,7 +113,7 @@ spmdm_compute_tc16p_kernel(const __grid_constant__ CUtensorMap tmB, const Comput
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
-  if (p.tc_twin <= 0) pdl_wait();       // barriers, tensor memory and the cluster hand-shake were set up while the kernel in front was still finishing
+  if (p.tc_twin <= 0 && 2 != p.sp_guard) pdl_wait();       // barriers, tensor memory and the cluster hand-shake were set up while the kernel in front was still finishing
 
   if (0 == warp) {
     // ---------------- TMA producer: this CTA's 128 columns of every B stage ----------------

@@ -95,8 +95,12 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
   uint32_t* tmem_slot = (uint32_t*)(meta_free + 1);
 
   const Geom& g = p.g;
-  if (p.tc_twin > 0) pdl_wait();        // the twin decision reads the slices' counts
-  if (p.tc_twin > 0 && xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb) < p.tc_min_nnz) return;   // uniform over the grid
+  if (p.tc_twin > 0 || p.sp_guard) {    // the twin / guard decision reads the slices' counts
+    pdl_wait();
+    const unsigned long long total = xb_total_nnz(p.sl.slice_nnz, g.mb * g.kb);
+    if (p.tc_twin > 0 && total < p.tc_min_nnz) return;      // uniform over the grid
+    if (p.sp_guard && total > p.sp_max_nnz) return;         // too dense for the overflow path: the dense kernel enqueued behind this one multiplies
+  }
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank();
   const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
@@ -145,7 +149,7 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
   const uint32_t tmem_d = *tmem_slot;
   // everything above (barriers, tensor memory, cluster hand-shake) ran while the slicing kernel was still finishing: from here
   // on its output is read
-  if (p.tc_twin <= 0) pdl_wait();
+  if (p.tc_twin <= 0 && !p.sp_guard) pdl_wait();
 
   if (0 == warp) {
     // ---------------- TMA producer: this CTA's 128 columns of every B stage ----------------
@@ -528,7 +532,8 @@ bool launch_compute_tc16s(const ComputeArgs& a, cudaStream_t stream)
   if (env && '0' == *env) return false;
   if (0 == a.aux_valid || 0 == a.sp_valid || 0 == a.sl.tcsp || 0 == a.sl.slice_ovf || 0 == a.sl.ovf_list) return false;
   if (!a.is_bf16 || a.transb) return false;
-  if (!(env && '1' == *env) && !(a.density_hint >= 0.f && a.density_hint <= kSpMaxDensity)) return false;
+  const bool forced = env && '1' == *env;
+  if (!forced && !(a.density_hint >= 0.f && a.density_hint <= kSpMaxDensity)) return false;
   if (!a.transc && (0 != ((uintptr_t)a.c & 15) || 0 != (a.ldc & 3))) return false;
   CUtensorMap map;
   if (!make_tensor_map_2d_sw128(&map, a.b, 2, (unsigned long long)a.ncols, (unsigned long long)a.g.k, (unsigned long long)a.ldb * 2, 64, S_KB, false)) return false;
@@ -550,6 +555,7 @@ bool launch_compute_tc16s(const ComputeArgs& a, cudaStream_t stream)
   count_launch(1);
   note_compute_kernel("spmdm_compute_tc16s_kernel");
   ComputeArgs a2 = a;
+  if (forced) a2.sp_guard = 0;
   if (const char* dbg = getenv("LIBXSMM_B200_K4S_DEBUG")) a2.debug_flags = atoi(dbg);   // developer timing aid: results are wrong when set
   // programmatic dependent launch: the CTAs may be scheduled, and run their prologue, while the kernel in front of this one
   // (normally the slicing kernel) is still draining

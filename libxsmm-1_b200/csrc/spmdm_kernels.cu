@@ -1209,7 +1209,15 @@ static int tc_mode()
 static bool launch_tc_bf16(const ComputeArgs& a, cudaStream_t stream)
 {
   const char* e = getenv("LIBXSMM_B200_TC16_PAIR");
-  if (launch_compute_tc16s(a, stream)) return true;      // 2:4 structured-sparse form (low density, slices from the wide kernel)
+  if (launch_compute_tc16s(a, stream)) {                 // 2:4 structured-sparse form (low density, slices from the wide kernel)
+    const char* fe = getenv("LIBXSMM_B200_TC16_SPARSE");
+    if (a.sp_guard && !(fe && '1' == *fe)) {             // the estimate is fresh or has just moved: the dense kernel stands by (ComputeArgs::sp_guard)
+      ComputeArgs g2 = a;
+      g2.sp_guard = 2;
+      if (launch_compute_tc16p(g2, stream)) note_compute_kernel("guarded: spmdm_compute_tc16s_kernel | spmdm_compute_tc16p_kernel (selected on the device by nnz)");
+    }
+    return true;
+  }
   if (!(e && '0' == *e) && launch_compute_tc16p(a, stream)) return true;
   return launch_compute_tc16(a, stream);
 }

@@ -180,3 +180,32 @@ def test_exec_host_rectangles(gpu, oracle, monkeypatch, shape, density, beta, tc
             assert rel(C, OC) <= 1e-5
     finally:
         xs.libxsmm_spmdm_destroy(h)
+
+
+def test_changing_density_through_one_handle(gpu, monkeypatch):
+    """a handle that sees matrices of very different density in turn (a cache keyed by shape, as TensorFlow's wrapper keeps):
+    whenever the host's estimate is fresh or has just moved, the structured-sparse kernel is enqueued together with the dense one
+    and the device picks by the slices' own counts -- a dense matrix never runs through the overflow path of K4s -- and every
+    result is right; after two multiplies at about the same density K4s runs alone."""
+    monkeypatch.delenv("LIBXSMM_B200_SPMDM_TC", raising=False)
+    monkeypatch.delenv("LIBXSMM_B200_TC16_SPARSE", raising=False)
+    M = N = K = 1024
+    xs = gpu
+    sets = {d: xs.workloads.spmdm_inputs(M, N, K, d, dtype="bf16", seed=int(d * 1000)) for d in (0.01, 0.30)}
+    refs = {d: xs.workloads.from_bf16_bits(A).astype(np.float64) @ xs.workloads.from_bf16_bits(B).astype(np.float64) for d, (A, B, _) in sets.items()}
+    p = xs.Spmdm(M, N, K, 1)
+    names = []
+    for d in (0.01, 0.30, 0.01, 0.30, 0.01, 0.01, 0.01, 0.01):
+        A, B, C0 = sets[d]
+        dA, dB, dC = (xs.DeviceBuffer.from_numpy(x) for x in (A, B, C0))
+        p.create_slices(dA, "N", True)
+        p.compute(dB, dC, "N", "N", 0.0, True)       # no synchronisation in between: the estimate is the previous pass's
+        xs.synchronize()
+        names.append(xs.last_compute_kernel())
+        assert rel(dC.to_numpy(np.float32, C0.shape), refs[d]) <= 1e-5, (d, names)
+        for b in (dA, dB, dC):
+            b.free()
+    assert names[-1] == K4S, names
+    assert any(n.startswith("guarded:") for n in names), names
+    p.destroy()
+    gpu.check()
