@@ -129,7 +129,7 @@ static void density_guard(SpmdmCtx* c, ComputeArgs* a)
   const float prev = c->d_seen;
   c->d_seen_prev = prev; c->d_seen = d;
   const bool stable = d >= 0.f && prev >= 0.f && prev <= 2.f * d && d <= 2.f * prev;
-  a->sp_guard = stable ? 0 : 1;
+  a->sp_guard = (stable && !c->captured) ? 0 : 1;      // recorded into a graph: the replay may bring any matrix, the device decides every time
   a->sp_max_nnz = (unsigned long long)(0.03 * (double)c->g.m * (double)c->g.k);
 }
 
