@@ -19,6 +19,7 @@
 #include "tc_common.cuh"
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace xb {
 
@@ -36,8 +37,12 @@ struct FsTcArgs {
   const unsigned char* op_packed;   // 4 planes of M_pad x 128 B, already swizzled
   long long ncols, ldb, ldc;
   int M, M_pad, K, beta_one;
+  int pf_mode;                      // 0: L2 prefetch through the TMA unit, 1: prefetch instructions of the producer warp
+  int pf_dist;                      // the tile this many of the CTA's steps ahead is pulled into L2
+  int debug;                        // developer timing aid (LIBXSMM_B200_K4F_DEBUG; results are wrong when set): 1 no b_lo, 2 no C stores, 4 no MMAs, 8 no B loads
 };
 
+template <int EPI>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
 {
@@ -78,21 +83,37 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
   const uint32_t tmem_d = *tmem_slot;
 
   if (0 == warp) {
-    if (0 == lane) {
-      tma_prefetch_desc(&tmB);
-      long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = (int)(it & 1);
+    if (0 == lane) tma_prefetch_desc(&tmB);
+    long long it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = (int)(it & 1);
+      if (0 == lane) {
         if (it >= 2) mbar_wait(&b_free[s], (uint32_t)(((it >> 1) - 1) & 1));
-        mbar_arrive_expect_tx(&b_full[s], FT_STAGE_HALF);
-        unsigned char* dst = smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF;
+        if (p.debug & 8) mbar_arrive(&b_full[s]);
+        else {
+          mbar_arrive_expect_tx(&b_full[s], FT_STAGE_HALF);
+          unsigned char* dst = smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * (64 * 128), &tmB, (int)(t * FT_BN) + 32 * j, 0, &b_full[s]);
-        // the tile this CTA will need after the two in flight: into L2 now (the ring is only two stages deep)
-        const long long tn = t + 2 * (long long)gridDim.x;
-        if (tn < ntiles) {
+          for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * (64 * 128), &tmB, (int)(t * FT_BN) + 32 * j, 0, &b_full[s]);
+        }
+      }
+      if (p.debug & 8) continue;
+      // A tile this CTA will need after the two in flight: into L2 now.  The ring is only two stages deep (64 KiB in flight per
+      // SM), and with C's stores filling the DRAM queues a tile fetched from DRAM takes several microseconds to arrive.
+      const long long tn = t + (long long)p.pf_dist * (long long)gridDim.x;
+      if (tn < ntiles) {
+        if (0 == p.pf_mode) {          // through the TMA unit (measured: these requests queue in front of the next tile's loads)
+          if (0 == lane) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_prefetch_l2_2d(&tmB, (int)(tn * FT_BN) + 32 * j, 0);
+            for (int j = 0; j < 4; ++j) tma_prefetch_l2_2d(&tmB, (int)(tn * FT_BN) + 32 * j, 0);
+          }
+        }
+        else {                         // prefetch instructions of the whole warp: one per 128-byte line, four lines per row of B
+          __syncwarp();
+          const long long c0 = tn * FT_BN + 32 * (lane & 3);
+          if (c0 < p.ncols) {
+            for (int k = lane >> 2; k < p.K; k += 8) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.B + (long long)k * p.ldb + c0) : "memory");
+          }
         }
       }
     }
@@ -117,6 +138,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
           const uint32_t o = sbase + FT_SMEM_OP + (uint32_t)((ks >> 2) * plane + (ks & 3) * 32);
           const uint64_t doh = tc_smem_desc(o, 16, 1024, 2);
           const uint64_t dol = tc_smem_desc(o + 2 * plane, 16, 1024, 2);
+          if (p.debug & 4) continue;
           tc_mma_tf32(tacc, dxh, doh, idesc, ks > 0 ? 1u : 0u);
           tc_mma_tf32(tacc, dxl, doh, idesc, 1u);
           tc_mma_tf32(tacc, dxh, dol, idesc, 1u);
@@ -137,6 +159,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
       uint4* dst = (uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF + FT_STAGE_HALF);
 #pragma unroll 4
       for (int i = wt; i < FT_STAGE_HALF / 16; i += FT_WORKERS * 32) {
+        if (p.debug & 1) break;
         const uint4 b = src[i];
         uint4 l;
         l.x = __float_as_uint(__uint_as_float(b.x) - __uint_as_float(b.x & 0xFFFFE000u));
@@ -157,28 +180,101 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
     // lane quarter, taking the 32-row chunks in turn.
     const int quarter = warp & 3, part = (warp - 2 - FT_WORKERS) >> 2;
     long long it = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int ab = (int)(it & 1);
-      mbar_wait(&acc_full[ab], (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
-      const long long col = t * FT_BN + quarter * 32 + lane;
-      for (int m0 = 32 * part; m0 < p.M; m0 += 32 * (FT_EPI / 4)) {
-        uint32_t v[32];
-        tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * 256 + m0), v);
-        if (col < p.ncols) {
+    if (0 == EPI) {
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int ab = (int)(it & 1);
+        mbar_wait(&acc_full[ab], (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        const long long col = t * FT_BN + quarter * 32 + lane;
+        for (int m0 = 32 * part; m0 < p.M; m0 += 32 * (FT_EPI / 4)) {
+          uint32_t v[32];
+          tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * 256 + m0), v);
+          if (col < p.ncols && !(p.debug & 2)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (m0 + j < p.M) {
-              float* dst = p.C + (long long)(m0 + j) * p.ldc + col;
-              const float r = __uint_as_float(v[j]);
-              __stcs(dst, p.beta_one ? (r + __ldcs(dst)) : r);
+            for (int j = 0; j < 32; ++j) {
+              if (m0 + j < p.M) {
+                float* dst = p.C + (long long)(m0 + j) * p.ldc + col;
+                const float r = __uint_as_float(v[j]);
+                __stcs(dst, p.beta_one ? (r + __ldcs(dst)) : r);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (0 == lane) mbar_arrive(&acc_free[ab]);
+      }
+    }
+    else {
+      // The operator's rows in chunks of eight, dealt round-robin to the four warps of a lane quarter (150 rows: 40 / 40 / 40 / 30).
+      // All of a warp's chunks are fetched from tensor memory first, the accumulator is handed back to the tensor core, and only
+      // then the rows are stored: one pointer stepping by ldc, no per-row branch in full chunks; for beta = 1 the eight C
+      // values of a chunk are all requested before the first is used.
+      const int nchunk = (p.M + 7) >> 3;
+      const uint32_t tq = tmem_d + ((uint32_t)(quarter * 32) << 16);
+      const long long ldc = p.ldc;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int ab = (int)(it & 1);
+        if (p.beta_one && t + gridDim.x < ntiles) {
+          // beta = 1: the lines of C this warp will read for the CTA's NEXT tile go into L2 now (lane = row of a chunk)
+          const long long cn = (t + gridDim.x) * FT_BN + quarter * 32;
+          if (cn < p.ncols) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int i = 4 * r + (lane >> 3), m = 8 * (part + 4 * i) + (lane & 7);
+              if (i < 6 && m < p.M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.C + (long long)m * ldc + cn) : "memory");
+            }
+          }
+        }
+        mbar_wait(&acc_full[ab], (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        const long long col = t * FT_BN + quarter * 32 + lane;
+        float* dst = p.C + (long long)(8 * part) * ldc + col;
+        const bool live = col < p.ncols && !(p.debug & 2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {          // M_pad <= 192: at most 24 chunks, six per warp, fetched three at a time
+          uint32_t v[3][8];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) if (part + 4 * (3 * h + i) < nchunk) tc_ld8_nowait(tq + (uint32_t)(ab * 256 + 8 * (part + 4 * (3 * h + i))), v[i]);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 3; ++i) tc_pin8(v[i]);
+          if (1 == h) {                        // the accumulator is in registers: hand it back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (0 == lane) mbar_arrive(&acc_free[ab]);
+          }
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int m0 = 8 * (part + 4 * (3 * h + i));
+              if (m0 + 8 <= p.M) {
+                if (p.beta_one) {      // the eight C values of the chunk are all requested before the first is used
+                  float o[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) o[j] = __ldcs(dst + j * ldc);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) __stcs(dst + j * ldc, __uint_as_float(v[i][j]) + o[j]);
+                }
+                else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) __stcs(dst + j * ldc, __uint_as_float(v[i][j]));
+                }
+              }
+              else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (m0 + j < p.M) {
+                    const float r = __uint_as_float(v[i][j]);
+                    __stcs(dst + j * ldc, p.beta_one ? (r + __ldcs(dst + j * ldc)) : r);
+                  }
+                }
+              }
+              dst += 32 * ldc;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (0 == lane) mbar_arrive(&acc_free[ab]);
     }
   }
   __syncthreads();
@@ -192,7 +288,7 @@ bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes
                               unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows, bool atom32);
 
 // ---- host side ---------------------------------------------------------------------------------------------
-struct FsTc { unsigned char* d_op; int M, M_pad, K, beta_one; size_t smem; int sms; };
+struct FsTc { unsigned char* d_op; int M, M_pad, K, beta_one; size_t smem; int sms; int epi, pf_mode, pf_dist, debug; };
 
 static int fs_tc_mpad(int M) { return (M + 15) / 16 * 16; }
 
@@ -223,7 +319,16 @@ FsTc* fs_tc_build(int M, int K, int lda, int beta_one, const float* a_dense)
   int dev = 0; cudaDeviceProp prop;
   t->sms = 148;
   if (cudaSuccess == cudaGetDevice(&dev) && cudaSuccess == cudaGetDeviceProperties(&prop, dev)) t->sms = prop.multiProcessorCount;
-  ensure_smem_optin((const void*)fsspmdm_tc_kernel, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256));
+  ensure_smem_optin((const void*)fsspmdm_tc_kernel<0>, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256));
+  ensure_smem_optin((const void*)fsspmdm_tc_kernel<1>, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256));
+  const char* e = getenv("LIBXSMM_B200_K4F_EPI");        // 0: the round-1 epilogue (32-row chunks, per-row address arithmetic)
+  t->epi = (e && '0' == *e) ? 0 : 1;
+  e = getenv("LIBXSMM_B200_K4F_PF");
+  t->pf_dist = (e && atoi(e) >= 2) ? atoi(e) : 4;
+  e = getenv("LIBXSMM_B200_K4F_PFMODE");
+  t->pf_mode = (e && '0' == *e) ? 0 : 1;
+  e = getenv("LIBXSMM_B200_K4F_DEBUG");
+  t->debug = e ? atoi(e) : 0;
   return t;
 }
 
@@ -235,10 +340,11 @@ bool fs_tc_launch(const FsTc* t, const void* dB, void* dC, long long ncols, long
   if (!make_tensor_map_2d_sw128(&map, dB, 4, (unsigned long long)ncols, (unsigned long long)t->K, (unsigned long long)ldb * 4, 32, 64, true)) return false;
   FsTcArgs a;
   a.B = (const float*)dB; a.C = (float*)dC; a.op_packed = t->d_op; a.ncols = ncols; a.ldb = ldb; a.ldc = ldc;
-  a.M = t->M; a.M_pad = t->M_pad; a.K = t->K; a.beta_one = t->beta_one;
+  a.M = t->M; a.M_pad = t->M_pad; a.K = t->K; a.beta_one = t->beta_one; a.pf_dist = t->pf_dist; a.pf_mode = t->pf_mode; a.debug = t->debug;
   const long long ntiles = (ncols + FT_BN - 1) / FT_BN;
   const unsigned grid = (unsigned)(ntiles < t->sms ? ntiles : t->sms);
-  fsspmdm_tc_kernel<<<grid, FT_THREADS, t->smem, stream>>>(map, a);
+  if (t->epi) fsspmdm_tc_kernel<1><<<grid, FT_THREADS, t->smem, stream>>>(map, a);
+  else fsspmdm_tc_kernel<0><<<grid, FT_THREADS, t->smem, stream>>>(map, a);
   XB_CUDA(cudaGetLastError());
   return true;
 }

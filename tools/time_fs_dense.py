@@ -5,10 +5,10 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import bench
 xs = importlib.import_module("libxsmm-1_b200")
-for tc in ("1", "0"):
+for tc in (("1",) if os.environ.get("LIBXSMM_B200_FSSPMDM_TC") == "1" else ("1", "0")):
     os.environ["LIBXSMM_B200_FSSPMDM_TC"] = tc
     for dens in ([float(x) for x in sys.argv[1:]] or [1.0, 0.5]):
-        wl = dict(bench.WORKLOADS["c5"], density=dens, n_unique=None, N=1 << 22)
+        wl = dict(bench.WORKLOADS["c5"], density=dens, n_unique=None, N=1 << 22, beta=float(os.environ.get("FS_BETA", "0")))
         gen = bench.run_fs_gpu(xs, wl, 10, 3, 1, want_e2e=False)
         assert next(gen) == "ready"
         r = next(gen)
