@@ -213,13 +213,13 @@ FsOperator* fs_create(int is_double, int M, int N, int K, int lda, int ldb, int 
   }
   // Dense float operators: once the FMA pipe, not HBM, bounds the baked kernel (more than ~4 nonzeros per byte
   // moved per column), the apply is a dense contraction and goes to the tensor cores (3xTF32, fsspmdm_tc.cu).
-  // Measured on B200, 150 x 64, N = 2^22: tensor cores 819 us at any density; baked 652 / 716 / 996 / 1367 / 1767 us
-  // at 30 / 35 / 40 / 45-50 / 60 % -> break-even ~37 %.
+  // Measured on B200, 150 x 64, N = 2^22: tensor cores 760-780 us at any density (round 1: 819; beta = 1: 1711 us, was 6388);
+  // baked 652 / 716 / 996 / 1367 / 1767 us at 30 / 35 / 40 / 45-50 / 60 % -> break-even ~36 %.
   // LIBXSMM_B200_FSSPMDM_TC=1 forces that kernel for every eligible operator, =0 disables it.
   if (fs_tc_supported(is_double, M, K)) {
     const char* e = getenv("LIBXSMM_B200_FSSPMDM_TC");
     const double bytes_per_col = 4.0 * (K + M * (o->beta_one ? 2.0 : 1.0));
-    const bool want = (e && *e) ? ('1' == *e) : ((double)o->nnz > 4.2 * bytes_per_col);
+    const bool want = (e && *e) ? ('1' == *e) : ((double)o->nnz > 4.0 * bytes_per_col);
     if (want) o->tc = fs_tc_build(M, K, lda, o->beta_one, (const float*)a_dense);
   }
   // bake the operator into a specialised kernel (the GPU counterpart of the reference's JIT)

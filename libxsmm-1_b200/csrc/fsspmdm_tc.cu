@@ -61,6 +61,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
   const long long ntiles = (p.ncols + FT_BN - 1) / FT_BN;
   const uint32_t sbase = smem_u32(smem);
   const int nks = (p.K + 7) / 8;     // k-steps of 8
+  auto tile_of = [&](long long i) -> long long { return (long long)blockIdx.x + i * (long long)gridDim.x; };      // the i-th tile of this CTA
 
   if (0 == tid) {
 #pragma unroll
@@ -85,7 +86,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
   if (0 == warp) {
     if (0 == lane) tma_prefetch_desc(&tmB);
     long long it = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
       const int s = (int)(it & 1);
       if (0 == lane) {
         if (it >= 2) mbar_wait(&b_free[s], (uint32_t)(((it >> 1) - 1) & 1));
@@ -100,7 +101,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
       if (p.debug & 8) continue;
       // A tile this CTA will need after the two in flight: into L2 now.  The ring is only two stages deep (64 KiB in flight per
       // SM), and with C's stores filling the DRAM queues a tile fetched from DRAM takes several microseconds to arrive.
-      const long long tn = t + (long long)p.pf_dist * (long long)gridDim.x;
+      const long long tn = tile_of(it + p.pf_dist);
       if (tn < ntiles) {
         if (0 == p.pf_mode) {          // through the TMA unit (measured: these requests queue in front of the next tile's loads)
           if (0 == lane) {
@@ -123,7 +124,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
       // D = F32, A = B = TF32, A MN-major (the B tile), B K-major (the operator), M = 128, N = M_pad
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(p.M_pad >> 3) << 17) | ((uint32_t)(FT_BN >> 4) << 24);
       long long it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
         const int s = (int)(it & 1), ab = (int)(it & 1);
         if (it >= 2) mbar_wait(&acc_free[ab], (uint32_t)(((it >> 1) - 1) & 1));
         mbar_wait(&b_split[s], (uint32_t)((it >> 1) & 1));
@@ -152,7 +153,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
     // ---------------- b_lo = b - trunc_tf32(b) for every tile (same swizzled addresses) ----------------
     const int wt = tid - 64;                      // 0..127
     long long it = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
       const int s = (int)(it & 1);
       mbar_wait(&b_full[s], (uint32_t)((it >> 1) & 1));
       const uint4* src = (const uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF);
@@ -181,7 +182,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
     const int quarter = warp & 3, part = (warp - 2 - FT_WORKERS) >> 2;
     long long it = 0;
     if (0 == EPI) {
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
         const int ab = (int)(it & 1);
         mbar_wait(&acc_full[ab], (uint32_t)((it >> 1) & 1));
         tc_fence_after();
@@ -213,11 +214,11 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
       const int nchunk = (p.M + 7) >> 3;
       const uint32_t tq = tmem_d + ((uint32_t)(quarter * 32) << 16);
       const long long ldc = p.ldc;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
         const int ab = (int)(it & 1);
-        if (p.beta_one && t + gridDim.x < ntiles) {
+        if (p.beta_one && tile_of(it + 1) < ntiles) {
           // beta = 1: the lines of C this warp will read for the CTA's NEXT tile go into L2 now (lane = row of a chunk)
-          const long long cn = (t + gridDim.x) * FT_BN + quarter * 32;
+          const long long cn = tile_of(it + 1) * FT_BN + quarter * 32;
           if (cn < p.ncols) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
