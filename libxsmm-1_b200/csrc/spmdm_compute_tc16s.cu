@@ -63,6 +63,7 @@ constexpr int S_STAGE = 32 * 128;
 constexpr int S_SMEM_BAR = S_SMEM_STAGE + S_NE * S_STAGE;
 constexpr int S_NOVF = 4;                       // overflow entries of a row an epilogue thread keeps in registers
 static_assert(0 == (S_SMEM_STAGE & 1023), "SWIZZLE_128B boxes sit on 1 KiB boundaries");
+static_assert(S_NE * (S_BN / 32) * S_STAGE <= S_SMEM_META, "the last tile's C boxes fit in the (then idle) A / B ring");
 constexpr int S_SMEM_BYTES = S_SMEM_BAR + 256;
 // Tensor memory: two accumulators of 256 columns fill it.  The metadata ring of a tile (4 columns per k-block buffer) lives
 // in the first columns of the accumulator the tile does NOT accumulate into: that accumulator belongs to the epilogue of the
@@ -461,16 +462,24 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         if (p.debug_flags & 4) continue;
         if (use_tma) {
           // thread = row: eight 16-byte units of the row's 128 bytes, swizzled like the tensor map (unit ^ row % 8): no bank
-          // conflicts, and the store engine, not the load / store unit the workers depend on, moves the box
-          if (0 == lane) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-          __syncwarp();
+          // conflicts, and the store engine, not the load / store unit the workers depend on, moves the box.
+          // One staging box per warp: a chunk waits until the store engine has read the previous one out (about a microsecond,
+          // hidden behind the next tile's k loop) -- except in the pair's LAST tile, whose epilogue nothing overlaps: once its
+          // MMAs have completed the ring is idle, and every chunk gets a box of its own there (measured: 4.7 us of tail for a
+          // half tile, 9.3 us for a full one, with the single box).
+          unsigned char* sbox = stage;
+          if (wi == nwork - 1) sbox = smem + S_SMEM_A + ((warp - (2 + S_GW * S_NG)) * (S_BN / 32) + (cb >> 5)) * S_STAGE;
+          else {
+            if (0 == lane) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            __syncwarp();
+          }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) *(uint4*)(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+          for (int u = 0; u < 8; ++u) *(uint4*)(sbox + lane * 128 + ((u ^ (lane & 7)) << 4)) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
           fence_proxy_async();
           __syncwarp();
           if (0 == lane) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
-                         ::"l"(&tmC), "r"(t.n0 + cb), "r"((int)(crow - (size_t)lane)), "r"(smem_u32(stage)) : "memory");
+                         ::"l"(&tmC), "r"(t.n0 + cb), "r"((int)(crow - (size_t)lane)), "r"(smem_u32(sbox)) : "memory");
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
           }
         }
@@ -511,7 +520,7 @@ spmdm_compute_tc16s_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       __syncwarp();
       if (0 == lane) mbar_arrive_cluster(lead_empty0 + acc * 8);
     }
-    if (0 == lane) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    if (0 == lane) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");    // shared memory stays alive until the store engine has read every box
   }
   tc_fence_before();
   __syncthreads();
