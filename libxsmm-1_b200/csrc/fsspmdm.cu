@@ -224,8 +224,49 @@ FsOperator* fs_create(int is_double, int M, int N, int K, int lda, int ldb, int 
   }
   // bake the operator into a specialised kernel (the GPU counterpart of the reference's JIT)
   // (not when the tensor-core kernel took the operator: panels it cannot take fall back to the generic kernel)
-  if (0 == o->tc) o->jit = fs_jit_build(is_double, (0 == ((ldb | ldc) & 1)) ? 1 : 0, M, K, o->beta_one, o->sparse_branch /*skip empty rows*/,
-                                       o->rowptr.data(), o->col.data(), o->val.data());
+  if (0 == o->tc) {
+    const int vec2 = (0 == ((ldb | ldc) & 1)) ? 1 : 0;
+    o->jit = fs_jit_build(is_double, vec2, M, K, o->beta_one, o->sparse_branch /*skip empty rows*/, o->rowptr.data(), o->col.data(), o->val.data());
+    // fma-heavy fp64 operators (the dense tet / tri families): the emitter has three forms and none wins everywhere, so the
+    // candidates are timed here, once, on a scratch panel, and the fastest is kept (the reference spends its create on a JIT too)
+    const int nvar = o->jit ? fs_jit_variants(is_double, vec2, M, K, o->rowptr.data(), o->col.data()) : 1;
+    if (nvar > 1) {
+      const long long nt = (N > 0 && N < (1 << 17)) ? ((N + 15) / 16 * 16) : (1 << 17);
+      void* sb = 0; void* sc = 0;
+      cudaEvent_t e0 = 0, e1 = 0;
+      if (cudaSuccess == cudaMalloc(&sb, (size_t)K * nt * 8) && cudaSuccess == cudaMalloc(&sc, (size_t)M * nt * 8) &&
+          cudaSuccess == cudaEventCreate(&e0) && cudaSuccess == cudaEventCreate(&e1)) {
+        cudaMemset(sb, 0, (size_t)K * nt * 8); cudaMemset(sc, 0, (size_t)M * nt * 8);
+        auto time_of = [&](FsJit* j) -> float {
+          float best = 1e30f;
+          if (!fs_jit_launch(j, sb, sc, nt, nt, nt, 0)) return best;
+          for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0, 0);
+            fs_jit_launch(j, sb, sc, nt, nt, nt, 0);
+            cudaEventRecord(e1, 0);
+            float ms = 1e30f;
+            if (cudaSuccess == cudaEventSynchronize(e1) && cudaSuccess == cudaEventElapsedTime(&ms, e0, e1) && ms < best) best = ms;
+          }
+          return best;
+        };
+        float tbest = time_of(o->jit);
+        int vbest = 0;
+        for (int v = 1; v < nvar; ++v) {
+          FsJit* cand = fs_jit_build(is_double, vec2, M, K, o->beta_one, o->sparse_branch, o->rowptr.data(), o->col.data(), o->val.data(), 0, v);
+          if (0 == cand) continue;
+          const float t = time_of(cand);
+          if (t < 0.97f * tbest) { fs_jit_destroy(o->jit); o->jit = cand; tbest = t; vbest = v; }
+          else fs_jit_destroy(cand);
+        }
+        if (verbosity() > 0) fprintf(stderr, "LIBXSMM_B200 fsspmdm: %dx%d nnz=%d: emitter variant %d of %d (%.1f us for %lld columns)\n", M, K, o->nnz, vbest, nvar, tbest * 1e3f, nt);
+      }
+      (void)cudaGetLastError();
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      if (sb) cudaFree(sb);
+      if (sc) cudaFree(sc);
+    }
+  }
   o->kernel = o->jit;
   if (verbosity() > 0) {
     fprintf(stderr, "LIBXSMM_B200 fsspmdm: %dx%d nnz=%d unique=%d branch=%s kernel=%s\n", M, K, o->nnz, o->n_unique,

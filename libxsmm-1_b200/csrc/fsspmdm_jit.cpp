@@ -179,7 +179,7 @@ static int fs_prefetch_groups()
 // batched: the columns are (element, column-in-element) pairs -- thread n works on element n / J, column n % J, whose B / C
 // rows start at element * stride (the [element][row][column][soa] tensors of the CSR x SoA kernels)
 std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
-                     const int* rowptr, const int* col, const double* val, int batched = 0)
+                     const int* rowptr, const int* col, const double* val, int batched = 0, int variant = 0)
 {
   const int cpt = (vec2 && !is_double && !batched) ? 2 : 1;
   const int esz = is_double ? 8 : 4;
@@ -188,13 +188,50 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
   for (int u = 0; u < rowptr[M]; ++u) used[col[u]] = 1;
   std::string s;
   s.reserve(96 * (size_t)rowptr[M] * cpt + 8192);
+  // Register-heavy operators (fp64 with ~50 or more used B rows: 100+ registers of B alone): left to itself the assembler interleaves
+  // the rows' fma chains until all 255 registers are taken, which leaves two 128-thread CTAs = 8 warps per SM -- too few to keep
+  // the FP64 pipe busy (PyFR p4/tet/m6: half its rate).  For those the rows are emitted IL at a time with their chains
+  // interleaved explicitly, a bar.warp.sync between the groups keeps the assembler from mixing more, and three CTAs per SM are
+  // asked for.  LIBXSMM_B200_FSSPMDM_IL / _MINCTAS (developer switches) override; IL = 0 is the plain row-after-row form.
+  int nused = 0;
+  for (int k = 0; k < K; ++k) nused += used[k] ? 1 : 0;
+  int il = 0, minctas = 0;
+  // variant (chosen by the caller, which times the candidates of fs_jit_variants() at create): 0 the plain form, 1 / 2 the explicit
+  // form with eight / two rows interleaved.  No variant wins everywhere -- measured on B200, N = 2^20, beta = 0 / 1, plain against
+  // eight (beta = 0) or two (beta = 1) rows: p4/tet/m6 362 / 453 -> 300 / 382 us, p5/tet/m460 4674 / 2317 -> 1650 / 2671, p5/tet/m0
+  // 522 / 483 -> 714 / 453, p4/tet/m3 226 / 243 -> 239 / 198: what the assembler makes of thousands of straight-line fp64 fmas with
+  // hundreds of distinct constants is not predictable from the operator, hence the timing.
+  if (is_double && !batched && variant > 0) { il = (1 == variant) ? 8 : 2; minctas = (nused <= 72) ? 3 : 2; }
+  { const char* e = getenv("LIBXSMM_B200_FSSPMDM_IL"); if (e && *e) { const int v = atoi(e); if (0 == v || (v >= 2 && v <= 8)) il = v; } }
+  { const char* e = getenv("LIBXSMM_B200_FSSPMDM_MINCTAS"); if (e && *e) { const int v = atoi(e); if (0 == v || (v >= 2 && v <= 8)) minctas = v; } }
   s += ".version 8.6\n.target sm_100a\n.address_size 64\n\n";
+  // fp64 operators with many distinct values (the reference's dense branch: tet / tri / pri families): a 64-bit literal is not an
+  // instruction operand, so the assembler builds each one in (uniform) registers again and again -- a third more instructions, and
+  // the values it chooses to keep fill the register file.  Their values go to constant memory instead; the fma takes the
+  // constant-bank word as its operand directly.  LIBXSMM_B200_FSSPMDM_CONST=0 (developer switch): literals as before.
+  std::vector<unsigned long long> ctab;
+  std::map<unsigned long long, int> cidx;
+  if (is_double) {
+    for (int u = 0; u < rowptr[M]; ++u) {
+      unsigned long long bits; const double v = val[u];
+      memcpy(&bits, &v, 8);
+      if (cidx.find(bits) == cidx.end()) { cidx[bits] = (int)ctab.size(); ctab.push_back(bits); }
+    }
+  }
+  const char* cenv = getenv("LIBXSMM_B200_FSSPMDM_CONST");
+  const bool use_const = is_double && ctab.size() > 31 && ctab.size() <= 4096 && ((cenv && *cenv) ? ('1' == *cenv) : (il >= 2));     // by default only with the explicit form (alone it is slower)
+  if (use_const) {
+    append(s, ".const .align 8 .b64 fsv[%d] = {", (int)ctab.size());
+    for (size_t i = 0; i < ctab.size(); ++i) append(s, "%s0x%016llX", i ? ", " : "", ctab[i]);
+    s += "};\n\n";
+  }
   if (batched) s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC, .param .u64 pJ, .param .u64 pSB, .param .u64 pSC, .param .u64 pIPE, .param .u64 pIB, .param .u64 pIC)\n";
   else s += ".visible .entry fs_baked(.param .u64 pB, .param .u64 pC, .param .u64 pN, .param .u64 pLDB, .param .u64 pLDC)\n";
   append(s, ".maxntid %d, 1, 1\n", kBlock);
+  if (minctas >= 2) append(s, ".minnctapersm %d\n", minctas);
   s += "{\n";
   s += "  .reg .pred %p, %pf;\n  .reg .b32 %r<4>;\n  .reg .b64 %rd<28>;\n";
-  append(s, "  .reg .%s %%bx<%d>, %%by<%d>, %%cx<%d>, %%cy<%d>, %%ax, %%ay;\n", ty, K, K, M, M);
+  append(s, "  .reg .%s %%bx<%d>, %%by<%d>, %%cx<%d>, %%cy<%d>, %%ax, %%ay, %%ai<8>, %%aj<8>, %%kv;\n", ty, K, K, M, M);
   s += "  ld.param.u64 %rd0, [pB];\n  ld.param.u64 %rd1, [pC];\n  ld.param.u64 %rd2, [pN];\n  ld.param.u64 %rd3, [pLDB];\n  ld.param.u64 %rd4, [pLDC];\n";
   s += "  mov.u32 %r0, %ctaid.x;\n  mov.u32 %r1, %tid.x;\n";
   append(s, "  mul.wide.u32 %%rd5, %%r0, %d;\n  cvt.u64.u32 %%rd6, %%r1;\n  add.s64 %%rd5, %%rd5, %%rd6;\n", kBlock);
@@ -213,8 +250,14 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
   append(s, "  mad.lo.s64 %%rd0, %%rd5, %d, %%rd0;\n  mad.lo.s64 %%rd1, %%rd5, %d, %%rd1;\n", esz, esz);   // b = B + n, c = C + n
   append(s, "  mul.lo.s64 %%rd3, %%rd3, %d;\n  mul.lo.s64 %%rd4, %%rd4, %d;\n", esz, esz);                 // row pitches in bytes
   s += "  and.b32 %r2, %r1, 15;\n  setp.eq.u32 %pf, %r2, 0;\n";                                          // one lane per 128-byte line issues prefetches
-  for (int k = 0; k < K; ++k) if (used[k]) {
-    append(s, "  mad.lo.s64 %%rd7, %%rd3, %d, %%rd0;\n", k);
+  if (il >= 2) s += "  mov.b64 %rd7, %rd0;\n";
+  for (int k = 0, kprev = 0; k < K; ++k) if (used[k]) {
+    if (il >= 2) {     // explicit form: running pointers everywhere (see the row loop)
+      if (k - kprev == 1) s += "  add.s64 %rd7, %rd7, %rd3;\n";
+      else if (k != kprev) append(s, "  mad.lo.s64 %%rd7, %%rd3, %d, %%rd7;\n", k - kprev);
+      kprev = k;
+    }
+    else append(s, "  mad.lo.s64 %%rd7, %%rd3, %d, %%rd0;\n", k);
     if (2 == cpt) append(s, "  ld.global.cs.v2.%s {%%bx%d, %%by%d}, [%%rd7];\n", ty, k, k);
     else append(s, "  ld.global.cs.%s %%bx%d, [%%rd7];\n", ty, k);
   }
@@ -228,9 +271,18 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
     append(s, "  mul.wide.u32 %%rd10, %%r3, %d;\n", fs_prefetch_b() * kBlock * cpt / 2);                                          // columns ahead
     s += "  add.s64 %rd11, %rd5, %rd10;\n  setp.lt.s64 %p, %rd11, %rd2;\n  and.pred %p, %p, %pf;\n";
     append(s, "  mad.lo.s64 %%rd10, %%rd10, %d, %%rd0;\n", esz);
+    if (il >= 2) {
+      for (int k = 0, kprev = 0; k < K; ++k) if (used[k]) {
+        if (k - kprev == 1) s += "  add.s64 %rd10, %rd10, %rd3;\n";
+        else if (k != kprev) append(s, "  mad.lo.s64 %%rd10, %%rd3, %d, %%rd10;\n", k - kprev);
+        kprev = k;
+        s += "  @%p prefetch.global.L2 [%rd10];\n";
+      }
+    }
+    else
     for (int k = 0; k < K; ++k) if (used[k]) append(s, "  mad.lo.s64 %%rd7, %%rd3, %d, %%rd10;\n  @%%p prefetch.global.L2 [%%rd7];\n", k);
   }
-  const int group = beta_one ? (is_double ? 8 : 16) : 1;
+  const int group = (il >= 2) ? (beta_one ? ((is_double ? 8 : 16) + il - 1) / il * il : il) : (beta_one ? (is_double ? 8 : 16) : 1);
   // beta = 1: the C rows that will be read are pulled into L2 two groups ahead by prefetch instructions (one lane
   // per 128-byte line, no registers held), so that the group's loads pay the L2 latency instead of the DRAM one
   const int ahead = fs_prefetch_groups();
@@ -240,14 +292,86 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
     }
   };
   if (beta_one && ahead > 0) for (int a = 0; a < ahead; ++a) prefetch_group(a * group);
+  int ld_row = 0, st_row = 0;        // explicit form: rows the running load / store pointers (%rd26 / %rd27) stand on
+  if (il >= 2) s += "  mov.b64 %rd26, %rd1;\n  mov.b64 %rd27, %rd1;\n";
   for (int m0 = 0; m0 < M; m0 += group) {
     if (beta_one) {
       if (ahead > 0) prefetch_group(m0 + ahead * group);
       for (int m = m0; m < M && m < m0 + group; ++m) if (rowptr[m + 1] != rowptr[m]) {
+        if (il >= 2) {       // running pointer (a product per row invites the assembler to compute all row addresses up front and spill them)
+          if (m - ld_row == 1) s += "  add.s64 %rd26, %rd26, %rd4;\n";
+          else append(s, "  mad.lo.s64 %%rd26, %%rd4, %d, %%rd26;\n", m - ld_row);
+          ld_row = m;
+          if (2 == cpt) append(s, "  ld.global.cs.v2.%s {%%cx%d, %%cy%d}, [%%rd26];\n", ty, m, m);
+          else append(s, "  ld.global.cs.%s %%cx%d, [%%rd26];\n", ty, m);
+          continue;
+        }
         append(s, "  mad.lo.s64 %%rd8, %%rd4, %d, %%rd1;\n", m);
         if (2 == cpt) append(s, "  ld.global.cs.v2.%s {%%cx%d, %%cy%d}, [%%rd8];\n", ty, m, m);
         else append(s, "  ld.global.cs.%s %%cx%d, [%%rd8];\n", ty, m);
       }
+    }
+    auto literal = [&](int u, char (&lit)[32]) {      // the operand text of value u (constant-bank form: after loading it)
+      if (use_const) {
+        unsigned long long bits; const double v = val[u];
+        memcpy(&bits, &v, 8);
+        append(s, "  ld.const.f64 %%kv, [fsv+%d];\n", 8 * cidx[bits]);
+        snprintf(lit, sizeof(lit), "%%kv");
+      }
+      else if (is_double) {
+        unsigned long long bits; const double v = val[u];
+        memcpy(&bits, &v, 8);
+        snprintf(lit, sizeof(lit), "0d%016llX", bits);
+      }
+      else {
+        unsigned int bits; const float v = (float)val[u];
+        memcpy(&bits, &v, 4);
+        snprintf(lit, sizeof(lit), "0f%08X", bits);
+      }
+    };
+    if (il >= 2) {
+      // explicit form: the non-empty rows of the group il at a time, step j of every chain before step j + 1 of any (each row's
+      // own order is unchanged: same bits), stores at the end, then a fence for the assembler's scheduler
+      const char* zero = is_double ? "0d0000000000000000" : "0f00000000";
+      std::vector<int> rows;
+      for (int m = m0; m < M && m < m0 + group; ++m) {
+        if (rowptr[m + 1] != rowptr[m]) rows.push_back(m);
+        else if (!skip_empty && !beta_one) {
+          append(s, "  mad.lo.s64 %%rd8, %%rd4, %d, %%rd1;\n  mov.%s %%ax, %s;\n", m, ty, zero);
+          if (2 == cpt) append(s, "  st.global.cs.v2.%s [%%rd8], {%%ax, %%ax};\n", ty);
+          else append(s, "  st.global.cs.%s [%%rd8], %%ax;\n", ty);
+        }
+      }
+      for (size_t r0 = 0; r0 < rows.size(); r0 += (size_t)il) {
+        const size_t r1 = (r0 + (size_t)il < rows.size()) ? r0 + (size_t)il : rows.size();
+        int maxlen = 0;
+        for (size_t r = r0; r < r1; ++r) {
+          const int m = rows[r], a = (int)(r - r0);
+          maxlen = (rowptr[m + 1] - rowptr[m] > maxlen) ? rowptr[m + 1] - rowptr[m] : maxlen;
+          if (beta_one) { append(s, "  mov.%s %%ai%d, %%cx%d;\n", ty, a, m); if (2 == cpt) append(s, "  mov.%s %%aj%d, %%cy%d;\n", ty, a, m); }
+          else { append(s, "  mov.%s %%ai%d, %s;\n", ty, a, zero); if (2 == cpt) append(s, "  mov.%s %%aj%d, %s;\n", ty, a, zero); }
+        }
+        for (int j = 0; j < maxlen; ++j) {
+          for (size_t r = r0; r < r1; ++r) {
+            const int m = rows[r], a = (int)(r - r0), u = rowptr[m] + j;
+            if (u >= rowptr[m + 1]) continue;
+            char lit[32];
+            literal(u, lit);
+            append(s, "  fma.rn.%s %%ai%d, %s, %%bx%d, %%ai%d;\n", ty, a, lit, col[u], a);
+            if (2 == cpt) append(s, "  fma.rn.%s %%aj%d, %s, %%by%d, %%aj%d;\n", ty, a, lit, col[u], a);
+          }
+        }
+        for (size_t r = r0; r < r1; ++r) {
+          const int m = rows[r], a = (int)(r - r0);
+          if (m - st_row == 1) s += "  add.s64 %rd27, %rd27, %rd4;\n";
+          else if (m != st_row) append(s, "  mad.lo.s64 %%rd27, %%rd4, %d, %%rd27;\n", m - st_row);
+          st_row = m;
+          if (2 == cpt) append(s, "  st.global.cs.v2.%s [%%rd27], {%%ai%d, %%aj%d};\n", ty, a, a);
+          else append(s, "  st.global.cs.%s [%%rd27], %%ai%d;\n", ty, a);
+        }
+        s += "  bar.warp.sync 0xffffffff;\n";
+      }
+      continue;
     }
     for (int m = m0; m < M && m < m0 + group; ++m) {
       const int lo = rowptr[m], hi = rowptr[m + 1];
@@ -270,16 +394,7 @@ std::string emit_ptx(int is_double, int vec2, int M, int K, int beta_one, int sk
       }
       for (int u = lo; u < hi; ++u) {
         char lit[32];
-        if (is_double) {
-          unsigned long long bits; const double v = val[u];
-          memcpy(&bits, &v, 8);
-          snprintf(lit, sizeof(lit), "0d%016llX", bits);
-        }
-        else {
-          unsigned int bits; const float v = (float)val[u];
-          memcpy(&bits, &v, 4);
-          snprintf(lit, sizeof(lit), "0f%08X", bits);
-        }
+        literal(u, lit);
         append(s, "  fma.rn.%s %%ax, %s, %%bx%d, %%ax;\n", ty, lit, col[u]);
         if (2 == cpt) append(s, "  fma.rn.%s %%ay, %s, %%by%d, %%ay;\n", ty, lit, col[u]);
       }
@@ -454,8 +569,18 @@ char* fs_jit_source(int is_double, int vec2, int M, int K, int beta_one, int ski
   return out;
 }
 
+// how many emitter variants are worth timing for this operator (1 = only the plain form): fp64 operators in the register form whose
+// fma count makes the FP64 pipe, not HBM, the likely bound
+int fs_jit_variants(int is_double, int vec2, int M, int K, const int* rowptr, const int* col)
+{
+  if (!is_double || !supported(is_double, vec2, M, K, rowptr, col)) return 1;
+  const char* e = getenv("LIBXSMM_B200_FSSPMDM_TUNE");      // 0: never time, always the plain form
+  if (e && '0' == *e) return 1;
+  return (rowptr[M] >= 16 * (M + K)) ? 3 : 1;
+}
+
 FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int skip_empty,
-                    const int* rowptr, const int* col, const double* val, int batched)
+                    const int* rowptr, const int* col, const double* val, int batched, int variant)
 {
   if (batched) vec2 = 0;
   const char* env = getenv("LIBXSMM_B200_FSSPMDM_JIT");
@@ -474,7 +599,7 @@ FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int ski
     cubin.push_back(0);
   }
   else if (!use_nvrtc) {
-    const std::string ptx = emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val, batched);
+    const std::string ptx = emit_ptx(is_double, vec2, M, K, beta_one, skip_empty, rowptr, col, val, batched, variant);
     cubin.assign(ptx.begin(), ptx.end());
     cubin.push_back(0);
   }

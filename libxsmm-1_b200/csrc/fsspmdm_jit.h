@@ -9,7 +9,9 @@ struct FsJit;
 // returns NULL when the operator is outside what the baked kernel supports (the caller then uses the
 // generic kernel) or when NVRTC is not available (reported through set_error).
 FsJit* fs_jit_build(int is_double, int vec2, int M, int K, int beta_one, int skip_empty_rows,
-                    const int* rowptr, const int* col, const double* val, int batched = 0);
+                    const int* rowptr, const int* col, const double* val, int batched = 0, int variant = 0);
+// number of emitter variants worth timing at create (1: only variant 0, the plain form)
+int fs_jit_variants(int is_double, int vec2, int M, int K, const int* rowptr, const int* col);
 // batched form: thread n -> item n / cols_per_item (element item / items_per_elem, item-in-element item % items_per_elem), column
 // n % cols_per_item; B / C of an item start at element * stride + item-in-element * item stride
 bool fs_jit_launch_batched(const FsJit* j, const void* dB, void* dC, long long n_elem, long long items_per_elem, long long cols_per_item, long long ldb, long long ldc,
