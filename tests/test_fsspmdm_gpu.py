@@ -156,6 +156,23 @@ def test_golden_pyfr_operators(gpu):
             same_bits(C, z[key])
 
 
+@pytest.mark.parametrize("il", ["0", "2", "8"])
+def test_emitter_forms_give_the_same_bits(gpu, monkeypatch, il):
+    """fma-heavy fp64 operators: every form of the baked kernel's emitter (plain; rows interleaved explicitly with the values
+    in constant memory and three CTAs per SM asked for) keeps each row's own fma order, so every form reproduces the compiled
+    reference's output bit for bit -- whichever one the timing at create would pick."""
+    monkeypatch.setenv("LIBXSMM_B200_FSSPMDM_TUNE", "0")          # no timing: exactly the form named below is baked
+    monkeypatch.setenv("LIBXSMM_B200_FSSPMDM_IL", il)
+    monkeypatch.setenv("LIBXSMM_B200_FSSPMDM_CONST", "0" if il == "0" else "1")
+    monkeypatch.setenv("LIBXSMM_B200_FSSPMDM_MINCTAS", "0" if il == "0" else "3")
+    z = np.load(os.path.join(GOLDEN, "pyfr_p4_tet_m6.npz"))
+    a, B, C0 = z["a"], z["B"], z["C0"]
+    for beta, key in ((0.0, "C_beta0"), (1.0, "C_beta1")):
+        C, sparse, baked = run_gpu(gpu, a, B, C0, beta)
+        assert baked and not sparse
+        same_bits(C, z[key])
+
+
 @pytest.mark.parametrize("dtype,logn", [(np.float64, 20), (np.float32, 22)])
 def test_full_size_properties(gpu, oracle, dtype, logn):
     """C3 (fp64, N = 2^20) and a 2^22-column slab of C5 (fp32): (1) a sample of columns equals the oracle
