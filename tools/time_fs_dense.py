@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import bench
 xs = importlib.import_module("libxsmm-1_b200")
-for tc in (("1",) if os.environ.get("LIBXSMM_B200_FSSPMDM_TC") == "1" else ("1", "0")):
+for tc in ((os.environ["LIBXSMM_B200_FSSPMDM_TC"],) if os.environ.get("LIBXSMM_B200_FSSPMDM_TC") in ("0", "1") else ("1", "0")):
     os.environ["LIBXSMM_B200_FSSPMDM_TC"] = tc
     for dens in ([float(x) for x in sys.argv[1:]] or [1.0, 0.5]):
         wl = dict(bench.WORKLOADS["c5"], density=dens, n_unique=None, N=1 << 22, beta=float(os.environ.get("FS_BETA", "0")))
