@@ -24,13 +24,17 @@
 namespace xb {
 
 constexpr int FT_BN = 128;                  // panel columns per tile (UMMA M)
-constexpr int FT_STAGES = 2;
+constexpr int FT_STAGES = 2;                // raw B tiles in flight; ONE b_lo buffer serves them in turn
 constexpr int FT_WORKERS = 4;               // warps that write b_lo for the next tile
 constexpr int FT_EPI = 16;                  // epilogue warps: four per TMEM lane quarter, taking the 32-row chunks of the operator in turn
 constexpr int FT_THREADS = (2 + FT_WORKERS + FT_EPI) * 32;
-constexpr int FT_STAGE_HALF = 64 * FT_BN * 4;          // 32 KiB: 64 k x 128 columns fp32 (raw); the lo copy follows
-constexpr int FT_SMEM_B = 0;                           // stages: raw | lo
-constexpr int FT_SMEM_OP = FT_STAGES * 2 * FT_STAGE_HALF;   // operator: chunk 0 hi, chunk 1 hi, chunk 0 lo, chunk 1 lo (M_pad x 128 B each)
+constexpr int FT_STAGE_HALF = 64 * FT_BN * 4;          // 32 KiB: 64 k x 128 columns fp32
+constexpr int FT_SMEM_B = 0;                           // FT_STAGES raw tiles
+constexpr int FT_SMEM_LO = FT_STAGES * FT_STAGE_HALF;  // b_lo of the tile the tensor core works on (next)
+constexpr int FT_CBOX_ROWS = 32;                       // rows of C per TMA store box
+constexpr int FT_CBOX = FT_CBOX_ROWS * FT_BN * 4;      // 16 KiB: [32 rows][128 columns] fp32, plain row-major
+constexpr int FT_SMEM_CBOX = FT_SMEM_LO + FT_STAGE_HALF;        // two staging boxes for C (EPI = 2)
+constexpr int FT_SMEM_OP = FT_SMEM_CBOX + 2 * FT_CBOX; // operator: chunk 0 hi, chunk 1 hi, chunk 0 lo, chunk 1 lo (M_pad x 128 B each)
 
 struct FsTcArgs {
   const float* B; float* C;
@@ -44,18 +48,24 @@ struct FsTcArgs {
 
 template <int EPI>
 __global__ void __launch_bounds__(FT_THREADS, 1)
-fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
+fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const FsTcArgs p)
 {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int plane = p.M_pad * 128;
   unsigned char* sop = smem + FT_SMEM_OP;
   uint64_t* bar = (uint64_t*)(sop + 4 * plane);
-  uint64_t* b_full = bar;            // [2] TMA landed
-  uint64_t* b_split = bar + 2;       // [2] workers wrote b_lo
-  uint64_t* b_free = bar + 4;        // [2] MMAs that read the stage have completed
-  uint64_t* acc_full = bar + 6;      // [2] tile's MMAs completed
-  uint64_t* acc_free = bar + 8;      // [2] epilogue drained the accumulator
-  uint32_t* tmem_slot = (uint32_t*)(bar + 10);
+  // Shared memory holds the operator (80 KiB for 150 rows) and 128 KiB of B.  Two stages of {raw, lo} left 64 KiB of loads in
+  // flight per SM and no room for anything else.  Two raw stages and ONE b_lo buffer instead (b_lo of tile t + 1 is written once the
+  // MMAs of tile t have completed: the tensor core idles for that half microsecond of the 2.5 us a tile may take), which frees 32 KiB
+  // for two staging boxes of C (EPI = 2): the epilogue's 600 line stores per tile, waiting in the load / store unit for DRAM, held up
+  // the shared-memory instructions of the b_lo warps behind them, so that stores and loads + MMAs ran one after the other.
+  uint64_t* b_full = bar;            // [<= 3] TMA landed
+  uint64_t* b_free = bar + 3;        // [<= 3] MMAs that read the stage have completed
+  uint64_t* b_split = bar + 6;       // [1] workers wrote b_lo of the next tile
+  uint64_t* lo_free = bar + 7;       // [1] MMAs that read b_lo have completed
+  uint64_t* acc_full = bar + 8;      // [2] tile's MMAs completed
+  uint64_t* acc_free = bar + 10;     // [2] epilogue drained the accumulator
+  uint32_t* tmem_slot = (uint32_t*)(bar + 12);
 
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ntiles = (p.ncols + FT_BN - 1) / FT_BN;
@@ -65,10 +75,10 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
 
   if (0 == tid) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 1); mbar_init(&b_split[i], FT_WORKERS); mbar_init(&b_free[i], 1);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], FT_EPI);
-    }
+    for (int i = 0; i < FT_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_free[i], 1); }
+    mbar_init(b_split, FT_WORKERS); mbar_init(lo_free, 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], FT_EPI); }
     mbar_fence_init();
   }
   if (1 == warp) {
@@ -87,20 +97,20 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
     if (0 == lane) tma_prefetch_desc(&tmB);
     long long it = 0;
     for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
-      const int s = (int)(it & 1);
+      const int s = (int)(it % FT_STAGES);
       if (0 == lane) {
-        if (it >= 2) mbar_wait(&b_free[s], (uint32_t)(((it >> 1) - 1) & 1));
+        if (it >= FT_STAGES) mbar_wait(&b_free[s], (uint32_t)(((it / FT_STAGES) - 1) & 1));
         if (p.debug & 8) mbar_arrive(&b_full[s]);
         else {
           mbar_arrive_expect_tx(&b_full[s], FT_STAGE_HALF);
-          unsigned char* dst = smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF;
+          unsigned char* dst = smem + FT_SMEM_B + s * FT_STAGE_HALF;
 #pragma unroll
           for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * (64 * 128), &tmB, (int)(t * FT_BN) + 32 * j, 0, &b_full[s]);
         }
       }
       if (p.debug & 8) continue;
-      // A tile this CTA will need after the two in flight: into L2 now.  The ring is only two stages deep (64 KiB in flight per
-      // SM), and with C's stores filling the DRAM queues a tile fetched from DRAM takes several microseconds to arrive.
+      // A tile this CTA will need after the ones in flight: into L2 now (with C's stores filling the DRAM queues a tile fetched
+      // from DRAM takes several microseconds to arrive).
       const long long tn = tile_of(it + p.pf_dist);
       if (tn < ntiles) {
         if (0 == p.pf_mode) {          // through the TMA unit (measured: these requests queue in front of the next tile's loads)
@@ -125,11 +135,11 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(p.M_pad >> 3) << 17) | ((uint32_t)(FT_BN >> 4) << 24);
       long long it = 0;
       for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
-        const int s = (int)(it & 1), ab = (int)(it & 1);
+        const int s = (int)(it % FT_STAGES), ab = (int)(it & 1);
         if (it >= 2) mbar_wait(&acc_free[ab], (uint32_t)(((it >> 1) - 1) & 1));
-        mbar_wait(&b_split[s], (uint32_t)((it >> 1) & 1));
+        mbar_wait(b_split, (uint32_t)(it & 1));
         tc_fence_after();
-        const uint32_t x_hi = sbase + FT_SMEM_B + s * 2 * FT_STAGE_HALF, x_lo = x_hi + FT_STAGE_HALF;
+        const uint32_t x_hi = sbase + FT_SMEM_B + s * FT_STAGE_HALF, x_lo = sbase + FT_SMEM_LO;
         const uint32_t tacc = tmem_d + (uint32_t)(ab * 256);
         for (int ks = 0; ks < nks; ++ks) {
           // tile operand (MN-major, 128B/32B-atom swizzle): 8 k = 1024 B; 32-column blocks 64*128 B apart, 4-k groups 512 B
@@ -145,6 +155,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
           tc_mma_tf32(tacc, dxh, dol, idesc, 1u);
         }
         tc_commit(&b_free[s]);
+        tc_commit(lo_free);
         tc_commit(&acc_full[ab]);
       }
     }
@@ -154,10 +165,11 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
     const int wt = tid - 64;                      // 0..127
     long long it = 0;
     for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
-      const int s = (int)(it & 1);
-      mbar_wait(&b_full[s], (uint32_t)((it >> 1) & 1));
-      const uint4* src = (const uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF);
-      uint4* dst = (uint4*)(smem + FT_SMEM_B + s * 2 * FT_STAGE_HALF + FT_STAGE_HALF);
+      const int s = (int)(it % FT_STAGES);
+      mbar_wait(&b_full[s], (uint32_t)((it / FT_STAGES) & 1));
+      if (it >= 1) mbar_wait(lo_free, (uint32_t)((it - 1) & 1));       // the MMAs of the tile before have read b_lo
+      const uint4* src = (const uint4*)(smem + FT_SMEM_B + s * FT_STAGE_HALF);
+      uint4* dst = (uint4*)(smem + FT_SMEM_LO);
 #pragma unroll 4
       for (int i = wt; i < FT_STAGE_HALF / 16; i += FT_WORKERS * 32) {
         if (p.debug & 1) break;
@@ -171,7 +183,7 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
       }
       fence_proxy_async();
       __syncwarp();
-      if (0 == lane) mbar_arrive(&b_split[s]);
+      if (0 == lane) mbar_arrive(b_split);
     }
   }
   else {
@@ -181,7 +193,52 @@ fsspmdm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const FsTcArgs p)
     // lane quarter, taking the 32-row chunks in turn.
     const int quarter = warp & 3, part = (warp - 2 - FT_WORKERS) >> 2;
     long long it = 0;
-    if (0 == EPI) {
+    if (2 == EPI) {
+      // C through the store engine: the sixteen warps put 32 rows x 128 columns of the tile into a staging box (thread = column,
+      // eight rows per warp: conflict-free 4-byte stores), one thread hands the box to TMA (beta = 1: as a reduction, C is never
+      // read by the SM) and the next 32 rows go to the other box.  Nothing of the epilogue waits in the load / store unit for DRAM.
+      const int ew = warp - 2 - FT_WORKERS;                 // 0..15
+      const bool issuer = (0 == ew) && (0 == lane);
+      const int nbox = (p.M + FT_CBOX_ROWS - 1) / FT_CBOX_ROWS;
+      const uint32_t tq = tmem_d + ((uint32_t)(quarter * 32) << 16);
+      uint32_t nb = 0;                                      // boxes issued so far (parity picks the staging box)
+      for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
+        const int ab = (int)(it & 1);
+        mbar_wait(&acc_full[ab], (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        for (int b = 0; b < nbox; ++b, ++nb) {
+          unsigned char* box = smem + FT_SMEM_CBOX + (nb & 1u) * FT_CBOX;
+          uint32_t v[8];
+          tc_ld8_nowait(tq + (uint32_t)(ab * 256 + FT_CBOX_ROWS * b + 8 * part), v);
+          tc_wait_ld();
+          tc_pin8(v);
+          if (b == nbox - 1) {                              // the accumulator is in registers: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (0 == lane) mbar_arrive(&acc_free[ab]);
+          }
+          // the box is free once the store engine has read its previous content out (the issuing thread waited for that after
+          // handing over the box before this one)
+          asm volatile("bar.sync 1, %0;\n" ::"n"(FT_EPI * 32) : "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *(uint32_t*)(box + ((8 * part + j) * FT_BN + quarter * 32 + lane) * 4) = v[j];
+          fence_proxy_async();
+          asm volatile("bar.sync 2, %0;\n" ::"n"(FT_EPI * 32) : "memory");
+          if (issuer && !(p.debug & 2)) {
+            if (p.beta_one)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];\n"
+                           ::"l"(&tmC), "r"((int)(t * FT_BN)), "r"(FT_CBOX_ROWS * b), "r"(smem_u32(box)) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
+                           ::"l"(&tmC), "r"((int)(t * FT_BN)), "r"(FT_CBOX_ROWS * b), "r"(smem_u32(box)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");      // the OTHER box (the next one to be filled) has been read out
+          }
+        }
+      }
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    }
+    else if (0 == EPI) {
       for (long long t = tile_of(0); t < ntiles; t = tile_of(++it)) {
         const int ab = (int)(it & 1);
         mbar_wait(&acc_full[ab], (uint32_t)((it >> 1) & 1));
@@ -291,6 +348,9 @@ bool make_tensor_map_2d_sw128(CUtensorMap* map, const void* base, int elem_bytes
 // ---- host side ---------------------------------------------------------------------------------------------
 struct FsTc { unsigned char* d_op; int M, M_pad, K, beta_one; size_t smem; int sms; int epi, pf_mode, pf_dist, debug; };
 
+bool make_tensor_map_2d(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
+                        unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows);
+
 static int fs_tc_mpad(int M) { return (M + 15) / 16 * 16; }
 
 // can this operator use the tensor-core kernel at all?
@@ -322,8 +382,9 @@ FsTc* fs_tc_build(int M, int K, int lda, int beta_one, const float* a_dense)
   if (cudaSuccess == cudaGetDevice(&dev) && cudaSuccess == cudaGetDeviceProperties(&prop, dev)) t->sms = prop.multiProcessorCount;
   ensure_smem_optin((const void*)fsspmdm_tc_kernel<0>, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256));
   ensure_smem_optin((const void*)fsspmdm_tc_kernel<1>, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256));
+  ensure_smem_optin((const void*)fsspmdm_tc_kernel<2>, (int)((size_t)FT_SMEM_OP + (size_t)4 * 192 * 128 + 256));
   const char* e = getenv("LIBXSMM_B200_K4F_EPI");        // 0: the round-1 epilogue (32-row chunks, per-row address arithmetic)
-  t->epi = (e && '0' == *e) ? 0 : 1;
+  t->epi = (e && *e >= '0' && *e <= '2') ? (*e - '0') : 2;       // 2: C through TMA store boxes; 1: per-thread stores, 8-row chunks; 0: the round-1 epilogue
   e = getenv("LIBXSMM_B200_K4F_PF");
   t->pf_dist = (e && atoi(e) >= 2) ? atoi(e) : 4;
   e = getenv("LIBXSMM_B200_K4F_PFMODE");
@@ -344,8 +405,13 @@ bool fs_tc_launch(const FsTc* t, const void* dB, void* dC, long long ncols, long
   a.M = t->M; a.M_pad = t->M_pad; a.K = t->K; a.beta_one = t->beta_one; a.pf_dist = t->pf_dist; a.pf_mode = t->pf_mode; a.debug = t->debug;
   const long long ntiles = (ncols + FT_BN - 1) / FT_BN;
   const unsigned grid = (unsigned)(ntiles < t->sms ? ntiles : t->sms);
-  if (t->epi) fsspmdm_tc_kernel<1><<<grid, FT_THREADS, t->smem, stream>>>(map, a);
-  else fsspmdm_tc_kernel<0><<<grid, FT_THREADS, t->smem, stream>>>(map, a);
+  // C as a tensor of (ncols, M) for the store engine: rows past M and columns past ncols of a box are clipped by the hardware
+  CUtensorMap cmap = map;
+  int epi = t->epi;
+  if (2 == epi && !make_tensor_map_2d(&cmap, dC, 4, (unsigned long long)ncols, (unsigned long long)t->M, (unsigned long long)ldc * 4, FT_BN, FT_CBOX_ROWS)) { cmap = map; epi = 1; }   // unaligned C
+  if (2 == epi) fsspmdm_tc_kernel<2><<<grid, FT_THREADS, t->smem, stream>>>(map, cmap, a);
+  else if (1 == epi) fsspmdm_tc_kernel<1><<<grid, FT_THREADS, t->smem, stream>>>(map, cmap, a);
+  else fsspmdm_tc_kernel<0><<<grid, FT_THREADS, t->smem, stream>>>(map, cmap, a);
   XB_CUDA(cudaGetLastError());
   return true;
 }
