@@ -213,8 +213,8 @@ FsOperator* fs_create(int is_double, int M, int N, int K, int lda, int ldb, int 
   }
   // Dense float operators: once the FMA pipe, not HBM, bounds the baked kernel (more than ~4 nonzeros per byte
   // moved per column), the apply is a dense contraction and goes to the tensor cores (3xTF32, fsspmdm_tc.cu).
-  // Measured on B200, 150 x 64, N = 2^22: tensor cores 760-780 us at any density (round 1: 819; beta = 1: 1711 us, was 6388);
-  // baked 652 / 716 / 996 / 1367 / 1767 us at 30 / 35 / 40 / 45-50 / 60 % -> break-even ~36 %.
+  // Measured on B200, 150 x 64, N = 2^22: tensor cores 625 us at any density (round 1: 819; beta = 1: 1067 us, was 6388);
+  // baked 652 / 716 / 996 / 1367 / 1767 us at 30 / 35 / 40 / 45-50 / 60 % -> break-even ~30 % (beta = 0; the rule below keeps its margin).
   // LIBXSMM_B200_FSSPMDM_TC=1 forces that kernel for every eligible operator, =0 disables it.
   if (fs_tc_supported(is_double, M, K)) {
     const char* e = getenv("LIBXSMM_B200_FSSPMDM_TC");

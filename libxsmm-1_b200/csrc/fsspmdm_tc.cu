@@ -386,7 +386,7 @@ FsTc* fs_tc_build(int M, int K, int lda, int beta_one, const float* a_dense)
   const char* e = getenv("LIBXSMM_B200_K4F_EPI");        // 0: the round-1 epilogue (32-row chunks, per-row address arithmetic)
   t->epi = (e && *e >= '0' && *e <= '2') ? (*e - '0') : 2;       // 2: C through TMA store boxes; 1: per-thread stores, 8-row chunks; 0: the round-1 epilogue
   e = getenv("LIBXSMM_B200_K4F_PF");
-  t->pf_dist = (e && atoi(e) >= 2) ? atoi(e) : 4;
+  t->pf_dist = (e && atoi(e) >= 2) ? atoi(e) : 2;       // measured with the TMA-store epilogue: 2 / 3 / 4 / 6 tiles ahead 624 / 624 / 698 / 784 us (further ahead the lines are evicted by C's stream before they are used)
   e = getenv("LIBXSMM_B200_K4F_PFMODE");
   t->pf_mode = (e && '0' == *e) ? 0 : 1;
   e = getenv("LIBXSMM_B200_K4F_DEBUG");
