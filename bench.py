@@ -58,6 +58,12 @@ WORKLOADS = {
                    desc="spmdm fp32 2048^3 50%, transB (backprop)"),
     "c5": dict(kind="fsspmdm", M=150, K=64, density=0.30, n_unique=8, dtype="f32", N=1 << 24, beta=0.0,
                desc="sfsspmdm fp32 150x64 30% dense, N=2^24 columns, beta=0"),
+    # dense float operator: the branch where the reference itself applies the operator through its dense SMM kernel; here the
+    # tcgen05 kernel K4f (not a BASELINE.json config; reported because the north star names that branch)
+    "c5-dense": dict(kind="fsspmdm", M=150, K=64, density=1.0, n_unique=None, dtype="f32", N=1 << 22, beta=0.0,
+                     desc="sfsspmdm fp32 150x64 fully dense operator, N=2^22 columns, beta=0"),
+    "c5-dense-b1": dict(kind="fsspmdm", M=150, K=64, density=1.0, n_unique=None, dtype="f32", N=1 << 22, beta=1.0,
+                        desc="sfsspmdm fp32 150x64 fully dense operator, N=2^22 columns, beta=1"),
     "c3-b1": dict(kind="fsspmdm", M=150, K=64, density=0.30, n_unique=8, dtype="f64", N=1 << 20, beta=1.0,
                   desc="dfsspmdm fp64 150x64 30% dense (8 distinct values), N=2^20 columns, beta=1"),
     # real PyFR operators (reference samples/pyfr/mats/p4/hex/m0-sp.mtx, p4/tet/m6-sp.mtx; the matrices travel as the
@@ -555,7 +561,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--others", default="c1,c4,c4-tnt,c4-ntn,c3-b1,c3-hex,c3-tet,soa,soa-b", help="extra workloads reported inside the line (N=1 only); '' = none")
+    ap.add_argument("--others", default="c1,c4,c4-tnt,c4-ntn,c3-b1,c3-hex,c3-tet,c5-dense,c5-dense-b1,soa,soa-b", help="extra workloads reported inside the line (N=1 only); '' = none")
     ap.add_argument("--sharded", default="c3,c5", help="column-sharded fsspmdm configs reported in `column_sharded` at every N (strong scaling); '' = none")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of reference CPU time for the headline cpu_baseline (a quarter of it per secondary workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
