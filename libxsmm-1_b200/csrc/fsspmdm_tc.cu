@@ -10,10 +10,15 @@
 //   * "A" operand = the B tile as it lies in memory ([k][n], n contiguous -> MN-major TF32 operand, TMA boxes of
 //     32 columns with the 128B/32B-atom swizzle), "B" operand = the operator (K-major, SWIZZLE_128B), resident in
 //     shared memory for the whole persistent CTA.
-//   * 3xTF32: operator hi/lo split once at create time; b_lo = b - trunc(b) by the worker warps per tile.
-//   * accumulator [128 lanes = columns][M_pad TMEM columns], double buffered: the epilogue of tile t (tcgen05.ld:
-//     thread = panel column, registers = operator rows -> every store instruction writes one full 128-byte line
-//     of a C row) overlaps the MMAs of tile t+1.  22 warps: TMA, MMA, four for b_lo, sixteen for the epilogue.
+//   * 3xTF32: operator hi/lo split once at create time; b_lo = b - trunc(b) by four worker warps per tile, into ONE
+//     buffer that serves both raw B stages (written once the MMAs of the tile before have completed).
+//   * accumulator [128 lanes = columns][M_pad TMEM columns], double buffered: the epilogue of tile t overlaps the MMAs
+//     of tile t+1.  Epilogue (EPI = 2, default): tcgen05.ld (thread = panel column, registers = operator rows) ->
+//     shared-memory staging box of 32 rows x 128 columns -> TMA store (beta = 1: TMA reduce-add; C is never read by
+//     the SM).  Per-thread stores (EPI = 1, also what an unaligned C gets; EPI = 0: the round-1 loop) left 600 line
+//     stores per tile waiting in the load / store unit for DRAM, in front of the b_lo warps' shared-memory
+//     instructions, so that stores and loads + MMAs ran one after the other (0.67-0.72 of HBM; now 0.88).
+//   * 22 warps: TMA (+ L2 prefetch instructions two tiles ahead), MMA, four for b_lo, sixteen for the epilogue.
 // Not the reference's rounding sequence; contract 1e-5 relative (observed ~2e-6; at most 24 accumulations).
 #include "common.cuh"
 #include "tc_common.cuh"
